@@ -1,0 +1,113 @@
+/*
+ * multiviewnative.h -- C ABI of libmultiviewnative, B200-native build.
+ *
+ * Drop-in boundary.  Every declaration below is binary compatible with the
+ * reference header (psteinb/libmultiviewnative, inc/multiviewnative.h): same
+ * symbol names, same argument lists, same POD layouts, so Fiji/SPIM_Registration
+ * (JNA), the reference's own tests and its bench programs link against this
+ * library unchanged.  Citations "ref:" are file:line in the reference checkout.
+ *
+ * Conventions (ref: inc/cpu_convolve.h:44-52, inc/image_stack_utils.h:141-155):
+ *   - stacks are float32, row major, dims arrays are int[3] = {z, y, x}, x fastest;
+ *   - every pointer is caller-owned HOST memory unless stated otherwise;
+ *   - psi is the only output and is updated in place;
+ *   - convolutions are CIRCULAR at the image extents with the kernel centre
+ *     (index k/2 per axis) at the origin (ref: inc/padd_utils.h:11-40, 57-100).
+ *
+ * Error behaviour differs from the reference on purpose: no
+ * entry point calls exit() or throws across the ABI.  On failure a message goes
+ * to stderr, the output buffers are left untouched, and lmvn_last_error()
+ * (include/lmvn_b200.h) returns the text.
+ */
+#ifndef LMVN_B200_MULTIVIEWNATIVE_H
+#define LMVN_B200_MULTIVIEWNATIVE_H
+
+#ifdef __cplusplus
+#include <cstddef>
+#else
+#include <stddef.h>
+#endif
+
+typedef float imageType; /* ref: inc/multiviewnative.h:4 */
+
+#if defined(_WIN32)
+#define LMVN_EXPORT __declspec(dllexport)
+#else
+#define LMVN_EXPORT __attribute__((visibility("default")))
+#endif
+#ifdef __cplusplus
+#define FUNCTION_PREFIX extern "C" LMVN_EXPORT
+#else
+#define FUNCTION_PREFIX LMVN_EXPORT
+#endif
+
+/* One view of the acquisition.  64 bytes on LP64.  ref: inc/multiviewnative.h:15-26 */
+struct view_data {
+  imageType* image_;   /* observed view, dims image_dims_                         */
+  imageType* kernel1_; /* PSF of this view                                         */
+  imageType* kernel2_; /* compound (flipped / virtual-view) PSF                    */
+  imageType* weights_; /* per-voxel blending weights, same dims as image_          */
+  int* image_dims_;    /* {z, y, x}                                                */
+  int* kernel1_dims_;  /* {z, y, x}, each <= image dims, may be even / anisotropic */
+  int* kernel2_dims_;
+  int* weights_dims_;  /* never read (ref: no use in src/ or inc/); may be NULL    */
+};
+
+/* Argument bundle, passed BY VALUE.  32 bytes: ptr@0, u16@8, f64@16, f32@24,
+ * i32@28.  ref: inc/multiviewnative.h:28-35 */
+struct workspace {
+  struct view_data* data_;
+  unsigned short num_views_;
+  double lambda_;      /* > 0 selects the Tikhonov-regularised update (ref: src/multiviewnative.cpp:216) */
+  float minValue_;     /* floor of the multiplicative update                        */
+  int num_iterations_; /* one iteration = one sweep over all views                  */
+};
+
+#ifndef __cplusplus
+typedef struct view_data view_data;
+typedef struct workspace workspace;
+#endif
+
+/* ---- CPU entry points (link compatibility; not the accelerated path) ---------
+ * ref: inc/multiviewnative.h:43-51, src/multiviewnative.cpp:244-293           */
+FUNCTION_PREFIX void inplace_cpu_convolution(imageType* im, int* imDim, imageType* kernel,
+                                             int* kernelDim, int nthreads);
+FUNCTION_PREFIX void inplace_cpu_deconvolve(imageType* psi, workspace input, int nthreads);
+
+/* ---- GPU entry points: the hot path -------------------------------------------
+ * ref: inc/multiviewnative.h:59-67, src/multiviewnative.cu:58-75, 89-142.
+ * device < 0 selects the device with the highest compute capability.          */
+FUNCTION_PREFIX void inplace_gpu_convolution(imageType* im, int* imDim, imageType* kernel,
+                                             int* kernelDim, int device);
+FUNCTION_PREFIX void inplace_gpu_deconvolve(imageType* psi, workspace input, int device);
+
+/* ---- legacy single-step API kept for older Fiji bindings ------------------------
+ * ref: inc/multiviewnative.h:77-102, src/multiviewnative.cu:199-595           */
+FUNCTION_PREFIX void convolution3DfftCUDAInPlace(imageType* im, int* imDim, imageType* kernel,
+                                                 int* kernelDim, int devCUDA);
+/* DEVICE pointers: _d_imCUDA holds z*y rows of 2*(x/2+1) floats (in-place r2c
+ * pitch), _d_kernelCUDA the unpadded kernel. */
+FUNCTION_PREFIX void convolution3DfftCUDAInPlace_core(imageType* _d_imCUDA, int* imDim,
+                                                      imageType* _d_kernelCUDA, int* kernelDim,
+                                                      int devCUDA);
+FUNCTION_PREFIX void compute_quotient(imageType* _input, imageType* _output, size_t _size,
+                                      int _device);
+FUNCTION_PREFIX void compute_final_values(imageType* _image, imageType* _integral,
+                                          imageType* _weight, size_t _size, float _minValue,
+                                          double _lambda, int _device);
+FUNCTION_PREFIX void iterate_fft_plain(imageType* _input, imageType* _kernel, imageType* _output,
+                                       int* _input_dims, int* _kernel_dims, int _device);
+FUNCTION_PREFIX void iterate_fft_tikhonov(imageType* _input, imageType* _kernel,
+                                          imageType* _output, int* _input_dims, int* _kernel_dims,
+                                          size_t _size, float _minValue, double _lambda,
+                                          int _device);
+
+/* ---- device queries.  ref: inc/multiviewnative.h:104-109, inc/cuda_helpers.cuh:70-136 */
+FUNCTION_PREFIX int selectDeviceWithHighestComputeCapability();
+FUNCTION_PREFIX int getCUDAcomputeCapabilityMinorVersion(int devCUDA);
+FUNCTION_PREFIX int getCUDAcomputeCapabilityMajorVersion(int devCUDA);
+FUNCTION_PREFIX int getNumDevicesCUDA();
+FUNCTION_PREFIX void getNameDeviceCUDA(int devCUDA, char* name); /* writes 256 bytes */
+FUNCTION_PREFIX long long int getMemDeviceCUDA(int devCUDA);     /* total bytes     */
+
+#endif /* LMVN_B200_MULTIVIEWNATIVE_H */

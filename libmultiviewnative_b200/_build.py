@@ -1,0 +1,106 @@
+"""In-tree builds.
+
+* ``build_cuda()``  -> libmultiviewnative_b200/lib/libmultiviewnative.so, nvcc, sm_100a
+  only.  This is the product: the C-ABI drop-in for the reference's
+  libmultiviewnative.so.
+* ``build_emu()``   -> tests/emu/_lmvn_emu.so, g++ with -DLMVN_EMU against
+  tests/emu/cuda_emu.h.  Test infrastructure only (kernel index math without a
+  GPU); never loaded by the package.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB_DIR = os.path.join(PKG, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libmultiviewnative.so")
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+EMU_PATH = os.path.join(EMU_DIR, "_lmvn_emu.so")
+
+CUDA_SOURCES = ["api.cu", "engine.cu"]
+HOST_SOURCES = ["cpu_path.cpp"]
+NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _sources():
+    out = []
+    for d, _, files in os.walk(CSRC):
+        out += [os.path.join(d, f) for f in files if f.endswith((".cu", ".cuh", ".cpp", ".h"))]
+    out += [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))]
+    return out
+
+
+def _stale(target: str, extra=()) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in list(_sources()) + list(extra))
+
+
+def build_cuda(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale(LIB_PATH):
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [_nvcc(), *NVCC_ARCH, "-lineinfo", "-O3", "-std=c++17", "-shared",
+           "-Xcompiler", "-fPIC,-fopenmp,-fvisibility=hidden,-Wall,-Wno-unknown-pragmas",
+           "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    fused = os.path.join(CSRC, "fft_fused.cu")
+    srcs = list(CUDA_SOURCES)
+    if os.path.exists(fused):
+        srcs.append("fft_fused.cu")
+        cmd += ["-DLMVN_HAVE_FUSED"]
+    cmd += [os.path.join(CSRC, s) for s in srcs + HOST_SOURCES]
+    cmd += ["-o", LIB_PATH, "-lgomp"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc build of libmultiviewnative.so failed")
+    if verbose:
+        sys.stderr.write(res.stdout + res.stderr)
+    return LIB_PATH
+
+
+def build_emu(force: bool = False) -> str:
+    emu_srcs = [os.path.join(EMU_DIR, "cuda_emu.cpp"), os.path.join(EMU_DIR, "cuda_emu.h")]
+    if not force and not _stale(EMU_PATH, emu_srcs):
+        return EMU_PATH
+    cxx = shutil.which("g++") or "g++"
+    cmd = [cxx, "-O2", "-g", "-std=c++17", "-shared", "-fPIC", "-fopenmp", "-DLMVN_EMU",
+           "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function",
+           "-I", EMU_DIR, "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    fused = os.path.join(CSRC, "fft_fused.cu")
+    srcs = list(CUDA_SOURCES)
+    if os.path.exists(fused):
+        srcs.append("fft_fused.cu")
+        cmd += ["-DLMVN_HAVE_FUSED"]
+    for s in srcs:
+        cmd += ["-x", "c++", os.path.join(CSRC, s)]
+    cmd += ["-x", "c++", os.path.join(CSRC, "cpu_path.cpp"), os.path.join(EMU_DIR, "cuda_emu.cpp")]
+    cmd += ["-o", EMU_PATH]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ build of the emulated test library failed")
+    return EMU_PATH
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "cuda"
+    if which in ("cuda", "all"):
+        print(build_cuda(force=True, verbose="-v" in sys.argv))
+    if which in ("emu", "all"):
+        print(build_emu(force=True))

@@ -1,0 +1,660 @@
+// engine.cu -- plan store, generic convolution engine and the resident
+// deconvolution handle (see engine.cuh).
+#include "engine.cuh"
+#include "fft_generic.cuh"
+
+#include <cmath>
+#include <cstdlib>
+
+namespace lmvn {
+
+// ------------------------------------------------------------------------------
+// error / trace plumbing
+// ------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+void set_last_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  // the reference prints and exits (ref: inc/cuda_helpers.cuh:17-24); we print and return
+  fprintf(stderr, "[libmultiviewnative] error: %s\n", buf);
+}
+const char* last_error() { return g_last_error.c_str(); }
+void clear_last_error() { g_last_error.clear(); }
+
+bool trace_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("LMVN_TRACE");
+    on = (e && *e && *e != '0') ? 1 : 0;
+  }
+  return on == 1;
+}
+void trace(const char* fmt, ...) {
+  if (!trace_enabled()) return;
+  va_list ap;
+  va_start(ap, fmt);
+  fprintf(stderr, "[lmvn trace] ");
+  vfprintf(stderr, fmt, ap);
+  fprintf(stderr, "\n");
+  va_end(ap);
+}
+
+static int g_default_strategy = -1;
+int default_strategy() {
+  if (g_default_strategy < 0) {
+    const char* e = getenv("LMVN_STRATEGY");
+    g_default_strategy = 0;
+    if (e && !strcmp(e, "generic")) g_default_strategy = 1;
+    if (e && !strcmp(e, "fused")) g_default_strategy = 2;
+  }
+  return g_default_strategy;
+}
+void set_default_strategy(int s) { g_default_strategy = s; }
+
+// ------------------------------------------------------------------------------
+// device selection (ref: inc/cuda_helpers.cuh:116-136)
+// ------------------------------------------------------------------------------
+int resolve_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    set_last_error("no CUDA device available");
+    return -1;
+  }
+  if (device >= n) {
+    set_last_error("device %d out of range (have %d)", device, n);
+    return -1;
+  }
+  if (device >= 0) return device;
+  int best = 0, best_cc = -1;
+  for (int d = 0; d < n; ++d) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, d) != cudaSuccess) continue;
+    int cc = p.major * 10 + p.minor;
+    if (cc > best_cc) { best_cc = cc; best = d; }
+  }
+  return best;
+}
+
+// ------------------------------------------------------------------------------
+// plan store
+// ------------------------------------------------------------------------------
+static void factorize(int n, gen::AxisPlan& P) {
+  P.n = n;
+  P.nf = 0;
+  int m = n;
+  while (m % 4 == 0) { P.factors[P.nf++] = 4; m /= 4; }
+  while (m % 2 == 0) { P.factors[P.nf++] = 2; m /= 2; }
+  for (int p = 3; p * p <= m; p += 2)
+    while (m % p == 0) { P.factors[P.nf++] = p; m /= p; }
+  if (m > 1) P.factors[P.nf++] = m;
+}
+
+FftPlan::~FftPlan() {
+  for (int a = 0; a < 3; ++a)
+    if (d_tw[a]) cudaFree(d_tw[a]);
+}
+
+static const size_t kMaxSmem = 200 * 1024;
+
+static int build_axis(FftPlan& fp, int a, int n) {
+  factorize(n, fp.ax[a]);
+  std::vector<cplx> tw(n);
+  for (int k = 0; k < n; ++k) {
+    const double ang = -2.0 * M_PI * double(k) / double(n);
+    tw[k] = cmake(float(cos(ang)), float(sin(ang)));
+  }
+  LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&fp.d_tw[a]), sizeof(cplx) * n));
+  LMVN_CUDA_TRY(cudaMemcpy(fp.d_tw[a], tw.data(), sizeof(cplx) * n, cudaMemcpyHostToDevice));
+  fp.ax[a].tw = fp.d_tw[a];
+  int L = 2048 / n;
+  if (L < 1) L = 1;
+  if (L > 32) L = 32;
+  fp.lines[a] = L;
+  fp.smem[a] = size_t(2) * n * L * sizeof(cplx);
+  if (fp.smem[a] > kMaxSmem) {
+    set_last_error("axis length %d exceeds the shared-memory transform limit", n);
+    return -1;
+  }
+  return 0;
+}
+
+struct PlanKey {
+  int device, nz, ny, nx;
+  bool operator<(const PlanKey& o) const {
+    if (device != o.device) return device < o.device;
+    if (nz != o.nz) return nz < o.nz;
+    if (ny != o.ny) return ny < o.ny;
+    return nx < o.nx;
+  }
+};
+static std::mutex g_store_mutex;
+static std::map<PlanKey, std::shared_ptr<FftPlan>> g_store;
+static bool g_attr_done = false;
+
+std::shared_ptr<FftPlan> get_fft_plan(int device, int nz, int ny, int nx) {
+  std::lock_guard<std::mutex> lock(g_store_mutex);
+  PlanKey key{device, nz, ny, nx};
+  auto it = g_store.find(key);
+  if (it != g_store.end()) return it->second;
+  if (cudaSetDevice(device) != cudaSuccess) {
+    set_last_error("cudaSetDevice(%d) failed", device);
+    return nullptr;
+  }
+  auto fp = std::make_shared<FftPlan>();
+  fp->device = device;
+  fp->nz = nz; fp->ny = ny; fp->nx = nx; fp->nxc = nx / 2 + 1;
+  const int n[3] = {nz, ny, nx};
+  for (int a = 0; a < 3; ++a)
+    if (build_axis(*fp, a, n[a]) != 0) return nullptr;
+  if (!g_attr_done) {
+    cudaFuncSetAttribute(gen::k_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxSmem));
+    cudaFuncSetAttribute(gen::k_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxSmem));
+    cudaFuncSetAttribute(gen::k_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxSmem));
+    g_attr_done = true;
+  }
+  g_store[key] = fp;
+  trace("new fft plan dev=%d dims=%dx%dx%d", device, nz, ny, nx);
+  return fp;
+}
+
+// ------------------------------------------------------------------------------
+// generic engine: five separable passes per convolution
+// ------------------------------------------------------------------------------
+static const int kGenThreads = 256;
+
+struct GenericEngine : ConvEngine {
+  int strategy() const override { return 1; }
+  size_t khat_elems() const override { return plan->spec_elems(); }
+  size_t work_elems() const override { return plan->spec_elems(); }
+  int launches_per_conv() const override { return 5; }
+  unsigned long long S() const { return plan->voxels() * sizeof(float); }
+  unsigned long long C() const { return plan->spec_elems() * sizeof(cplx); }
+
+  int rows_fwd(const gen::RealSource& src, cplx* spec, cudaStream_t s) {
+    const FftPlan& p = *plan;
+    const size_t rows = size_t(p.nz) * p.ny;
+    dim3 grid(unsigned(ceil_div(rows, p.lines[2])));
+    LMVN_LAUNCH(gen::k_rows_fwd, grid, dim3(kGenThreads), p.smem[2], s, src, spec, p.nz, p.ny, p.nx,
+                p.ax[2], p.lines[2]);
+    LMVN_CUDA_TRY(cudaGetLastError());
+    mark("gen_rows_fwd", S() + C(), s);
+    return 0;
+  }
+  int cols(cplx* data, const cplx* khat, int axis, int mode, float scale, cudaStream_t s) {
+    const FftPlan& p = *plan;
+    long long ostride, jstride, inner;
+    unsigned outer;
+    if (axis == 1) {  // y
+      ostride = (long long)p.ny * p.nxc; jstride = p.nxc; inner = p.nxc; outer = unsigned(p.nz);
+    } else {          // z
+      ostride = 0; jstride = (long long)p.ny * p.nxc; inner = (long long)p.ny * p.nxc; outer = 1;
+    }
+    if (outer > 65535u) {
+      set_last_error("z extent %u too large for the generic y pass", outer);
+      return -1;
+    }
+    dim3 grid(unsigned(ceil_div(size_t(inner), p.lines[axis])), outer);
+    LMVN_LAUNCH(gen::k_cols, grid, dim3(kGenThreads), p.smem[axis], s, data, khat, ostride, jstride,
+                inner, p.ax[axis], p.lines[axis], mode, scale);
+    LMVN_CUDA_TRY(cudaGetLastError());
+    if (mode == gen::COLS_FWD_MUL_INV) mark("gen_cols_z_mul", 3 * C(), s);
+    else mark(axis == 1 ? (mode == gen::COLS_FWD ? "gen_cols_y_fwd" : "gen_cols_y_inv") : "gen_cols_z", 2 * C(), s);
+    return 0;
+  }
+  int rows_inv(const cplx* spec, float* out, const gen::Epilogue& ep, cudaStream_t s) {
+    const FftPlan& p = *plan;
+    const size_t rows = size_t(p.nz) * p.ny;
+    dim3 grid(unsigned(ceil_div(rows, p.lines[2])));
+    LMVN_LAUNCH(gen::k_rows_inv, grid, dim3(kGenThreads), p.smem[2], s, spec, out, p.nz, p.ny, p.nx,
+                p.ax[2], p.lines[2], ep);
+    LMVN_CUDA_TRY(cudaGetLastError());
+    mark(ep.mode == gen::EPI_UPDATE ? "gen_rows_inv_update" : (ep.mode == gen::EPI_QUOTIENT ? "gen_rows_inv_quotient" : "gen_rows_inv"),
+         C() + S() * (ep.mode == gen::EPI_UPDATE ? 3 : (ep.mode == gen::EPI_QUOTIENT ? 2 : 1)), s);
+    return 0;
+  }
+
+  int kernel_spectrum(const float* d_kernel, const int kd[3], cplx* khat, cplx*, cudaStream_t s) override {
+    gen::RealSource src{d_kernel, 1, kd[0], kd[1], kd[2]};
+    LMVN_TRY(rows_fwd(src, khat, s));
+    LMVN_TRY(cols(khat, nullptr, 1, gen::COLS_FWD, 1.f, s));
+    // 1/N folded into K^ (decision q10; the reference scales after the c2r,
+    // ref: inc/cpu_convolve.h:271-278)
+    const float inv_n = float(1.0 / double(plan->voxels()));
+    LMVN_TRY(cols(khat, nullptr, 0, gen::COLS_FWD, inv_n, s));
+    return 0;
+  }
+  int convolve(const float* in, cplx* work, const cplx* khat, const gen::Epilogue& ep, float* out,
+               cudaStream_t s) override {
+    gen::RealSource src{in, 0, 0, 0, 0};
+    LMVN_TRY(rows_fwd(src, work, s));
+    LMVN_TRY(cols(work, nullptr, 1, gen::COLS_FWD, 1.f, s));
+    LMVN_TRY(cols(work, khat, 0, gen::COLS_FWD_MUL_INV, 1.f, s));
+    LMVN_TRY(cols(work, nullptr, 1, gen::COLS_INV, 1.f, s));
+    LMVN_TRY(rows_inv(work, out, ep, s));
+    return 0;
+  }
+};
+
+std::unique_ptr<ConvEngine> make_generic_engine(std::shared_ptr<FftPlan> plan) {
+  std::unique_ptr<GenericEngine> e(new GenericEngine());
+  e->plan = plan;
+  return std::unique_ptr<ConvEngine>(e.release());
+}
+
+#ifndef LMVN_HAVE_FUSED
+std::unique_ptr<ConvEngine> make_fused_engine(std::shared_ptr<FftPlan>) { return nullptr; }
+#endif
+
+// ------------------------------------------------------------------------------
+// resident deconvolution handle
+// ------------------------------------------------------------------------------
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+Deconv::~Deconv() {
+  if (arena || stream) cudaSetDevice(device);
+  if (stream) cudaStreamSynchronize(stream);
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  if (stream) cudaStreamDestroy(stream);
+  if (arena) cudaFree(arena);
+}
+
+static const size_t kMaxKernelVoxels = size_t(1) << 24;
+
+int Deconv::init(const int* d, int nviews, int dev, int strategy) {
+  if (!d || d[0] <= 0 || d[1] <= 0 || d[2] <= 0) {
+    set_last_error("invalid image dims");
+    return -1;
+  }
+  if (nviews <= 0 || nviews > 65535) {
+    set_last_error("invalid number of views %d", nviews);
+    return -1;
+  }
+  device = resolve_device(dev);
+  if (device < 0) return -1;
+  LMVN_CUDA_TRY(cudaSetDevice(device));
+  dims[0] = d[0]; dims[1] = d[1]; dims[2] = d[2];
+  num_views = nviews;
+  auto fp = get_fft_plan(device, d[0], d[1], d[2]);
+  if (!fp) return -1;
+  if (strategy == 0) strategy = default_strategy();
+  if (strategy == 0 || strategy == 2) {
+    engine = make_fused_engine(fp);
+    if (!engine && strategy == 2) {
+      set_last_error("fused strategy not available for dims %dx%dx%d", d[0], d[1], d[2]);
+      return -1;
+    }
+  }
+  if (!engine) engine = make_generic_engine(fp);
+
+  const size_t S = align_up(fp->voxels() * sizeof(float), 256);
+  const size_t K = align_up(engine->khat_elems() * sizeof(cplx), 256);
+  const size_t W = align_up(engine->work_elems() * sizeof(cplx), 256);
+  kernel_stage_elems = std::min(kMaxKernelVoxels, fp->voxels());
+  const size_t KS = align_up(kernel_stage_elems * sizeof(float), 256);
+  arena_bytes = 2 * S + W + KS + size_t(nviews) * (2 * S + 2 * K);
+  size_t free_b = 0, total_b = 0;
+  LMVN_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+  if (arena_bytes > free_b) {
+    // ref: src/multiviewnative.cu:138-141 prints and returns with psi untouched
+    set_last_error("deconvolution of %dx%dx%d with %d views needs %.2f GiB of device memory, %.2f GiB free",
+                   d[0], d[1], d[2], nviews, arena_bytes / 1073741824.0, free_b / 1073741824.0);
+    return -1;
+  }
+  LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&arena), arena_bytes));
+  unsigned char* p = arena;
+  auto take = [&](size_t bytes) { unsigned char* r = p; p += bytes; return r; };
+  psi = reinterpret_cast<float*>(take(S));
+  integral = reinterpret_cast<float*>(take(S));
+  work = reinterpret_cast<cplx*>(take(W));
+  kernel_stage = reinterpret_cast<float*>(take(KS));
+  image.resize(nviews); weights.resize(nviews); khat1.resize(nviews); khat2.resize(nviews);
+  view_set.assign(nviews, 0);
+  for (int v = 0; v < nviews; ++v) {
+    image[v] = reinterpret_cast<float*>(take(S));
+    weights[v] = reinterpret_cast<float*>(take(S));
+    khat1[v] = reinterpret_cast<cplx*>(take(K));
+    khat2[v] = reinterpret_cast<cplx*>(take(K));
+  }
+  LMVN_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  LMVN_CUDA_TRY(cudaEventCreate(&ev0));
+  LMVN_CUDA_TRY(cudaEventCreate(&ev1));
+  trace("deconv handle dev=%d dims=%dx%dx%d views=%d strategy=%d arena=%.1f MiB", device, d[0], d[1],
+        d[2], nviews, engine->strategy(), arena_bytes / 1048576.0);
+  return 0;
+}
+
+static int check_kernel_dims(const int* kd, const int* dims, const char* what) {
+  if (!kd) {
+    set_last_error("%s dims missing", what);
+    return -1;
+  }
+  for (int a = 0; a < 3; ++a) {
+    if (kd[a] <= 0 || kd[a] > dims[a]) {
+      // undefined in the reference (wraps into a too-small target,
+      // ref: inc/padd_utils.h:19-38); rejected here, decision q11
+      set_last_error("%s extent %d along axis %d does not fit the image extent %d", what, kd[a], a, dims[a]);
+      return -1;
+    }
+  }
+  return 0;
+}
+
+int Deconv::set_view(int v, const float* image_h, const float* weights_h, const float* k1, const int* k1d,
+                     const float* k2, const int* k2d) {
+  if (v < 0 || v >= num_views) {
+    set_last_error("view index %d out of range", v);
+    return -1;
+  }
+  if (!image_h || !weights_h || !k1 || !k2) {
+    set_last_error("null buffer for view %d", v);
+    return -1;
+  }
+  LMVN_TRY(check_kernel_dims(k1d, dims, "kernel1"));
+  LMVN_TRY(check_kernel_dims(k2d, dims, "kernel2"));
+  LMVN_CUDA_TRY(cudaSetDevice(device));
+  const size_t S = engine->plan->voxels() * sizeof(float);
+  LMVN_CUDA_TRY(cudaMemcpyAsync(image[v], image_h, S, cudaMemcpyHostToDevice, stream));
+  LMVN_CUDA_TRY(cudaMemcpyAsync(weights[v], weights_h, S, cudaMemcpyHostToDevice, stream));
+  const float* ks[2] = {k1, k2};
+  const int* kds[2] = {k1d, k2d};
+  cplx* dst[2] = {khat1[v], khat2[v]};
+  for (int i = 0; i < 2; ++i) {
+    const size_t kn = size_t(kds[i][0]) * kds[i][1] * kds[i][2];
+    if (kn > kernel_stage_elems) {
+      set_last_error("kernel too large for the staging buffer");
+      return -1;
+    }
+    LMVN_CUDA_TRY(cudaMemcpyAsync(kernel_stage, ks[i], kn * sizeof(float), cudaMemcpyHostToDevice, stream));
+    LMVN_TRY(engine->kernel_spectrum(kernel_stage, kds[i], dst[i], work, stream));
+    // kernel_stage is reused by the next upload: pageable H2D copies are staged
+    // synchronously by the runtime, stream order keeps the device side safe
+  }
+  view_set[v] = 1;
+  return 0;
+}
+
+int Deconv::set_psi(const float* psi_h) {
+  if (!psi_h) {
+    set_last_error("psi is null");
+    return -1;
+  }
+  LMVN_CUDA_TRY(cudaSetDevice(device));
+  LMVN_CUDA_TRY(cudaMemcpyAsync(psi, psi_h, engine->plan->voxels() * sizeof(float), cudaMemcpyHostToDevice, stream));
+  psi_set = true;
+  return 0;
+}
+
+int Deconv::get_psi(float* psi_h) {
+  if (!psi_h) {
+    set_last_error("psi is null");
+    return -1;
+  }
+  LMVN_CUDA_TRY(cudaSetDevice(device));
+  LMVN_CUDA_TRY(cudaMemcpyAsync(psi_h, psi, engine->plan->voxels() * sizeof(float), cudaMemcpyDeviceToHost, stream));
+  LMVN_CUDA_TRY(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+int Deconv::synchronize() {
+  LMVN_CUDA_TRY(cudaSetDevice(device));
+  LMVN_CUDA_TRY(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+int Deconv::iterate(int iterations, double lambda, float min_value, float* device_ms) {
+  if (!psi_set) {
+    set_last_error("psi has not been set");
+    return -1;
+  }
+  for (int v = 0; v < num_views; ++v)
+    if (!view_set[v]) {
+      set_last_error("view %d has not been set", v);
+      return -1;
+    }
+  LMVN_CUDA_TRY(cudaSetDevice(device));
+  const UpdateParams up = make_update_params(lambda, min_value);
+  LMVN_CUDA_TRY(cudaEventRecord(ev0, stream));
+  for (int it = 0; it < iterations; ++it) {
+    for (int v = 0; v < num_views; ++v) {
+      // integral = view_v / (psi (*) kernel1_v)      ref: src/multiviewnative.cpp:195-205
+      gen::Epilogue e1{gen::EPI_QUOTIENT, 1.f, image[v], nullptr, nullptr, up};
+      LMVN_TRY(engine->convolve(psi, work, khat1[v], e1, integral, stream));
+      // psi = update(psi, integral (*) kernel2_v, weights_v)   ref: :209-227
+      gen::Epilogue e2{gen::EPI_UPDATE, 1.f, nullptr, psi, weights[v], up};
+      LMVN_TRY(engine->convolve(integral, work, khat2[v], e2, psi, stream));
+    }
+  }
+  LMVN_CUDA_TRY(cudaEventRecord(ev1, stream));
+  if (device_ms) {
+    LMVN_CUDA_TRY(cudaEventSynchronize(ev1));
+    LMVN_CUDA_TRY(cudaEventElapsedTime(device_ms, ev0, ev1));
+  }
+  return 0;
+}
+
+int Deconv::convolve_psi(int view, int which, int repeats, float* device_ms) {
+  if (view < 0 || view >= num_views || !view_set[view] || !psi_set) {
+    set_last_error("convolve: view %d / psi not set", view);
+    return -1;
+  }
+  LMVN_CUDA_TRY(cudaSetDevice(device));
+  const cplx* kh = (which == 2) ? khat2[view] : khat1[view];
+  const UpdateParams up = make_update_params(0.0, 0.f);
+  LMVN_CUDA_TRY(cudaEventRecord(ev0, stream));
+  for (int r = 0; r < repeats; ++r) {
+    gen::Epilogue e{gen::EPI_STORE, 1.f, nullptr, nullptr, nullptr, up};
+    LMVN_TRY(engine->convolve(psi, work, kh, e, integral, stream));
+    std::swap(psi, integral);
+  }
+  LMVN_CUDA_TRY(cudaEventRecord(ev1, stream));
+  if (device_ms) {
+    LMVN_CUDA_TRY(cudaEventSynchronize(ev1));
+    LMVN_CUDA_TRY(cudaEventElapsedTime(device_ms, ev0, ev1));
+  }
+  return 0;
+}
+
+
+int PassTimer::begin(cudaStream_t s) {
+  LMVN_CUDA_TRY(cudaEventCreate(&start));
+  LMVN_CUDA_TRY(cudaEventRecord(start, s));
+  return 0;
+}
+void PassTimer::mark(const char* name, unsigned long long alg_bytes, cudaStream_t s) {
+  Mark m{name, alg_bytes, nullptr};
+  if (cudaEventCreate(&m.ev) != cudaSuccess) return;
+  cudaEventRecord(m.ev, s);
+  marks.push_back(m);
+}
+PassTimer::~PassTimer() {
+  if (start) cudaEventDestroy(start);
+  for (auto& m : marks)
+    if (m.ev) cudaEventDestroy(m.ev);
+}
+
+int Deconv::profile(double lambda, float min_value, std::vector<std::string>& names, std::vector<float>& ms,
+                    std::vector<unsigned long long>& alg_bytes) {
+  if (!psi_set || !view_set[0]) {
+    set_last_error("profile: psi / view 0 not set");
+    return -1;
+  }
+  LMVN_CUDA_TRY(cudaSetDevice(device));
+  const size_t S = engine->plan->voxels() * sizeof(float);
+  // keep psi: the profiled step runs on a copy parked in `integral`'s place afterwards
+  std::vector<float> dummy;
+  float* saved = nullptr;
+  LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&saved), S));
+  LMVN_CUDA_TRY(cudaMemcpyAsync(saved, psi, S, cudaMemcpyDeviceToDevice, stream));
+  const UpdateParams up = make_update_params(lambda, min_value);
+  PassTimer t;
+  int rc = t.begin(stream);
+  engine->timer = &t;
+  if (rc == 0) {
+    gen::Epilogue e1{gen::EPI_QUOTIENT, 1.f, image[0], nullptr, nullptr, up};
+    rc = engine->convolve(psi, work, khat1[0], e1, integral, stream);
+  }
+  if (rc == 0) {
+    gen::Epilogue e2{gen::EPI_UPDATE, 1.f, nullptr, psi, weights[0], up};
+    rc = engine->convolve(integral, work, khat2[0], e2, psi, stream);
+  }
+  engine->timer = nullptr;
+  cudaMemcpyAsync(psi, saved, S, cudaMemcpyDeviceToDevice, stream);
+  cudaStreamSynchronize(stream);
+  cudaFree(saved);
+  if (rc != 0) return rc;
+  cudaEvent_t prev = t.start;
+  for (auto& m : t.marks) {
+    float v = 0.f;
+    LMVN_CUDA_TRY(cudaEventElapsedTime(&v, prev, m.ev));
+    names.push_back(m.name);
+    ms.push_back(v);
+    alg_bytes.push_back(m.alg_bytes);
+    prev = m.ev;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------
+// helpers behind the debug hooks and the legacy single-step entry points
+// ------------------------------------------------------------------------------
+// natural-layout transforms through the generic passes (tests)
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t n) { LMVN_CUDA_TRY(cudaMalloc(&p, n)); return 0; }
+};
+
+int debug_transform(const float* in, const int* dims, float* out, int device, bool inverse) {
+  if (!in || !dims || !out) { set_last_error("null argument"); return -1; }
+  int dev = resolve_device(device);
+  if (dev < 0) return -1;
+  LMVN_CUDA_TRY(cudaSetDevice(dev));
+  auto fp = get_fft_plan(dev, dims[0], dims[1], dims[2]);
+  if (!fp) return -1;
+  const size_t S = fp->voxels() * sizeof(float), C = fp->spec_elems() * sizeof(cplx);
+  DevBuf real, spec;
+  LMVN_TRY(real.alloc(S));
+  LMVN_TRY(spec.alloc(C));
+  const FftPlan& p = *fp;
+  const size_t rows = size_t(p.nz) * p.ny;
+  dim3 grid_rows(unsigned(ceil_div(rows, p.lines[2])));
+  dim3 grid_y(unsigned(ceil_div(size_t(p.nxc), p.lines[1])), unsigned(p.nz));
+  dim3 grid_z(unsigned(ceil_div(size_t(p.ny) * p.nxc, p.lines[0])), 1);
+  cplx* sp = static_cast<cplx*>(spec.p);
+  float* re = static_cast<float*>(real.p);
+  if (!inverse) {
+    LMVN_CUDA_TRY(cudaMemcpy(re, in, S, cudaMemcpyHostToDevice));
+    gen::RealSource src{re, 0, 0, 0, 0};
+    LMVN_LAUNCH(gen::k_rows_fwd, grid_rows, dim3(256), p.smem[2], 0, src, sp, p.nz, p.ny, p.nx, p.ax[2], p.lines[2]);
+    LMVN_LAUNCH(gen::k_cols, grid_y, dim3(256), p.smem[1], 0, sp, (const cplx*)nullptr, (long long)p.ny * p.nxc,
+                (long long)p.nxc, (long long)p.nxc, p.ax[1], p.lines[1], int(gen::COLS_FWD), 1.f);
+    LMVN_LAUNCH(gen::k_cols, grid_z, dim3(256), p.smem[0], 0, sp, (const cplx*)nullptr, 0ll,
+                (long long)p.ny * p.nxc, (long long)p.ny * p.nxc, p.ax[0], p.lines[0], int(gen::COLS_FWD), 1.f);
+    LMVN_CUDA_TRY(cudaGetLastError());
+    LMVN_CUDA_TRY(cudaMemcpy(out, sp, C, cudaMemcpyDeviceToHost));
+  } else {
+    LMVN_CUDA_TRY(cudaMemcpy(sp, in, C, cudaMemcpyHostToDevice));
+    LMVN_LAUNCH(gen::k_cols, grid_z, dim3(256), p.smem[0], 0, sp, (const cplx*)nullptr, 0ll,
+                (long long)p.ny * p.nxc, (long long)p.ny * p.nxc, p.ax[0], p.lines[0], int(gen::COLS_INV), 1.f);
+    LMVN_LAUNCH(gen::k_cols, grid_y, dim3(256), p.smem[1], 0, sp, (const cplx*)nullptr, (long long)p.ny * p.nxc,
+                (long long)p.nxc, (long long)p.nxc, p.ax[1], p.lines[1], int(gen::COLS_INV), 1.f);
+    gen::Epilogue ep{gen::EPI_STORE, 1.f, nullptr, nullptr, nullptr, make_update_params(0.0, 0.f)};
+    LMVN_LAUNCH(gen::k_rows_inv, grid_rows, dim3(256), p.smem[2], 0, (const cplx*)sp, re, p.nz, p.ny, p.nx,
+                p.ax[2], p.lines[2], ep);
+    LMVN_CUDA_TRY(cudaGetLastError());
+    LMVN_CUDA_TRY(cudaMemcpy(out, re, S, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+static __global__ void k_unpitch(const float* __restrict__ src, float* __restrict__ dst, size_t rows, int nx, int pitch,
+                          int to_pitched) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  const size_t n = rows * size_t(nx);
+  for (; i < n; i += stride) {
+    const size_t r = i / nx, x = i % nx;
+    if (to_pitched) dst[r * pitch + x] = src[i];
+    else dst[i] = src[r * pitch + x];
+  }
+}
+
+int legacy_core_impl(float* d_im, const int* imDim, const float* d_kernel, const int* kernelDim, int dev) {
+  if (!d_im || !imDim || !d_kernel || !kernelDim) { set_last_error("null argument"); return -1; }
+  int device = resolve_device(dev);
+  if (device < 0) return -1;
+  LMVN_CUDA_TRY(cudaSetDevice(device));
+  for (int a = 0; a < 3; ++a)
+    if (kernelDim[a] <= 0 || kernelDim[a] > imDim[a]) { set_last_error("kernel does not fit image"); return -1; }
+  auto fp = get_fft_plan(device, imDim[0], imDim[1], imDim[2]);
+  if (!fp) return -1;
+  std::unique_ptr<ConvEngine> eng = make_fused_engine(fp);
+  if (!eng) eng = make_generic_engine(fp);
+  const size_t rows = size_t(fp->nz) * fp->ny;
+  const int pitch = 2 * fp->nxc;
+  DevBuf real, khat, work;
+  LMVN_TRY(real.alloc(fp->voxels() * sizeof(float)));
+  LMVN_TRY(khat.alloc(eng->khat_elems() * sizeof(cplx)));
+  LMVN_TRY(work.alloc(eng->work_elems() * sizeof(cplx)));
+  float* re = static_cast<float*>(real.p);
+  const unsigned blocks = unsigned(std::min<size_t>(ceil_div(fp->voxels(), 256), 148 * 16));
+  LMVN_LAUNCH(k_unpitch, dim3(blocks), dim3(256), 0, 0, (const float*)d_im, re, rows, fp->nx, pitch, 0);
+  const int kd[3] = {kernelDim[0], kernelDim[1], kernelDim[2]};
+  LMVN_TRY(eng->kernel_spectrum(d_kernel, kd, static_cast<cplx*>(khat.p), static_cast<cplx*>(work.p), 0));
+  gen::Epilogue ep{gen::EPI_STORE, 1.f, nullptr, nullptr, nullptr, make_update_params(0.0, 0.f)};
+  // in == out is not allowed by the engines, go through the pitched buffer as scratch target
+  DevBuf out;
+  LMVN_TRY(out.alloc(fp->voxels() * sizeof(float)));
+  LMVN_TRY(eng->convolve(re, static_cast<cplx*>(work.p), static_cast<cplx*>(khat.p), ep, static_cast<float*>(out.p), 0));
+  LMVN_LAUNCH(k_unpitch, dim3(blocks), dim3(256), 0, 0, (const float*)out.p, d_im, rows, fp->nx, pitch, 1);
+  LMVN_CUDA_TRY(cudaGetLastError());
+  LMVN_CUDA_TRY(cudaDeviceSynchronize());
+  return 0;
+}
+
+int quotient_impl(const float* in, float* out, size_t n, int dev) {
+  if (!in || !out) { set_last_error("null argument"); return -1; }
+  int device = resolve_device(dev);
+  if (device < 0) return -1;
+  LMVN_CUDA_TRY(cudaSetDevice(device));
+  DevBuf a, b;
+  LMVN_TRY(a.alloc(n * sizeof(float)));
+  LMVN_TRY(b.alloc(n * sizeof(float)));
+  LMVN_CUDA_TRY(cudaMemcpy(a.p, in, n * sizeof(float), cudaMemcpyHostToDevice));
+  LMVN_CUDA_TRY(cudaMemcpy(b.p, out, n * sizeof(float), cudaMemcpyHostToDevice));
+  const unsigned blocks = unsigned(std::max<size_t>(1, std::min<size_t>(ceil_div(n, 1024), 148 * 8)));
+  LMVN_LAUNCH(k_divide, dim3(blocks), dim3(256), 0, 0, (const float*)a.p, (float*)b.p, n);
+  LMVN_CUDA_TRY(cudaGetLastError());
+  LMVN_CUDA_TRY(cudaMemcpy(out, b.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int final_values_impl(float* image, const float* integral, const float* weight, size_t n, float min_value,
+                      double lambda, int dev) {
+  if (!image || !integral || !weight) { set_last_error("null argument"); return -1; }
+  int device = resolve_device(dev);
+  if (device < 0) return -1;
+  LMVN_CUDA_TRY(cudaSetDevice(device));
+  DevBuf a, b, c;
+  LMVN_TRY(a.alloc(n * sizeof(float)));
+  LMVN_TRY(b.alloc(n * sizeof(float)));
+  LMVN_TRY(c.alloc(n * sizeof(float)));
+  LMVN_CUDA_TRY(cudaMemcpy(a.p, image, n * sizeof(float), cudaMemcpyHostToDevice));
+  LMVN_CUDA_TRY(cudaMemcpy(b.p, integral, n * sizeof(float), cudaMemcpyHostToDevice));
+  LMVN_CUDA_TRY(cudaMemcpy(c.p, weight, n * sizeof(float), cudaMemcpyHostToDevice));
+  const unsigned blocks = unsigned(std::max<size_t>(1, std::min<size_t>(ceil_div(n, 1024), 148 * 8)));
+  LMVN_LAUNCH(k_final_values, dim3(blocks), dim3(256), 0, 0, (float*)a.p, (const float*)b.p, (const float*)c.p, n,
+              make_update_params(lambda, min_value));
+  LMVN_CUDA_TRY(cudaGetLastError());
+  LMVN_CUDA_TRY(cudaMemcpy(image, a.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+
+}  // namespace lmvn

@@ -1,0 +1,120 @@
+// engine.cuh -- host side of the all-on-device strategy.
+//
+//   FftPlan      twiddle tables + per-axis factorisation for one (device, dims);
+//                kept in a process-wide, mutex-protected store keyed by shape
+//                (replaces ref: inc/plan_store.cuh:20-217, which caches cufftHandles
+//                in an unsynchronised singleton).
+//   ConvEngine   one FFT-convolution strategy: kernel-spectrum precompute and
+//                `out = epilogue(irfftn(rfftn(in) * K^))`.
+//   Deconv       the persistent handle behind lmvn_plan_* / inplace_gpu_deconvolve:
+//                one arena allocation, views + weights + 2V spectra resident,
+//                the (iteration, view) loop of ref: src/multiviewnative.cpp:191-229
+//                with no host round trip (replaces ref:
+//                src/gpu_deconvolve_methods.cuh:345-562, which re-uploads four
+//                stacks and re-transforms both kernels every step).
+#pragma once
+#include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "fft_types.cuh"
+#include "lmvn_common.cuh"
+
+namespace lmvn {
+
+bool trace_enabled();
+void trace(const char* fmt, ...);
+
+struct FftPlan {
+  int device = 0;
+  int nz = 0, ny = 0, nx = 0, nxc = 0;
+  gen::AxisPlan ax[3];  // 0: z, 1: y, 2: x
+  cplx* d_tw[3] = {nullptr, nullptr, nullptr};
+  int lines[3] = {1, 1, 1};    // lines per CTA in the generic passes
+  size_t smem[3] = {0, 0, 0};  // dynamic shared memory of the generic passes
+  size_t voxels() const { return size_t(nz) * ny * nx; }
+  size_t spec_elems() const { return size_t(nz) * ny * nxc; }
+  ~FftPlan();
+};
+
+// returns nullptr (and sets the last error) on failure
+std::shared_ptr<FftPlan> get_fft_plan(int device, int nz, int ny, int nx);
+
+// Optional per-launch timing: engines call mark() after every kernel launch; the
+// events sit on the same stream as the kernels.
+struct PassTimer {
+  struct Mark { const char* name; unsigned long long alg_bytes; cudaEvent_t ev; };
+  cudaEvent_t start = nullptr;
+  std::vector<Mark> marks;
+  int begin(cudaStream_t s);
+  void mark(const char* name, unsigned long long alg_bytes, cudaStream_t s);
+  ~PassTimer();
+};
+
+struct ConvEngine {
+  std::shared_ptr<FftPlan> plan;
+  PassTimer* timer = nullptr;  // set only while profiling
+  void mark(const char* name, unsigned long long bytes, cudaStream_t s) { if (timer) timer->mark(name, bytes, s); }
+  virtual ~ConvEngine() {}
+  virtual int strategy() const = 0;
+  virtual size_t khat_elems() const = 0;  // complex elements of one precomputed PSF spectrum
+  virtual size_t work_elems() const = 0;  // complex elements of the spectrum work buffer
+  virtual int launches_per_conv() const = 0;
+  // K^ = rfftn(wrap(kernel)) / N in this engine's layout.  d_kernel: device, unpadded.
+  virtual int kernel_spectrum(const float* d_kernel, const int kd[3], cplx* khat, cplx* work,
+                              cudaStream_t s) = 0;
+  virtual int convolve(const float* in, cplx* work, const cplx* khat, const gen::Epilogue& ep,
+                       float* out, cudaStream_t s) = 0;
+};
+
+std::unique_ptr<ConvEngine> make_generic_engine(std::shared_ptr<FftPlan> plan);
+// nullptr when the shape is not eligible (no error set)
+std::unique_ptr<ConvEngine> make_fused_engine(std::shared_ptr<FftPlan> plan);
+
+int default_strategy();
+void set_default_strategy(int s);
+
+struct Deconv {
+  int device = 0;
+  int dims[3] = {0, 0, 0};
+  int num_views = 0;
+  std::unique_ptr<ConvEngine> engine;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  unsigned char* arena = nullptr;
+  size_t arena_bytes = 0;
+  float* psi = nullptr;
+  float* integral = nullptr;
+  cplx* work = nullptr;
+  float* kernel_stage = nullptr;  // device staging for the unpadded PSFs
+  size_t kernel_stage_elems = 0;
+  std::vector<float*> image, weights;
+  std::vector<cplx*> khat1, khat2;
+  std::vector<char> view_set;
+  bool psi_set = false;
+
+  ~Deconv();
+  int init(const int* dims_zyx, int nviews, int dev, int strategy);
+  int set_view(int v, const float* image_h, const float* weights_h, const float* k1, const int* k1d,
+               const float* k2, const int* k2d);
+  int set_psi(const float* psi_h);
+  int get_psi(float* psi_h);
+  int iterate(int iterations, double lambda, float min_value, float* device_ms);
+  int convolve_psi(int view, int which, int repeats, float* device_ms);
+  int synchronize();
+  // one (view 0, iteration) with an event after every launch; psi is restored afterwards
+  int profile(double lambda, float min_value, std::vector<std::string>& names, std::vector<float>& ms,
+              std::vector<unsigned long long>& alg_bytes);
+};
+
+int resolve_device(int device);  // < 0 -> highest compute capability; validates range
+
+// debug hooks / legacy single-step entry points (host pointers unless noted)
+int debug_transform(const float* in, const int* dims, float* out, int device, bool inverse);
+int legacy_core_impl(float* d_im, const int* imDim, const float* d_kernel, const int* kernelDim, int dev);  // device ptrs
+int quotient_impl(const float* in, float* out, size_t n, int dev);
+int final_values_impl(float* image, const float* integral, const float* weight, size_t n, float min_value,
+                      double lambda, int dev);
+
+}  // namespace lmvn

@@ -1,0 +1,70 @@
+// lmvn_common.cuh -- shared definitions of the sm_100a build.
+//
+// Every kernel in csrc/ is written against CUDA directly.  The only indirection is
+// the pair of macros LMVN_LAUNCH / LMVN_DYN_SMEM, which exist so that the very
+// same sources can also be compiled by g++ against tests/emu/cuda_emu.h (a host
+// emulator of blocks/threads/barriers used by the CPU-only tests to check index
+// math).  The product library never defines LMVN_EMU.
+#pragma once
+
+#ifdef LMVN_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#define LMVN_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define LMVN_DYN_SMEM(type, name)                                  \
+  extern __shared__ __align__(16) unsigned char name##_raw_[];     \
+  type* name = reinterpret_cast<type*>(name##_raw_)
+#endif
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+namespace lmvn {
+
+typedef float2 cplx;
+
+__host__ __device__ __forceinline__ cplx cmake(float re, float im) { return make_float2(re, im); }
+__host__ __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_float2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_float2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// a * conj(b)
+__host__ __device__ __forceinline__ cplx cmulc(cplx a, cplx b) {
+  return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__host__ __device__ __forceinline__ cplx cconj(cplx a) { return make_float2(a.x, -a.y); }
+__host__ __device__ __forceinline__ cplx cscale(cplx a, float s) { return make_float2(a.x * s, a.y * s); }
+// multiply by -i (forward quarter turn) and +i
+__host__ __device__ __forceinline__ cplx cmul_mi(cplx a) { return make_float2(a.y, -a.x); }
+__host__ __device__ __forceinline__ cplx cmul_pi(cplx a) { return make_float2(-a.y, a.x); }
+
+// ---- error plumbing: nothing in this library exits or throws across the ABI ----
+void set_last_error(const char* fmt, ...);
+const char* last_error();
+void clear_last_error();
+
+#define LMVN_CUDA_TRY(expr)                                                               \
+  do {                                                                                    \
+    cudaError_t lmvn_e_ = (expr);                                                         \
+    if (lmvn_e_ != cudaSuccess) {                                                         \
+      ::lmvn::set_last_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(lmvn_e_), \
+                             __FILE__, __LINE__);                                         \
+      return -1;                                                                          \
+    }                                                                                     \
+  } while (0)
+
+#define LMVN_TRY(expr)            \
+  do {                            \
+    int lmvn_r_ = (expr);         \
+    if (lmvn_r_ != 0) return lmvn_r_; \
+  } while (0)
+
+static inline size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
+
+}  // namespace lmvn

@@ -1,0 +1,96 @@
+"""CPU-only: the library's sources compiled against the host emulator
+(tests/emu/cuda_emu.h) and driven through the same C ABI and the same parity
+cases as the GPU tests.  This checks kernel index math and host logic without
+a GPU; it says nothing about performance and is never the product path."""
+import numpy as np
+import pytest
+
+from tests import parity_cases as pc
+
+
+@pytest.fixture(scope="module")
+def L():
+    from libmultiviewnative_b200._build import build_emu
+    from libmultiviewnative_b200.capi import Library
+
+    return Library(build_emu())
+
+
+def test_emu_is_labelled(L):
+    assert "emulation" in L.version()
+
+
+@pytest.mark.parametrize("dims", [(8, 8, 8), (13, 17, 19), (16, 16, 16), (14, 14, 14), (9, 5, 25)])
+def test_fft_round_trip(L, dims):
+    pc.case_fft_round_trip(L, dims)
+
+
+@pytest.mark.parametrize("name", ["trivial", "identity", "horizontal", "vertical", "depth", "all1"])
+def test_conv_fixture(L, name):
+    pc.case_conv_fixture(L, name)
+
+
+@pytest.mark.parametrize("name", ["asymm_cross", "asymm_one", "asymm_identity"])
+def test_conv_impulse(L, name):
+    pc.case_conv_impulse(L, name)
+
+
+def test_conv_identity_asymmetric_image(L):
+    pc.case_conv_identity_asymmetric_image(L)
+
+
+@pytest.mark.parametrize("dims,kdims", [((16, 16, 32), (5, 5, 5)), ((12, 10, 14), (4, 3, 2)), ((8, 8, 8), (8, 8, 8))])
+def test_conv_random(L, dims, kdims):
+    pc.case_conv_random_vs_oracle(L, dims, kdims)
+
+
+def test_conv_rejects_oversized_kernel(L):
+    pc.case_conv_rejects_oversized_kernel(L)
+
+
+def test_pointwise(L):
+    pc.case_pointwise(L)
+
+
+@pytest.mark.parametrize("lam", [0.0, 0.006])
+def test_deconvolve_vs_oracle(L, lam):
+    pc.case_deconvolve_vs_oracle(L, (16, 16, 32), 3, 7, lam, iters_list=(1, 3), n_sources=10)
+
+
+def test_deconvolve_odd_dims(L):
+    pc.case_deconvolve_vs_oracle(L, (9, 10, 15), 2, 5, 0.006, iters_list=(1,), n_sources=6)
+
+
+def test_zero_iterations(L):
+    pc.case_zero_iterations(L)
+
+
+def test_deterministic(L):
+    pc.case_deterministic(L)
+
+
+def test_mismatched_views_rejected(L):
+    pc.case_mismatched_views_rejected(L)
+
+
+def test_plan_resume_equals_one_shot(L):
+    pc.case_plan_resume_equals_one_shot(L)
+
+
+def test_legacy_entry_points(L):
+    pc.case_legacy_iterate(L)
+
+
+def test_cpu_entry_points_match_oracle(L):
+    """inplace_cpu_* are link-compat symbols (host FFT); they must agree with the oracle."""
+    from libmultiviewnative_b200.synthetic import make_views
+    from oracle import mvn_oracle as orc
+
+    d = make_views((12, 16, 20), num_views=2, kernel_size=5, n_sources=6, workers=1)
+    psi = d["psi0"].copy()
+    L.inplace_cpu_deconvolve(psi, d["views"], d["kernels1"], d["kernels2"], d["weights"], 2, 0.006, 1e-4, nthreads=2)
+    exp = orc.inplace_cpu_deconvolve(d["psi0"], d["views"], d["kernels1"], d["kernels2"], d["weights"], 2, 0.006, 1e-4)
+    assert pc.max_rel(psi, exp) < 1e-4
+    im = d["views"][0].copy()
+    L.inplace_cpu_convolution(im, d["kernels1"][0], nthreads=1)
+    assert pc.rel_l2(im, orc.inplace_cpu_convolution(d["views"][0], d["kernels1"][0])) < 1e-5

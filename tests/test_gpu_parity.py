@@ -1,0 +1,178 @@
+"""GPU parity tests proper: the sm_100a library, through the C ABI, against the
+oracle on the same seeded inputs (sizes the oracle finishes in seconds), against
+the committed golden fixtures, and -- at BASELINE.json's full size -- through
+size-independent properties.  Run with `pytest -m gpu` on a B200."""
+import numpy as np
+import pytest
+
+from tests import parity_cases as pc
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def L():
+    from libmultiviewnative_b200.capi import load
+
+    lib = load()
+    assert "sm_100a" in lib.version()
+    assert lib.num_devices() >= 1
+    return lib
+
+
+@pytest.fixture(params=["generic", "auto"])
+def LS(L, request):
+    """every case runs on the generic passes and on whatever AUTO resolves to"""
+    from libmultiviewnative_b200 import capi
+
+    L.set_default_strategy(capi.STRATEGY_GENERIC if request.param == "generic" else capi.STRATEGY_AUTO)
+    yield L
+    L.set_default_strategy(capi.STRATEGY_AUTO)
+
+
+def test_device_queries(L):
+    dev = L.select_device()
+    assert 0 <= dev < L.num_devices()
+    major, minor = L.compute_capability(dev)
+    assert major >= 10, "this build targets sm_100a"
+    assert L.device_memory(dev) > (100 << 30)
+    assert len(L.device_name(dev)) > 0
+    assert L.compute_capability(99) == (-1, -1)
+
+
+@pytest.mark.parametrize("dims", [(8, 8, 8), (13, 17, 19), (16, 16, 16), (27, 27, 27), (25, 25, 25), (14, 14, 14),
+                                  (64, 64, 64), (128, 64, 32)])
+def test_fft_round_trip(L, dims):
+    pc.case_fft_round_trip(L, dims)
+
+
+@pytest.mark.parametrize("name", ["trivial", "identity", "horizontal", "vertical", "depth", "all1"])
+def test_conv_fixture(LS, name):
+    pc.case_conv_fixture(LS, name)
+
+
+@pytest.mark.parametrize("name", ["identity", "horizontal", "all1"])
+def test_legacy_conv_fixture(L, name):
+    pc.case_conv_fixture(L, name, entry="convolution3DfftCUDAInPlace")
+
+
+@pytest.mark.parametrize("name", ["asymm_cross", "asymm_one", "asymm_identity"])
+def test_conv_impulse(LS, name):
+    pc.case_conv_impulse(LS, name)
+
+
+def test_conv_identity_asymmetric_image(LS):
+    pc.case_conv_identity_asymmetric_image(LS)
+
+
+@pytest.mark.parametrize("dims,kdims", [
+    ((64, 64, 64), (15, 15, 15)), ((128, 64, 64), (21, 21, 21)), ((128, 128, 64), (31, 31, 31)),
+    ((64, 64, 64), (63, 63, 63)), ((12, 10, 14), (4, 3, 2)), ((8, 8, 8), (8, 8, 8)), ((50, 36, 30), (7, 9, 5)),
+    ((256, 128, 128), (41, 41, 41)),
+])
+def test_conv_random_vs_oracle(LS, dims, kdims):
+    pc.case_conv_random_vs_oracle(LS, dims, kdims)
+
+
+def test_conv_rejects_oversized_kernel(L):
+    pc.case_conv_rejects_oversized_kernel(L)
+
+
+def test_pointwise(L):
+    pc.case_pointwise(L)
+
+
+def test_divide_large_ragged(L):
+    # ref: tests/test_gpu_kernels_impl.cu:24-108 (256^3 and 256x255x257)
+    n = 256 * 255 * 257
+    out = np.full(n, 5.0, F32)
+    L.compute_quotient(np.full(n, 10.0, F32), out)
+    assert (out == 2.0).all()
+
+
+# ---- config 1: 3 views, 128^3, 31^3 PSFs, 1 and 10 iterations -------------------
+@pytest.mark.parametrize("lam", [0.0, 0.006])
+def test_config1_deconvolve_vs_oracle(LS, lam):
+    res = pc.case_deconvolve_vs_oracle(LS, (128, 128, 128), 3, 31, lam, iters_list=(1, 10), n_sources=200)
+    print("config1 lam=%g: %s" % (lam, res))
+
+
+def test_deconvolve_non_power_of_two(L):
+    pc.case_deconvolve_vs_oracle(L, (50, 36, 30), 2, 9, 0.006, iters_list=(1, 10), n_sources=20)
+
+
+def test_deconvolve_config4_block_shape(LS):
+    pc.case_deconvolve_vs_oracle(LS, (256, 256, 256), 2, 41, 0.006, iters_list=(1,), n_sources=500)
+
+
+def test_zero_iterations(L):
+    pc.case_zero_iterations(L)
+
+
+def test_deterministic(LS):
+    pc.case_deterministic(LS)
+
+
+def test_mismatched_views_rejected(L):
+    pc.case_mismatched_views_rejected(L)
+
+
+def test_plan_resume_equals_one_shot(LS):
+    pc.case_plan_resume_equals_one_shot(LS)
+
+
+def test_legacy_entry_points(L):
+    pc.case_legacy_iterate(L)
+
+
+def test_reference_bench_protocol_closed_form(LS):
+    """bench/synthetic_data.hpp:58-96: constant views 16+4i, unit weights, delta kernels of
+    value i+1 / i+2, psi0 = view 0.  With delta kernels every voxel evolves independently, so
+    the result is a scalar recurrence that float64 evaluates exactly enough."""
+    from libmultiviewnative_b200.synthetic import reference_bench_views
+
+    dims = (64, 32, 48)
+    d = reference_bench_views(dims, num_views=6)
+    psi = d["psi0"].copy()
+    lam, mn, iters = 0.006, 1e-3, 3
+    LS.inplace_gpu_deconvolve(psi, d["views"], d["kernels1"], d["kernels2"], d["weights"], iters, lam, mn)
+    p = 16.0
+    for _ in range(iters):
+        for i in range(6):
+            integ = (16.0 + 4.0 * i) / (p * (i + 1)) * (i + 2)
+            v = p * integ
+            v = (np.sqrt(1 + 2 * lam * v) - 1) / lam
+            p = max(v, mn)
+    np.testing.assert_allclose(psi, np.full(dims, p, F32), rtol=2e-5)
+
+
+# ---- full size (config 3: 512 x 512 x 256), size-independent properties -------------
+def test_full_size_properties(L):
+    dims = (512, 512, 256)
+    rng = np.random.default_rng(5)
+    a = (rng.random(dims, dtype=F32) + 1).astype(F32)
+    b = (rng.random(dims, dtype=F32) + 1).astype(F32)
+    from libmultiviewnative_b200.synthetic import gaussian_psf
+
+    k = gaussian_psf(41, (4.0, 1.5, 1.5))
+    ident = np.zeros((41, 41, 41), F32)
+    ident[20, 20, 20] = 1
+    # identity kernel returns the image
+    out = a.copy()
+    L.inplace_gpu_convolution(out, ident)
+    assert np.max(np.abs(out - a)) < 2e-5
+    # mass conservation: sum(conv) = sum(img) * sum(k)
+    ca = a.copy()
+    L.inplace_gpu_convolution(ca, k)
+    assert abs(ca.sum(dtype=np.float64) / (a.sum(dtype=np.float64) * k.sum(dtype=np.float64)) - 1) < 1e-6
+    # linearity
+    cb = b.copy()
+    L.inplace_gpu_convolution(cb, k)
+    cab = (a + b).astype(F32)
+    L.inplace_gpu_convolution(cab, k)
+    assert pc.rel_l2(cab, ca.astype(np.float64) + cb) < 2e-6
+    # shift equivariance of the circular convolution
+    sh = np.roll(a, (3, -5, 7), axis=(0, 1, 2)).copy()
+    L.inplace_gpu_convolution(sh, k)
+    assert pc.rel_l2(sh, np.roll(ca, (3, -5, 7), axis=(0, 1, 2))) < 2e-6
