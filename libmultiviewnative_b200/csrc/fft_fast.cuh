@@ -1,0 +1,520 @@
+// fft_fast.cuh -- power-of-two fast path of the in-house 3-D R2C/C2R convolution.
+//
+// Why it looks the way it does (B200 numbers): one SM's fair share of HBM is
+// ~23 B/clk while its shared-memory/L1 pipe moves 128 B/clk, so a transform that
+// bounces every byte through shared memory five or six times is limited by the
+// on-chip pipe, not by HBM.  Hence:
+//   * butterflies are radix-8 / radix-16 held in REGISTERS, so a 512-point axis
+//     needs two shared-memory exchanges and a 256-point real row needs one;
+//   * the first stage of every pass loads straight from global memory into
+//     registers and the last stage stores straight from registers -- shared
+//     memory only carries the inter-stage exchanges;
+//   * strided (y, z) passes work on tiles of 16 adjacent kx columns, i.e. every
+//     global access of a half-warp is one full, aligned 128-byte line;
+//   * forward passes are decimation-in-frequency (natural in, digit-reversed
+//     out), inverse passes decimation-in-time (digit-reversed in, natural out);
+//     the spectrum lives in HBM in digit-reversed (y, z) order and is never
+//     unscrambled -- the PSF spectra are produced by the same passes, so the
+//     pointwise product is order-agnostic;
+//   * the pointwise work of the iteration is fused into the pass edges: kernel
+//     wrap-around into the first pass's loads (ref: inc/padd_utils.h:11-40), the
+//     1/N scale into K^ (ref: inc/cpu_convolve.h:271-278), the spectrum product
+//     between the last forward and first inverse z stage (ref:
+//     inc/cpu_convolve.h:257-266), quotient / RL update into the last pass's
+//     stores (ref: inc/cpu_kernels.h:19-90).
+//
+// Spectrum layout: [z'][y'][kx] complex64, row pitch nxp = roundup(nx/2+1, 16)
+// so that every 16-column tile starts on a 128-byte line.
+#pragma once
+#include "fft_types.cuh"
+#include "lmvn_common.cuh"
+#include "pointwise.cuh"
+
+namespace lmvn {
+namespace fast {
+
+// ------------------------------------------------------------------------------
+// register butterflies.  INV = false: forward (e^{-i...}); true: inverse.
+// Outputs are in natural order: v[q] = sum_r v[r] w_R^{rq}.
+// ------------------------------------------------------------------------------
+template <bool INV>
+__device__ __forceinline__ cplx rot_q(cplx a) {  // * w_4^1  (forward: -i, inverse: +i)
+  return INV ? cmake(-a.y, a.x) : cmake(a.y, -a.x);
+}
+template <bool INV>
+__device__ __forceinline__ cplx mul_tw(cplx a, cplx w) {  // a * w (forward) or a * conj(w) (inverse)
+  return INV ? cmulc(a, w) : cmul(a, w);
+}
+
+template <int R, bool INV>
+struct Bfly;
+
+template <bool INV>
+struct Bfly<2, INV> {
+  static __device__ __forceinline__ void run(cplx* v) {
+    const cplx a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[1] = csub(a, b);
+  }
+};
+
+template <bool INV>
+struct Bfly<4, INV> {
+  static __device__ __forceinline__ void run(cplx* v) {
+    const cplx c0 = cadd(v[0], v[2]), c2 = csub(v[0], v[2]);
+    const cplx c1 = cadd(v[1], v[3]), c3 = rot_q<INV>(csub(v[1], v[3]));
+    v[0] = cadd(c0, c1);
+    v[2] = csub(c0, c1);
+    v[1] = cadd(c2, c3);
+    v[3] = csub(c2, c3);
+  }
+};
+
+template <bool INV>
+struct Bfly<8, INV> {
+  static __device__ __forceinline__ void run(cplx* v) {
+    const float h = 0.70710678118654752440f;
+    const cplx a0 = cadd(v[0], v[4]), a4 = csub(v[0], v[4]);
+    const cplx a1 = cadd(v[1], v[5]);
+    cplx a5 = csub(v[1], v[5]);
+    const cplx a2 = cadd(v[2], v[6]), a6 = rot_q<INV>(csub(v[2], v[6]));
+    const cplx a3 = cadd(v[3], v[7]);
+    cplx a7 = csub(v[3], v[7]);
+    // a5 *= w8^1, a7 *= w8^3
+    if (!INV) {
+      a5 = cmake(h * (a5.x + a5.y), h * (a5.y - a5.x));
+      a7 = cmake(h * (a7.y - a7.x), -h * (a7.x + a7.y));
+    } else {
+      a5 = cmake(h * (a5.x - a5.y), h * (a5.x + a5.y));
+      a7 = cmake(-h * (a7.x + a7.y), h * (a7.x - a7.y));
+    }
+    const cplx b0 = cadd(a0, a2), b2 = csub(a0, a2);
+    const cplx b1 = cadd(a1, a3), b3 = rot_q<INV>(csub(a1, a3));
+    const cplx b4 = cadd(a4, a6), b6 = csub(a4, a6);
+    const cplx b5 = cadd(a5, a7), b7 = rot_q<INV>(csub(a5, a7));
+    v[0] = cadd(b0, b1);
+    v[4] = csub(b0, b1);
+    v[2] = cadd(b2, b3);
+    v[6] = csub(b2, b3);
+    v[1] = cadd(b4, b5);
+    v[5] = csub(b4, b5);
+    v[3] = cadd(b6, b7);
+    v[7] = csub(b6, b7);
+  }
+};
+
+template <bool INV>
+struct Bfly<16, INV> {
+  static __device__ __forceinline__ void run(cplx* v) {
+    // 16 = 4 x 4 decimation in frequency: X[q + 4 q2] = sum_i (DFT4_r(v[i+4r])[q] * w16^{iq}) w4^{i q2}
+    const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;  // cos, sin(pi/8)
+    const float h = 0.70710678118654752440f;
+    cplx a[4][4];  // a[q][i]
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      cplx t[4] = {v[i], v[i + 4], v[i + 8], v[i + 12]};
+      Bfly<4, INV>::run(t);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a[q][i] = t[q];
+    }
+    // twiddles w16^{iq}: exponents 1,2,3 (i=1), 2,4,6 (i=2), 3,6,9 (i=3)
+    const cplx w1 = cmake(c1, -s1), w2 = cmake(h, -h), w3 = cmake(s1, -c1);
+    const cplx w6 = cmake(-h, -h), w9 = cmake(-c1, s1);
+    a[1][1] = mul_tw<INV>(a[1][1], w1);
+    a[2][1] = mul_tw<INV>(a[2][1], w2);
+    a[3][1] = mul_tw<INV>(a[3][1], w3);
+    a[1][2] = mul_tw<INV>(a[1][2], w2);
+    a[2][2] = rot_q<INV>(a[2][2]);  // w16^4
+    a[3][2] = mul_tw<INV>(a[3][2], w6);
+    a[1][3] = mul_tw<INV>(a[1][3], w3);
+    a[2][3] = mul_tw<INV>(a[2][3], w6);
+    a[3][3] = mul_tw<INV>(a[3][3], w9);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      cplx t[4] = {a[q][0], a[q][1], a[q][2], a[q][3]};
+      Bfly<4, INV>::run(t);
+#pragma unroll
+      for (int q2 = 0; q2 < 4; ++q2) v[q + 4 * q2] = t[q2];
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------
+// strided passes (y and z axes): tile = N rows x COLS adjacent kx columns.
+// ------------------------------------------------------------------------------
+enum StridedMode { SM_FWD = 0, SM_INV = 1, SM_FWD_MUL_INV = 2, SM_FWD_SCALE = 3 };
+
+struct StridedArgs {
+  cplx* data;          // spectrum, in place
+  const cplx* khat;    // SM_FWD_MUL_INV: same layout as data
+  long long row_stride;    // complex elements between consecutive transform rows
+  long long tile_stride;   // between consecutive tiles of the slow tile index (blockIdx.y)
+  int ncols;           // valid kx columns (nx/2+1)
+  const cplx* tw;      // w_N table, N entries
+  float scale;         // SM_FWD_SCALE
+};
+
+// number of stages and the radix of stage s for N = R1*R2*R3
+template <int N>
+struct Radix;
+template <> struct Radix<512> { static const int S = 3, R1 = 8, R2 = 8, R3 = 8; };
+template <> struct Radix<256> { static const int S = 3, R1 = 8, R2 = 8, R3 = 4; };
+template <> struct Radix<128> { static const int S = 3, R1 = 8, R2 = 4, R3 = 4; };
+template <> struct Radix<64> { static const int S = 2, R1 = 8, R2 = 8, R3 = 1; };
+template <> struct Radix<32> { static const int S = 2, R1 = 8, R2 = 4, R3 = 1; };
+template <> struct Radix<16> { static const int S = 2, R1 = 4, R2 = 4, R3 = 1; };
+
+template <int N> struct Cols { static const int V = (N >= 256) ? 16 : (N >= 128 ? 32 : 64); };
+
+static const int kStridedThreads = 256;
+
+// One DIF (forward) stage: load R inputs, butterfly, post-twiddle w_L^{jq}, store.
+// LOAD(row, col) / STORE(row, col, value) are functors over tile coordinates.
+template <int N, int R, int L, int COLS, bool INV, typename LoadF, typename StoreF>
+__device__ __forceinline__ void strided_stage(const cplx* __restrict__ tw, LoadF load, StoreF store) {
+  constexpr int M = L / R;
+  constexpr int PER_THREAD = (N / R) * COLS / kStridedThreads;
+  static_assert(PER_THREAD >= 1, "tile too small for the block");
+#pragma unroll
+  for (int i = 0; i < PER_THREAD; ++i) {
+    const int w = threadIdx.x + i * kStridedThreads;
+    const int c = w % COLS;
+    const int bf = w / COLS;
+    const int j = bf % M;
+    const int b = (bf / M) * L;
+    cplx v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = load(b + j + r * M, c);
+    if (INV && M > 1) {  // DIT: pre-twiddle with conj(w_L^{jq})
+#pragma unroll
+      for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], __ldg(tw + j * q * (N / L)));
+    }
+    Bfly<R, INV>::run(v);
+    if (!INV && M > 1) {
+#pragma unroll
+      for (int q = 1; q < R; ++q) v[q] = cmul(v[q], __ldg(tw + j * q * (N / L)));
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) store(b + j + q * M, c, v[q]);
+  }
+}
+
+// middle of the merged z pass: last forward stage, spectrum product, first inverse stage
+template <int N, int R, int COLS, typename LoadF, typename KF, typename StoreF>
+__device__ __forceinline__ void strided_middle(LoadF load, KF kload, StoreF store) {
+  constexpr int PER_THREAD = (N / R) * COLS / kStridedThreads;
+#pragma unroll
+  for (int i = 0; i < PER_THREAD; ++i) {
+    const int w = threadIdx.x + i * kStridedThreads;
+    const int c = w % COLS;
+    const int b = (w / COLS) * R;
+    cplx v[R], k[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) k[r] = kload(b + r, c);
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = load(b + r, c);
+    Bfly<R, false>::run(v);
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = cmul(v[r], k[r]);
+    Bfly<R, true>::run(v);
+#pragma unroll
+    for (int r = 0; r < R; ++r) store(b + r, c, v[r]);
+  }
+}
+
+template <int N, int MODE>
+static __global__ void __launch_bounds__(kStridedThreads, (MODE == SM_FWD_MUL_INV && N >= 64) ? 2 : 3) k_strided(StridedArgs A) {
+  typedef Radix<N> RX;
+  constexpr int COLS = Cols<N>::V;
+  constexpr int R1 = RX::R1, R2 = RX::R2, R3 = RX::R3;
+  constexpr int L2 = N / R1, L3 = N / (R1 * R2);
+  LMVN_DYN_SMEM(cplx, sm);  // [N][COLS]
+  const int col0 = blockIdx.x * COLS;
+  cplx* g = A.data + (long long)blockIdx.y * A.tile_stride + col0;
+  const cplx* gk = (MODE == SM_FWD_MUL_INV) ? A.khat + (long long)blockIdx.y * A.tile_stride + col0 : nullptr;
+  const int nvalid = A.ncols - col0;  // columns c < nvalid are real data
+  const long long rs = A.row_stride;
+  const cplx* tw = A.tw;
+
+  auto gload = [&](int row, int c) -> cplx { return (c < nvalid) ? g[row * rs + c] : cmake(0.f, 0.f); };
+  auto gstore = [&](int row, int c, cplx v) { if (c < nvalid) g[row * rs + c] = v; };
+  auto gstore_scaled = [&](int row, int c, cplx v) { if (c < nvalid) g[row * rs + c] = cscale(v, A.scale); };
+  auto kload = [&](int row, int c) -> cplx { return (c < nvalid) ? __ldg(gk + row * rs + c) : cmake(0.f, 0.f); };
+  auto sload = [&](int row, int c) -> cplx { return sm[row * COLS + c]; };
+  auto sstore = [&](int row, int c, cplx v) { sm[row * COLS + c] = v; };
+
+  if (MODE == SM_FWD || MODE == SM_FWD_SCALE) {
+    strided_stage<N, R1, N, COLS, false>(tw, gload, sstore);
+    __syncthreads();
+    if (RX::S == 3) {
+      strided_stage<N, R2, L2, COLS, false>(tw, sload, sstore);
+      __syncthreads();
+      if (MODE == SM_FWD) strided_stage<N, (R3 > 1 ? R3 : 2), (R3 > 1 ? L3 : 2), COLS, false>(tw, sload, gstore);
+      else strided_stage<N, (R3 > 1 ? R3 : 2), (R3 > 1 ? L3 : 2), COLS, false>(tw, sload, gstore_scaled);
+    } else {
+      if (MODE == SM_FWD) strided_stage<N, R2, L2, COLS, false>(tw, sload, gstore);
+      else strided_stage<N, R2, L2, COLS, false>(tw, sload, gstore_scaled);
+    }
+  } else if (MODE == SM_INV) {
+    if (RX::S == 3) {
+      strided_stage<N, (R3 > 1 ? R3 : 2), (R3 > 1 ? L3 : 2), COLS, true>(tw, gload, sstore);
+      __syncthreads();
+      strided_stage<N, R2, L2, COLS, true>(tw, sload, sstore);
+    } else {
+      strided_stage<N, R2, L2, COLS, true>(tw, gload, sstore);
+    }
+    __syncthreads();
+    strided_stage<N, R1, N, COLS, true>(tw, sload, gstore);
+  } else {  // SM_FWD_MUL_INV
+    strided_stage<N, R1, N, COLS, false>(tw, gload, sstore);
+    __syncthreads();
+    if (RX::S == 3) {
+      strided_stage<N, R2, L2, COLS, false>(tw, sload, sstore);
+      __syncthreads();
+      strided_middle<N, (R3 > 1 ? R3 : 2), COLS>(sload, kload, sstore);
+      __syncthreads();
+      strided_stage<N, R2, L2, COLS, true>(tw, sload, sstore);
+    } else {
+      strided_middle<N, R2, COLS>(sload, kload, sstore);
+    }
+    __syncthreads();
+    strided_stage<N, R1, N, COLS, true>(tw, sload, gstore);
+  }
+}
+
+// ------------------------------------------------------------------------------
+// x passes: one real row of nx = 2M samples <-> M+1 complex bins.
+// M = R1 * 8.  A row is handled by TPR = R1/2 threads holding 16 complex values
+// each; stage 1 = radix-R1 over elements j + 8r, one exchange through a padded
+// shared-memory slab, stage 2 = two radix-8 blocks (q and R1-q) per thread, which
+// puts every (k, M-k) pair of the real-transform split into ONE thread's registers.
+// ------------------------------------------------------------------------------
+static const int kRowThreads = 256;
+
+template <int M> struct RowCfg {
+  static const int R1 = M / 8;          // 4, 8, 16
+  static const int TPR = R1 / 2;        // threads per row: 2, 4, 8
+  static const int JPT = 16 / R1;       // stage-1 butterflies per thread
+  static const int ROWS = kRowThreads / TPR;  // rows per block pass
+  // exchange slab: element (q, j) at q*9 + j; 9-pitch makes both the j-contiguous writes
+  // and the q-strided reads conflict free; rows are offset by SLAB (= 8 mod 16)
+  static const int SLAB = ((R1 * 9 + 15) / 16) * 16 + 8;
+};
+
+struct RowArgs {
+  gen::RealSource src;   // forward: real input (volume or wrapped kernel)
+  cplx* spec;            // forward: output; inverse: input
+  float* out;            // inverse: real output
+  gen::Epilogue ep;      // inverse: pointwise epilogue
+  int nz, ny;
+  int nxp;               // spectrum row pitch (complex)
+  const cplx* tw_m;      // w_M table (M entries)
+  const cplx* tw_nx;     // w_nx^k, k = 0..M
+};
+
+// real-transform split for one (k, M-k) pair:  X[k] = E + w^k O,  X[M-k] = conj(E - w^k O)
+__device__ __forceinline__ void r2c_pair(cplx zk, cplx zm, cplx w, cplx& xk, cplx& xm) {
+  const cplx e = cmake(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));   // (Zk + conj Zm)/2
+  const cplx d = cmake(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));   // (Zk - conj Zm)/2
+  const cplx o = cmake(d.y, -d.x);                                    // d / i
+  const cplx wo = cmul(w, o);
+  xk = cadd(e, wo);
+  xm = cconj(csub(e, wo));
+}
+// inverse split (doubled, so that the result is the UNNORMALISED c2r):
+//   Z[k] = E' + i O',  Z[M-k] = conj(E') + i conj(O'),  E' = X[k] + conj X[M-k],  O' = (X[k] - conj X[M-k]) conj(w^k)
+__device__ __forceinline__ void c2r_pair(cplx xk, cplx xm, cplx w, cplx& zk, cplx& zm) {
+  const cplx e = cmake(xk.x + xm.x, xk.y - xm.y);
+  const cplx d = cmake(xk.x - xm.x, xk.y + xm.y);
+  const cplx o = cmulc(d, w);
+  zk = cmake(e.x - o.y, e.y + o.x);
+  zm = cmake(e.x + o.y, -e.y + o.x);
+}
+
+template <int M, bool WRAPPED>
+static __global__ void __launch_bounds__(kRowThreads) k_rows_fwd(RowArgs A) {
+  typedef RowCfg<M> CF;
+  constexpr int R1 = CF::R1, TPR = CF::TPR, JPT = CF::JPT;
+  constexpr int nx = 2 * M;
+  LMVN_DYN_SMEM(cplx, sm);
+  const int t = threadIdx.x % TPR;
+  const int lrow = threadIdx.x / TPR;
+  const long long rows = (long long)A.nz * A.ny;
+  const long long row = (long long)blockIdx.x * CF::ROWS + lrow;
+  cplx* slab = sm + lrow * CF::SLAB;
+  const bool active = row < rows;
+  cplx v[16];
+  if (active) {
+    if (!WRAPPED) {
+      const float2* in = reinterpret_cast<const float2*>(A.src.data + row * nx);
+#pragma unroll
+      for (int jj = 0; jj < JPT; ++jj)
+#pragma unroll
+        for (int r = 0; r < R1; ++r) v[jj * R1 + r] = in[(t * JPT + jj) + 8 * r];
+    } else {
+      const int z = int(row / A.ny), y = int(row % A.ny);
+      const int sz = gen::wrap_src_index(z, A.nz, A.src.kz);
+      const int sy = gen::wrap_src_index(y, A.ny, A.src.ky);
+#pragma unroll
+      for (int jj = 0; jj < JPT; ++jj)
+#pragma unroll
+        for (int r = 0; r < R1; ++r) {
+          const int n = (t * JPT + jj) + 8 * r;
+          float a = 0.f, b = 0.f;
+          if (sz >= 0 && sy >= 0) {
+            const float* kr = A.src.data + (size_t(sz) * A.src.ky + sy) * A.src.kx;
+            const int s0 = gen::wrap_src_index(2 * n, nx, A.src.kx);
+            const int s1 = gen::wrap_src_index(2 * n + 1, nx, A.src.kx);
+            if (s0 >= 0) a = kr[s0];
+            if (s1 >= 0) b = kr[s1];
+          }
+          v[jj * R1 + r] = cmake(a, b);
+        }
+    }
+    // stage 1: radix-R1 over r, twiddle w_M^{jq}, to the slab at (q, j)
+#pragma unroll
+    for (int jj = 0; jj < JPT; ++jj) {
+      const int j = t * JPT + jj;
+      Bfly<R1, false>::run(v + jj * R1);
+#pragma unroll
+      for (int q = 0; q < R1; ++q) {
+        cplx x = v[jj * R1 + q];
+        if (q > 0) x = cmul(x, __ldg(A.tw_m + j * q));
+        slab[q * 9 + j] = x;
+      }
+    }
+  }
+  __syncwarp();
+  if (active) {
+    // stage 2: radix-8 on blocks qa, qb
+    const int qa = t, qb = (t == 0) ? R1 / 2 : R1 - t;
+#pragma unroll
+    for (int q2 = 0; q2 < 8; ++q2) {
+      v[q2] = slab[qa * 9 + q2];
+      v[8 + q2] = slab[qb * 9 + q2];
+    }
+    Bfly<8, false>::run(v);
+    Bfly<8, false>::run(v + 8);
+    // v[q2] = Z[qa + R1 q2], v[8+q2] = Z[qb + R1 q2]
+    cplx* orow = A.spec + row * A.nxp;
+    if (t != 0) {
+#pragma unroll
+      for (int q2 = 0; q2 < 8; ++q2) {
+        const int k = qa + R1 * q2;  // partner M-k = qb + R1 (7-q2)
+        cplx xk, xm;
+        r2c_pair(v[q2], v[8 + 7 - q2], __ldg(A.tw_nx + k), xk, xm);
+        orow[k] = xk;
+        orow[M - k] = xm;
+      }
+    } else {
+      // block 0: k = R1 q2 pairs with R1 (8 - q2); q2 = 0 -> DC / Nyquist, q2 = 4 -> k = M/2
+      orow[0] = cmake(v[0].x + v[0].y, 0.f);
+      orow[M] = cmake(v[0].x - v[0].y, 0.f);
+      orow[M / 2] = cconj(v[4]);
+#pragma unroll
+      for (int q2 = 1; q2 < 4; ++q2) {
+        const int k = R1 * q2;
+        cplx xk, xm;
+        r2c_pair(v[q2], v[8 - q2], __ldg(A.tw_nx + k), xk, xm);
+        orow[k] = xk;
+        orow[M - k] = xm;
+      }
+      // block R1/2: k = R1/2 + R1 q2 pairs with R1/2 + R1 (7 - q2)
+#pragma unroll
+      for (int q2 = 0; q2 < 4; ++q2) {
+        const int k = R1 / 2 + R1 * q2;
+        cplx xk, xm;
+        r2c_pair(v[8 + q2], v[8 + 7 - q2], __ldg(A.tw_nx + k), xk, xm);
+        orow[k] = xk;
+        orow[M - k] = xm;
+      }
+    }
+  }
+}
+
+template <int M>
+static __global__ void __launch_bounds__(kRowThreads) k_rows_inv(RowArgs A) {
+  typedef RowCfg<M> CF;
+  constexpr int R1 = CF::R1, TPR = CF::TPR, JPT = CF::JPT;
+  constexpr int nx = 2 * M;
+  LMVN_DYN_SMEM(cplx, sm);
+  const int t = threadIdx.x % TPR;
+  const int lrow = threadIdx.x / TPR;
+  const long long rows = (long long)A.nz * A.ny;
+  const long long row = (long long)blockIdx.x * CF::ROWS + lrow;
+  cplx* slab = sm + lrow * CF::SLAB;
+  const bool active = row < rows;
+  cplx v[16];
+  if (active) {
+    const cplx* irow = A.spec + row * A.nxp;
+    const int qa = t, qb = (t == 0) ? R1 / 2 : R1 - t;
+    if (t != 0) {
+#pragma unroll
+      for (int q2 = 0; q2 < 8; ++q2) {
+        const int k = qa + R1 * q2;
+        c2r_pair(irow[k], irow[M - k], __ldg(A.tw_nx + k), v[q2], v[8 + 7 - q2]);
+      }
+    } else {
+      const float x0 = irow[0].x, xm = irow[M].x;  // imaginary parts ignored like a c2r transform
+      v[0] = cmake(x0 + xm, x0 - xm);
+      const cplx xh = irow[M / 2];
+      v[4] = cmake(2.f * xh.x, -2.f * xh.y);
+#pragma unroll
+      for (int q2 = 1; q2 < 4; ++q2) {
+        const int k = R1 * q2;
+        c2r_pair(irow[k], irow[M - k], __ldg(A.tw_nx + k), v[q2], v[8 - q2]);
+      }
+#pragma unroll
+      for (int q2 = 0; q2 < 4; ++q2) {
+        const int k = R1 / 2 + R1 * q2;
+        c2r_pair(irow[k], irow[M - k], __ldg(A.tw_nx + k), v[8 + q2], v[8 + 7 - q2]);
+      }
+    }
+    Bfly<8, true>::run(v);
+    Bfly<8, true>::run(v + 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      slab[qa * 9 + j] = v[j];
+      slab[qb * 9 + j] = v[8 + j];
+    }
+  }
+  __syncwarp();
+  if (active) {
+    float2* orow = reinterpret_cast<float2*>(A.out + row * nx);
+    const size_t base = size_t(row) * nx;
+#pragma unroll
+    for (int jj = 0; jj < JPT; ++jj) {
+      const int j = t * JPT + jj;
+#pragma unroll
+      for (int q = 0; q < R1; ++q) {
+        cplx x = slab[q * 9 + j];
+        if (q > 0) x = cmulc(x, __ldg(A.tw_m + j * q));
+        v[jj * R1 + q] = x;
+      }
+      Bfly<R1, true>::run(v + jj * R1);
+#pragma unroll
+      for (int r = 0; r < R1; ++r) {
+        const int n = j + 8 * r;  // complex sample n = real samples 2n, 2n+1
+        float2 val = make_float2(v[jj * R1 + r].x * A.ep.scale, v[jj * R1 + r].y * A.ep.scale);
+        if (A.ep.mode == gen::EPI_QUOTIENT) {
+          const float2 vw = reinterpret_cast<const float2*>(A.ep.view + base)[n];
+          val.x = quotient(vw.x, val.x);
+          val.y = quotient(vw.y, val.y);
+          orow[n] = val;
+        } else if (A.ep.mode == gen::EPI_UPDATE) {
+          float2* pp = reinterpret_cast<float2*>(A.ep.psi + base) + n;
+          const float2 ps = *pp;
+          const float2 wt = reinterpret_cast<const float2*>(A.ep.weights + base)[n];
+          val.x = rl_update(ps.x, val.x, wt.x, A.ep.up);
+          val.y = rl_update(ps.y, val.y, wt.y, A.ep.up);
+          *pp = val;
+        } else {
+          orow[n] = val;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace fast
+}  // namespace lmvn

@@ -1,0 +1,229 @@
+// fft_fused.cu -- host side of the power-of-two fast path (kernels: fft_fast.cuh).
+//
+// Strategy LMVN_STRATEGY_FUSED: five launches per convolution, every pointwise step
+// of the RL iteration fused into a transform pass:
+//   rows_fwd            S -> C     real rows (or wrapped PSF) -> half spectrum along x
+//   strided y forward   C -> C
+//   strided z fwd*K^*inv C,K -> C  last forward stage, spectrum product and first inverse
+//                                  stage share registers
+//   strided y inverse   C -> C
+//   rows_inv            C(+S..) -> S   inverse along x + quotient / RL update
+#include <cmath>
+#include <vector>
+
+#include "engine.cuh"
+#include "fft_fast.cuh"
+
+namespace lmvn {
+
+namespace {
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+struct FastEngine : ConvEngine {
+  int M = 0, nxc = 0, nxp = 0;
+  cplx* d_tw_m = nullptr;
+  cplx* d_tw_nx = nullptr;
+  cplx* d_tw_y = nullptr;
+  cplx* d_tw_z = nullptr;
+
+  ~FastEngine() override {
+    if (d_tw_m) cudaFree(d_tw_m);
+    if (d_tw_nx) cudaFree(d_tw_nx);
+    if (d_tw_y) cudaFree(d_tw_y);
+    if (d_tw_z) cudaFree(d_tw_z);
+  }
+  int strategy() const override { return 2; }
+  size_t khat_elems() const override { return size_t(plan->nz) * plan->ny * nxp; }
+  size_t work_elems() const override { return khat_elems(); }
+  int launches_per_conv() const override { return 5; }
+  unsigned long long S() const { return plan->voxels() * sizeof(float); }
+  unsigned long long C() const { return plan->spec_elems() * sizeof(cplx); }
+
+  static int upload_table(cplx** dst, int period, int count) {
+    std::vector<cplx> h(count);
+    for (int k = 0; k < count; ++k) {
+      const double a = -2.0 * M_PI * double(k) / double(period);
+      h[k] = cmake(float(cos(a)), float(sin(a)));
+    }
+    LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(dst), sizeof(cplx) * count));
+    LMVN_CUDA_TRY(cudaMemcpy(*dst, h.data(), sizeof(cplx) * count, cudaMemcpyHostToDevice));
+    return 0;
+  }
+
+  int init() {
+    M = plan->nx / 2;
+    nxc = plan->nxc;
+    nxp = (nxc + 15) / 16 * 16;
+    LMVN_TRY(upload_table(&d_tw_m, M, M));
+    LMVN_TRY(upload_table(&d_tw_nx, plan->nx, M + 1));
+    LMVN_TRY(upload_table(&d_tw_y, plan->ny, plan->ny));
+    LMVN_TRY(upload_table(&d_tw_z, plan->nz, plan->nz));
+    return 0;
+  }
+
+  // ---- launches -------------------------------------------------------------
+  template <int MM>
+  int launch_rows_fwd(const fast::RowArgs& a, bool wrapped, cudaStream_t s) {
+    typedef fast::RowCfg<MM> CF;
+    const size_t rows = size_t(plan->nz) * plan->ny;
+    const dim3 grid(unsigned(ceil_div(rows, CF::ROWS)));
+    const size_t smem = size_t(CF::ROWS) * CF::SLAB * sizeof(cplx);
+    auto kw = fast::k_rows_fwd<MM, true>;
+    auto kp = fast::k_rows_fwd<MM, false>;
+    if (wrapped) {
+      LMVN_LAUNCH(kw, grid, dim3(fast::kRowThreads), smem, s, a);
+    } else {
+      LMVN_LAUNCH(kp, grid, dim3(fast::kRowThreads), smem, s, a);
+    }
+    return 0;
+  }
+  template <int MM>
+  int launch_rows_inv(const fast::RowArgs& a, cudaStream_t s) {
+    typedef fast::RowCfg<MM> CF;
+    const size_t rows = size_t(plan->nz) * plan->ny;
+    const dim3 grid(unsigned(ceil_div(rows, CF::ROWS)));
+    const size_t smem = size_t(CF::ROWS) * CF::SLAB * sizeof(cplx);
+    auto kfn = fast::k_rows_inv<MM>;
+    LMVN_LAUNCH(kfn, grid, dim3(fast::kRowThreads), smem, s, a);
+    return 0;
+  }
+
+  int rows_fwd(const gen::RealSource& src, cplx* spec, cudaStream_t s) {
+    fast::RowArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.src = src;
+    a.spec = spec;
+    a.nz = plan->nz; a.ny = plan->ny; a.nxp = nxp;
+    a.tw_m = d_tw_m; a.tw_nx = d_tw_nx;
+    const bool w = src.wrapped != 0;
+    switch (M) {
+      case 32: LMVN_TRY(launch_rows_fwd<32>(a, w, s)); break;
+      case 64: LMVN_TRY(launch_rows_fwd<64>(a, w, s)); break;
+      case 128: LMVN_TRY(launch_rows_fwd<128>(a, w, s)); break;
+      default: set_last_error("fused path: unsupported nx"); return -1;
+    }
+    LMVN_CUDA_TRY(cudaGetLastError());
+    mark("fast_rows_fwd", S() + C(), s);
+    return 0;
+  }
+
+  int rows_inv(const cplx* spec, float* out, const gen::Epilogue& ep, cudaStream_t s) {
+    fast::RowArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.spec = const_cast<cplx*>(spec);
+    a.out = out;
+    a.ep = ep;
+    a.nz = plan->nz; a.ny = plan->ny; a.nxp = nxp;
+    a.tw_m = d_tw_m; a.tw_nx = d_tw_nx;
+    switch (M) {
+      case 32: LMVN_TRY(launch_rows_inv<32>(a, s)); break;
+      case 64: LMVN_TRY(launch_rows_inv<64>(a, s)); break;
+      case 128: LMVN_TRY(launch_rows_inv<128>(a, s)); break;
+      default: set_last_error("fused path: unsupported nx"); return -1;
+    }
+    LMVN_CUDA_TRY(cudaGetLastError());
+    mark(ep.mode == gen::EPI_UPDATE ? "fast_rows_inv_update"
+                                    : (ep.mode == gen::EPI_QUOTIENT ? "fast_rows_inv_quotient" : "fast_rows_inv"),
+         C() + S() * (ep.mode == gen::EPI_UPDATE ? 3 : (ep.mode == gen::EPI_QUOTIENT ? 2 : 1)), s);
+    return 0;
+  }
+
+  template <int N, int MODE>
+  int launch_strided(const fast::StridedArgs& a, dim3 grid, cudaStream_t s) {
+    constexpr int COLS = fast::Cols<N>::V;
+    const size_t smem = size_t(N) * COLS * sizeof(cplx);
+    auto kfn = fast::k_strided<N, MODE>;
+    if (smem > 48 * 1024) {  // per device, cheap: set every time
+      LMVN_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    }
+    LMVN_LAUNCH(kfn, grid, dim3(fast::kStridedThreads), smem, s, a);
+    return 0;
+  }
+  template <int N>
+  int launch_strided_mode(const fast::StridedArgs& a, int mode, dim3 grid, cudaStream_t s) {
+    switch (mode) {
+      case fast::SM_FWD: return launch_strided<N, fast::SM_FWD>(a, grid, s);
+      case fast::SM_INV: return launch_strided<N, fast::SM_INV>(a, grid, s);
+      case fast::SM_FWD_MUL_INV: return launch_strided<N, fast::SM_FWD_MUL_INV>(a, grid, s);
+      default: return launch_strided<N, fast::SM_FWD_SCALE>(a, grid, s);
+    }
+  }
+
+  // axis 1 = y, axis 0 = z
+  int strided(cplx* data, const cplx* khat, int axis, int mode, float scale, cudaStream_t s) {
+    const FftPlan& p = *plan;
+    fast::StridedArgs a;
+    a.data = data;
+    a.khat = khat;
+    a.ncols = nxc;
+    a.scale = scale;
+    int n;
+    unsigned slow;
+    if (axis == 1) {
+      n = p.ny; a.row_stride = nxp; a.tile_stride = (long long)p.ny * nxp; slow = unsigned(p.nz); a.tw = d_tw_y;
+    } else {
+      n = p.nz; a.row_stride = (long long)p.ny * nxp; a.tile_stride = nxp; slow = unsigned(p.ny); a.tw = d_tw_z;
+    }
+    int rc;
+#define LMVN_STRIDED_CASE(NN)                                                                   \
+  case NN: {                                                                                    \
+    const dim3 grid(unsigned(ceil_div(size_t(nxc), size_t(fast::Cols<NN>::V))), slow);          \
+    rc = launch_strided_mode<NN>(a, mode, grid, s);                                             \
+  } break;
+    switch (n) {
+      LMVN_STRIDED_CASE(16)
+      LMVN_STRIDED_CASE(32)
+      LMVN_STRIDED_CASE(64)
+      LMVN_STRIDED_CASE(128)
+      LMVN_STRIDED_CASE(256)
+      LMVN_STRIDED_CASE(512)
+      default: set_last_error("fused path: unsupported axis length %d", n); return -1;
+    }
+#undef LMVN_STRIDED_CASE
+    if (rc != 0) return rc;
+    LMVN_CUDA_TRY(cudaGetLastError());
+    if (mode == fast::SM_FWD_MUL_INV) mark("fast_z_mul", 3 * C(), s);
+    else mark(axis == 1 ? (mode == fast::SM_INV ? "fast_y_inv" : "fast_y_fwd") : "fast_z", 2 * C(), s);
+    return 0;
+  }
+
+  int kernel_spectrum(const float* d_kernel, const int kd[3], cplx* khat, cplx*, cudaStream_t s) override {
+    gen::RealSource src{d_kernel, 1, kd[0], kd[1], kd[2]};
+    LMVN_TRY(rows_fwd(src, khat, s));
+    LMVN_TRY(strided(khat, nullptr, 1, fast::SM_FWD, 1.f, s));
+    const float inv_n = float(1.0 / double(plan->voxels()));  // decision q10: 1/N folded into K^
+    LMVN_TRY(strided(khat, nullptr, 0, fast::SM_FWD_SCALE, inv_n, s));
+    return 0;
+  }
+
+  int convolve(const float* in, cplx* work, const cplx* khat, const gen::Epilogue& ep, float* out,
+               cudaStream_t s) override {
+    gen::RealSource src{in, 0, 0, 0, 0};
+    LMVN_TRY(rows_fwd(src, work, s));
+    LMVN_TRY(strided(work, nullptr, 1, fast::SM_FWD, 1.f, s));
+    LMVN_TRY(strided(work, khat, 0, fast::SM_FWD_MUL_INV, 1.f, s));
+    LMVN_TRY(strided(work, nullptr, 1, fast::SM_INV, 1.f, s));
+    LMVN_TRY(rows_inv(work, out, ep, s));
+    return 0;
+  }
+};
+
+bool axis_ok(int n) { return n == 16 || n == 32 || n == 64 || n == 128 || n == 256 || n == 512; }
+
+}  // namespace
+
+std::unique_ptr<ConvEngine> make_fused_engine(std::shared_ptr<FftPlan> plan) {
+  const int nx = plan->nx;
+  if (!(nx == 64 || nx == 128 || nx == 256)) return nullptr;
+  if (!axis_ok(plan->ny) || !axis_ok(plan->nz)) return nullptr;
+  const size_t rows = size_t(plan->nz) * plan->ny;
+  if (rows % 128 != 0) return nullptr;
+  std::unique_ptr<FastEngine> e(new FastEngine());
+  e->plan = plan;
+  if (cudaSetDevice(plan->device) != cudaSuccess) return nullptr;
+  if (e->init() != 0) return nullptr;
+  return std::unique_ptr<ConvEngine>(e.release());
+}
+
+}  // namespace lmvn

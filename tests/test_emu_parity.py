@@ -94,3 +94,59 @@ def test_cpu_entry_points_match_oracle(L):
     im = d["views"][0].copy()
     L.inplace_cpu_convolution(im, d["kernels1"][0], nthreads=1)
     assert pc.rel_l2(im, orc.inplace_cpu_convolution(d["views"][0], d["kernels1"][0])) < 1e-5
+
+
+# ---- power-of-two fast path (strategy "fused"): every template instantiation ----
+@pytest.fixture()
+def LF(L):
+    from libmultiviewnative_b200 import capi
+
+    L.set_default_strategy(capi.STRATEGY_FUSED)
+    yield L
+    L.set_default_strategy(capi.STRATEGY_AUTO)
+
+
+@pytest.mark.parametrize("dims,kdims", [
+    ((16, 16, 64), (5, 5, 5)), ((32, 64, 128), (7, 4, 3)), ((64, 16, 256), (3, 3, 9)), ((16, 128, 64), (5, 5, 5)),
+    ((256, 16, 64), (5, 5, 5)), ((16, 512, 64), (3, 9, 3)), ((512, 16, 64), (9, 3, 3)), ((16, 16, 64), (16, 16, 64)),
+])
+def test_fused_conv_random(LF, dims, kdims):
+    pc.case_conv_random_vs_oracle(LF, dims, kdims)
+
+
+def test_fused_strategy_is_selected_and_rejected(L, LF):
+    from libmultiviewnative_b200 import capi
+
+    with LF.plan((16, 16, 64), 1) as p:
+        assert p.info().strategy == capi.STRATEGY_FUSED
+    with pytest.raises(capi.LmvnError):
+        LF.plan((10, 10, 10), 1)  # not a power of two: no fused plan
+    L.set_default_strategy(capi.STRATEGY_AUTO)
+    with L.plan((10, 10, 10), 1) as p:
+        assert p.info().strategy == capi.STRATEGY_GENERIC
+    with L.plan((16, 16, 64), 1) as p:
+        assert p.info().strategy == capi.STRATEGY_FUSED
+
+
+@pytest.mark.parametrize("lam", [0.0, 0.006])
+def test_fused_deconvolve_vs_oracle(LF, lam):
+    pc.case_deconvolve_vs_oracle(LF, (16, 32, 64), 3, 7, lam, iters_list=(1, 3), n_sources=10)
+
+
+def test_fused_deconvolve_nx128(LF):
+    pc.case_deconvolve_vs_oracle(LF, (16, 16, 128), 2, 5, 0.006, iters_list=(1,), n_sources=6)
+
+
+def test_fused_equals_generic_closely(L):
+    from libmultiviewnative_b200 import capi
+    from libmultiviewnative_b200.synthetic import make_views
+
+    d = make_views((32, 16, 64), num_views=2, kernel_size=5, n_sources=8, workers=1)
+    outs = {}
+    for strat in (capi.STRATEGY_GENERIC, capi.STRATEGY_FUSED):
+        L.set_default_strategy(strat)
+        psi = d["psi0"].copy()
+        L.inplace_gpu_deconvolve(psi, d["views"], d["kernels1"], d["kernels2"], d["weights"], 2, 0.006, 1e-4)
+        outs[strat] = psi
+    L.set_default_strategy(capi.STRATEGY_AUTO)
+    assert pc.max_rel(outs[capi.STRATEGY_FUSED], outs[capi.STRATEGY_GENERIC]) < 1e-5
