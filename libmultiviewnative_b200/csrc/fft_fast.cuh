@@ -478,10 +478,34 @@ static __global__ void __launch_bounds__(kRowThreads) k_rows_inv(RowArgs A) {
       slab[qb * 9 + j] = v[8 + j];
     }
   }
+  // Operands of the pointwise epilogue are fetched BEFORE the exchange barrier and the last
+  // butterfly so that their latency overlaps the transform (they do not depend on it); all
+  // loads of a group are issued back to back, all stores afterwards.
+  const size_t base = size_t(active ? row : 0) * nx;
+  const float2* __restrict__ op_a = nullptr;   // view (quotient) or psi (update)
+  const float2* __restrict__ op_b = nullptr;   // weights (update)
+  if (A.ep.mode == gen::EPI_QUOTIENT) op_a = reinterpret_cast<const float2*>(A.ep.view + base);
+  if (A.ep.mode == gen::EPI_UPDATE) {
+    op_a = reinterpret_cast<const float2*>(A.ep.psi + base);
+    op_b = reinterpret_cast<const float2*>(A.ep.weights + base);
+  }
+  float2 oa[R1], ob[R1];
+  auto fetch = [&](int jj) {
+    const int j = t * JPT + jj;
+    if (op_a) {
+#pragma unroll
+      for (int r = 0; r < R1; ++r) oa[r] = op_a[j + 8 * r];
+    }
+    if (op_b) {
+#pragma unroll
+      for (int r = 0; r < R1; ++r) ob[r] = op_b[j + 8 * r];
+    }
+  };
+  if (active) fetch(0);
   __syncwarp();
   if (active) {
-    float2* orow = reinterpret_cast<float2*>(A.out + row * nx);
-    const size_t base = size_t(row) * nx;
+    float2* __restrict__ orow =
+        reinterpret_cast<float2*>((A.ep.mode == gen::EPI_UPDATE ? A.ep.psi : A.out) + base);
 #pragma unroll
     for (int jj = 0; jj < JPT; ++jj) {
       const int j = t * JPT + jj;
@@ -492,26 +516,23 @@ static __global__ void __launch_bounds__(kRowThreads) k_rows_inv(RowArgs A) {
         v[jj * R1 + q] = x;
       }
       Bfly<R1, true>::run(v + jj * R1);
+      float2 res[R1];
 #pragma unroll
       for (int r = 0; r < R1; ++r) {
-        const int n = j + 8 * r;  // complex sample n = real samples 2n, 2n+1
+        // complex sample n = j + 8 r holds the real samples 2n, 2n+1
         float2 val = make_float2(v[jj * R1 + r].x * A.ep.scale, v[jj * R1 + r].y * A.ep.scale);
         if (A.ep.mode == gen::EPI_QUOTIENT) {
-          const float2 vw = reinterpret_cast<const float2*>(A.ep.view + base)[n];
-          val.x = quotient(vw.x, val.x);
-          val.y = quotient(vw.y, val.y);
-          orow[n] = val;
+          val.x = quotient(oa[r].x, val.x);
+          val.y = quotient(oa[r].y, val.y);
         } else if (A.ep.mode == gen::EPI_UPDATE) {
-          float2* pp = reinterpret_cast<float2*>(A.ep.psi + base) + n;
-          const float2 ps = *pp;
-          const float2 wt = reinterpret_cast<const float2*>(A.ep.weights + base)[n];
-          val.x = rl_update(ps.x, val.x, wt.x, A.ep.up);
-          val.y = rl_update(ps.y, val.y, wt.y, A.ep.up);
-          *pp = val;
-        } else {
-          orow[n] = val;
+          val.x = rl_update(oa[r].x, val.x, ob[r].x, A.ep.up);
+          val.y = rl_update(oa[r].y, val.y, ob[r].y, A.ep.up);
         }
+        res[r] = val;
       }
+      if (jj + 1 < JPT) fetch(jj + 1);
+#pragma unroll
+      for (int r = 0; r < R1; ++r) orow[j + 8 * r] = res[r];
     }
   }
 }

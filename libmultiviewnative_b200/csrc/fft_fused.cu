@@ -71,6 +71,10 @@ struct FastEngine : ConvEngine {
     const size_t smem = size_t(CF::ROWS) * CF::SLAB * sizeof(cplx);
     auto kw = fast::k_rows_fwd<MM, true>;
     auto kp = fast::k_rows_fwd<MM, false>;
+    if (smem > 48 * 1024) {
+      LMVN_CUDA_TRY(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      LMVN_CUDA_TRY(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    }
     if (wrapped) {
       LMVN_LAUNCH(kw, grid, dim3(fast::kRowThreads), smem, s, a);
     } else {
@@ -85,6 +89,9 @@ struct FastEngine : ConvEngine {
     const dim3 grid(unsigned(ceil_div(rows, CF::ROWS)));
     const size_t smem = size_t(CF::ROWS) * CF::SLAB * sizeof(cplx);
     auto kfn = fast::k_rows_inv<MM>;
+    if (smem > 48 * 1024) {
+      LMVN_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    }
     LMVN_LAUNCH(kfn, grid, dim3(fast::kRowThreads), smem, s, a);
     return 0;
   }
