@@ -49,9 +49,12 @@ def _stale(target: str, extra=()) -> bool:
     return any(os.path.getmtime(s) > t for s in list(_sources()) + list(extra))
 
 
-def build_cuda(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale(LIB_PATH):
-        return LIB_PATH
+def build_cuda(force: bool = False, verbose: bool = False, out: str = None, defines=()) -> str:
+    """`out` / `defines` build an experimental variant next to the product library
+    (A/B timing of compile-time knobs); the default call builds the product."""
+    target = out or LIB_PATH
+    if not force and not _stale(target):
+        return target
     os.makedirs(LIB_DIR, exist_ok=True)
     cmd = [_nvcc(), *NVCC_ARCH, "-lineinfo", "-O3", "-std=c++17", "-shared",
            "-Xcompiler", "-fPIC,-fopenmp,-fvisibility=hidden,-Wall,-Wno-unknown-pragmas",
@@ -63,15 +66,16 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     if os.path.exists(fused):
         srcs.append("fft_fused.cu")
         cmd += ["-DLMVN_HAVE_FUSED"]
+    cmd += ["-D" + d for d in defines]
     cmd += [os.path.join(CSRC, s) for s in srcs + HOST_SOURCES]
-    cmd += ["-o", LIB_PATH, "-lgomp"]
+    cmd += ["-o", target, "-lgomp"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc build of libmultiviewnative.so failed")
     if verbose:
         sys.stderr.write(res.stdout + res.stderr)
-    return LIB_PATH
+    return target
 
 
 def build_emu(force: bool = False) -> str:

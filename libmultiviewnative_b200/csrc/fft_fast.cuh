@@ -167,17 +167,24 @@ template <> struct Radix<16> { static const int S = 2, R1 = 4, R2 = 4, R3 = 1; }
 template <int N> struct Cols { static const int V = (N >= 256) ? 16 : (N >= 128 ? 32 : 64); };
 
 static const int kStridedThreads = 256;
+#ifndef LMVN_MIDDLE_UNROLL
+#define LMVN_MIDDLE_UNROLL 4
+#endif
+static const int kMiddleUnroll = LMVN_MIDDLE_UNROLL;
+#ifndef LMVN_ZMUL_BLOCKS
+#define LMVN_ZMUL_BLOCKS 2
+#endif
 
 // One DIF (forward) stage: load R inputs, butterfly, post-twiddle w_L^{jq}, store.
 // LOAD(row, col) / STORE(row, col, value) are functors over tile coordinates.
-template <int N, int R, int L, int COLS, bool INV, typename LoadF, typename StoreF>
+template <int N, int R, int L, int COLS, bool INV, int NT = kStridedThreads, typename LoadF, typename StoreF>
 __device__ __forceinline__ void strided_stage(const cplx* __restrict__ tw, LoadF load, StoreF store) {
   constexpr int M = L / R;
-  constexpr int PER_THREAD = (N / R) * COLS / kStridedThreads;
+  constexpr int PER_THREAD = (N / R) * COLS / NT;
   static_assert(PER_THREAD >= 1, "tile too small for the block");
 #pragma unroll
   for (int i = 0; i < PER_THREAD; ++i) {
-    const int w = threadIdx.x + i * kStridedThreads;
+    const int w = threadIdx.x + i * NT;
     const int c = w % COLS;
     const int bf = w / COLS;
     const int j = bf % M;
@@ -185,14 +192,19 @@ __device__ __forceinline__ void strided_stage(const cplx* __restrict__ tw, LoadF
     cplx v[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = load(b + j + r * M, c);
+    cplx t[R];  // twiddles w_L^{jq}, fetched before the butterfly so their latency hides behind it
+    if (M > 1) {
+#pragma unroll
+      for (int q = 1; q < R; ++q) t[q] = __ldg(tw + j * q * (N / L));
+    }
     if (INV && M > 1) {  // DIT: pre-twiddle with conj(w_L^{jq})
 #pragma unroll
-      for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], __ldg(tw + j * q * (N / L)));
+      for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], t[q]);
     }
     Bfly<R, INV>::run(v);
     if (!INV && M > 1) {
 #pragma unroll
-      for (int q = 1; q < R; ++q) v[q] = cmul(v[q], __ldg(tw + j * q * (N / L)));
+      for (int q = 1; q < R; ++q) v[q] = cmul(v[q], t[q]);
     }
 #pragma unroll
     for (int q = 0; q < R; ++q) store(b + j + q * M, c, v[q]);
@@ -200,12 +212,12 @@ __device__ __forceinline__ void strided_stage(const cplx* __restrict__ tw, LoadF
 }
 
 // middle of the merged z pass: last forward stage, spectrum product, first inverse stage
-template <int N, int R, int COLS, typename LoadF, typename KF, typename StoreF>
+template <int N, int R, int COLS, int NT = kStridedThreads, typename LoadF, typename KF, typename StoreF>
 __device__ __forceinline__ void strided_middle(LoadF load, KF kload, StoreF store) {
-  constexpr int PER_THREAD = (N / R) * COLS / kStridedThreads;
-#pragma unroll
+  constexpr int PER_THREAD = (N / R) * COLS / NT;
+#pragma unroll(kMiddleUnroll)
   for (int i = 0; i < PER_THREAD; ++i) {
-    const int w = threadIdx.x + i * kStridedThreads;
+    const int w = threadIdx.x + i * NT;
     const int c = w % COLS;
     const int b = (w / COLS) * R;
     cplx v[R], k[R];
@@ -223,7 +235,7 @@ __device__ __forceinline__ void strided_middle(LoadF load, KF kload, StoreF stor
 }
 
 template <int N, int MODE>
-static __global__ void __launch_bounds__(kStridedThreads, (MODE == SM_FWD_MUL_INV && N >= 64) ? 2 : 3) k_strided(StridedArgs A) {
+static __global__ void __launch_bounds__(kStridedThreads, (MODE == SM_FWD_MUL_INV && N >= 64) ? LMVN_ZMUL_BLOCKS : 3) k_strided(StridedArgs A) {
   typedef Radix<N> RX;
   constexpr int COLS = Cols<N>::V;
   constexpr int R1 = RX::R1, R2 = RX::R2, R3 = RX::R3;
@@ -236,10 +248,10 @@ static __global__ void __launch_bounds__(kStridedThreads, (MODE == SM_FWD_MUL_IN
   const long long rs = A.row_stride;
   const cplx* tw = A.tw;
 
-  auto gload = [&](int row, int c) -> cplx { return (c < nvalid) ? g[row * rs + c] : cmake(0.f, 0.f); };
-  auto gstore = [&](int row, int c, cplx v) { if (c < nvalid) g[row * rs + c] = v; };
-  auto gstore_scaled = [&](int row, int c, cplx v) { if (c < nvalid) g[row * rs + c] = cscale(v, A.scale); };
-  auto kload = [&](int row, int c) -> cplx { return (c < nvalid) ? __ldg(gk + row * rs + c) : cmake(0.f, 0.f); };
+  auto gload = [&](int row, int c) -> cplx { return (c < nvalid) ? ld_stream(g + row * rs + c) : cmake(0.f, 0.f); };
+  auto gstore = [&](int row, int c, cplx v) { if (c < nvalid) st_stream(g + row * rs + c, v); };
+  auto gstore_scaled = [&](int row, int c, cplx v) { if (c < nvalid) st_stream(g + row * rs + c, cscale(v, A.scale)); };
+  auto kload = [&](int row, int c) -> cplx { return (c < nvalid) ? ld_stream(gk + row * rs + c) : cmake(0.f, 0.f); };
   auto sload = [&](int row, int c) -> cplx { return sm[row * COLS + c]; };
   auto sstore = [&](int row, int c, cplx v) { sm[row * COLS + c] = v; };
 
@@ -280,6 +292,131 @@ static __global__ void __launch_bounds__(kStridedThreads, (MODE == SM_FWD_MUL_IN
     __syncthreads();
     strided_stage<N, R1, N, COLS, true>(tw, sload, gstore);
   }
+}
+
+// ------------------------------------------------------------------------------
+// asynchronous global -> shared copies (LDGSTS).  16 bytes per call, L2 only.
+// ------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+#ifdef LMVN_EMU
+  std::memcpy(smem_dst, gsrc, 16);
+#else
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef LMVN_EMU
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+#endif
+}
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() {
+#ifndef LMVN_EMU
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING) : "memory");
+#endif
+}
+
+// ------------------------------------------------------------------------------
+// pipelined strided pass: persistent CTAs, tile i+1 streams into the second
+// shared-memory buffer (cp.async) while tile i is transformed in place in the first.
+// For the merged z pass the K^ tile streams into a third buffer during the first
+// two forward stages.  One CTA per SM for N = 512 (3 x 64 KiB).
+// ------------------------------------------------------------------------------
+template <int N> struct PipeThreads { static const int V = (N >= 512) ? 512 : 256; };
+
+template <int N, int MODE>
+static __global__ void __launch_bounds__(PipeThreads<N>::V, (N >= 512) ? 1 : 2) k_strided_pipe(StridedArgs A, int nchunks, int ntiles) {
+  typedef Radix<N> RX;
+  constexpr int NT = PipeThreads<N>::V;
+  constexpr int COLS = Cols<N>::V;
+  constexpr int R1 = RX::R1, R2 = RX::R2, R3 = RX::R3;
+  constexpr int R3E = (R3 > 1 ? R3 : 2);
+  constexpr int L2 = N / R1, L3 = (R3 > 1 ? N / (R1 * R2) : 2);
+  constexpr int PIECES = COLS / 2;  // 16-byte pieces per tile row
+  LMVN_DYN_SMEM(cplx, sm);
+  cplx* const buf0 = sm;
+  cplx* const buf1 = sm + N * COLS;
+  cplx* const kbuf = sm + 2 * N * COLS;
+  const long long rs = A.row_stride;
+  const cplx* tw = A.tw;
+
+  auto issue_tile = [&](int tile, cplx* dst, const cplx* base) {
+    const int chunk = tile % nchunks, slow = tile / nchunks;
+    const cplx* g = base + (long long)slow * A.tile_stride + chunk * COLS;
+    for (int w = threadIdx.x; w < N * PIECES; w += NT) {
+      const int row = w / PIECES, pc = w % PIECES;
+      if (chunk * COLS + pc * 2 < A.ncols) cp_async16(dst + row * COLS + pc * 2, g + row * rs + pc * 2);
+    }
+  };
+
+  int tile = blockIdx.x;
+  if (tile < ntiles) issue_tile(tile, buf0, A.data);
+  cp_async_commit();
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    cplx* const cur = (it & 1) ? buf1 : buf0;
+    cplx* const nxt = (it & 1) ? buf0 : buf1;
+    if (MODE == SM_FWD_MUL_INV) {
+      issue_tile(tile, kbuf, A.khat);
+      cp_async_commit();
+    }
+    const int next = tile + gridDim.x;
+    if (next < ntiles) issue_tile(next, nxt, A.data);
+    cp_async_commit();
+    if (MODE == SM_FWD_MUL_INV) cp_async_wait<2>();
+    else cp_async_wait<1>();
+    __syncthreads();
+
+    const int chunk = tile % nchunks, slow = tile / nchunks;
+    cplx* g = A.data + (long long)slow * A.tile_stride + chunk * COLS;
+    const int nvalid = A.ncols - chunk * COLS;
+    auto gstore = [&](int row, int c, cplx v) { if (c < nvalid) st_stream(g + row * rs + c, v); };
+    auto gstore_scaled = [&](int row, int c, cplx v) { if (c < nvalid) st_stream(g + row * rs + c, cscale(v, A.scale)); };
+    auto sload = [&](int row, int c) -> cplx { return cur[row * COLS + c]; };
+    auto sstore = [&](int row, int c, cplx v) { cur[row * COLS + c] = v; };
+    auto kload = [&](int row, int c) -> cplx { return kbuf[row * COLS + c]; };
+
+    if (MODE == SM_FWD || MODE == SM_FWD_SCALE) {
+      strided_stage<N, R1, N, COLS, false, NT>(tw, sload, sstore);
+      __syncthreads();
+      if (RX::S == 3) {
+        strided_stage<N, R2, L2, COLS, false, NT>(tw, sload, sstore);
+        __syncthreads();
+        if (MODE == SM_FWD) strided_stage<N, R3E, L3, COLS, false, NT>(tw, sload, gstore);
+        else strided_stage<N, R3E, L3, COLS, false, NT>(tw, sload, gstore_scaled);
+      } else {
+        if (MODE == SM_FWD) strided_stage<N, R2, L2, COLS, false, NT>(tw, sload, gstore);
+        else strided_stage<N, R2, L2, COLS, false, NT>(tw, sload, gstore_scaled);
+      }
+    } else if (MODE == SM_INV) {
+      if (RX::S == 3) {
+        strided_stage<N, R3E, L3, COLS, true, NT>(tw, sload, sstore);
+        __syncthreads();
+      }
+      strided_stage<N, R2, L2, COLS, true, NT>(tw, sload, sstore);
+      __syncthreads();
+      strided_stage<N, R1, N, COLS, true, NT>(tw, sload, gstore);
+    } else {
+      strided_stage<N, R1, N, COLS, false, NT>(tw, sload, sstore);
+      __syncthreads();
+      if (RX::S == 3) {
+        strided_stage<N, R2, L2, COLS, false, NT>(tw, sload, sstore);
+        cp_async_wait<1>();  // the K^ tile has landed (only the next data tile may be pending)
+        __syncthreads();
+        strided_middle<N, R3E, COLS, NT>(sload, kload, sstore);
+        __syncthreads();
+        strided_stage<N, R2, L2, COLS, true, NT>(tw, sload, sstore);
+      } else {
+        cp_async_wait<1>();
+        __syncthreads();
+        strided_middle<N, R2, COLS, NT>(sload, kload, sstore);
+      }
+      __syncthreads();
+      strided_stage<N, R1, N, COLS, true, NT>(tw, sload, gstore);
+    }
+    __syncthreads();  // every read of `cur` (and kbuf) is done before the next prefetch overwrites it
+  }
+  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------

@@ -8,7 +8,9 @@
 //                                  stage share registers
 //   strided y inverse   C -> C
 //   rows_inv            C(+S..) -> S   inverse along x + quotient / RL update
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "engine.cuh"
@@ -22,6 +24,8 @@ bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 struct FastEngine : ConvEngine {
   int M = 0, nxc = 0, nxp = 0;
+  int num_sms = 148;
+  bool use_pipe = false;
   cplx* d_tw_m = nullptr;
   cplx* d_tw_nx = nullptr;
   cplx* d_tw_y = nullptr;
@@ -55,6 +59,11 @@ struct FastEngine : ConvEngine {
     M = plan->nx / 2;
     nxc = plan->nxc;
     nxp = (nxc + 15) / 16 * 16;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, plan->device) == cudaSuccess && prop.multiProcessorCount > 0)
+      num_sms = prop.multiProcessorCount;
+    const char* e = getenv("LMVN_PIPE");
+    use_pipe = (e && *e == '1');  // experimental persistent double-buffered variant, off by default
     LMVN_TRY(upload_table(&d_tw_m, M, M));
     LMVN_TRY(upload_table(&d_tw_nx, plan->nx, M + 1));
     LMVN_TRY(upload_table(&d_tw_y, plan->ny, plan->ny));
@@ -66,7 +75,7 @@ struct FastEngine : ConvEngine {
   template <int MM>
   int launch_rows_fwd(const fast::RowArgs& a, bool wrapped, cudaStream_t s) {
     typedef fast::RowCfg<MM> CF;
-    const size_t rows = size_t(plan->nz) * plan->ny;
+    const size_t rows = size_t(a.nz) * plan->ny;
     const dim3 grid(unsigned(ceil_div(rows, CF::ROWS)));
     const size_t smem = size_t(CF::ROWS) * CF::SLAB * sizeof(cplx);
     auto kw = fast::k_rows_fwd<MM, true>;
@@ -85,7 +94,7 @@ struct FastEngine : ConvEngine {
   template <int MM>
   int launch_rows_inv(const fast::RowArgs& a, cudaStream_t s) {
     typedef fast::RowCfg<MM> CF;
-    const size_t rows = size_t(plan->nz) * plan->ny;
+    const size_t rows = size_t(a.nz) * plan->ny;
     const dim3 grid(unsigned(ceil_div(rows, CF::ROWS)));
     const size_t smem = size_t(CF::ROWS) * CF::SLAB * sizeof(cplx);
     auto kfn = fast::k_rows_inv<MM>;
@@ -96,12 +105,16 @@ struct FastEngine : ConvEngine {
     return 0;
   }
 
-  int rows_fwd(const gen::RealSource& src, cplx* spec, cudaStream_t s) {
+  // z0/nzs select a slab of planes (whole volume by default); wrapped sources are whole-volume only
+  int rows_fwd(const gen::RealSource& src_in, cplx* spec, cudaStream_t s, int z0 = 0, int nzs = -1) {
+    if (nzs < 0) nzs = plan->nz;
     fast::RowArgs a;
     std::memset(&a, 0, sizeof(a));
+    gen::RealSource src = src_in;
+    if (!src.wrapped) src.data += size_t(z0) * plan->ny * plan->nx;
     a.src = src;
-    a.spec = spec;
-    a.nz = plan->nz; a.ny = plan->ny; a.nxp = nxp;
+    a.spec = spec + size_t(z0) * plan->ny * nxp;
+    a.nz = nzs; a.ny = plan->ny; a.nxp = nxp;
     a.tw_m = d_tw_m; a.tw_nx = d_tw_nx;
     const bool w = src.wrapped != 0;
     switch (M) {
@@ -115,13 +128,19 @@ struct FastEngine : ConvEngine {
     return 0;
   }
 
-  int rows_inv(const cplx* spec, float* out, const gen::Epilogue& ep, cudaStream_t s) {
+  int rows_inv(const cplx* spec, float* out, const gen::Epilogue& ep_in, cudaStream_t s, int z0 = 0, int nzs = -1) {
+    if (nzs < 0) nzs = plan->nz;
     fast::RowArgs a;
     std::memset(&a, 0, sizeof(a));
-    a.spec = const_cast<cplx*>(spec);
-    a.out = out;
+    const size_t voff = size_t(z0) * plan->ny * plan->nx;
+    gen::Epilogue ep = ep_in;
+    if (ep.view) ep.view += voff;
+    if (ep.psi) ep.psi += voff;
+    if (ep.weights) ep.weights += voff;
+    a.spec = const_cast<cplx*>(spec) + size_t(z0) * plan->ny * nxp;
+    a.out = out ? out + voff : out;
     a.ep = ep;
-    a.nz = plan->nz; a.ny = plan->ny; a.nxp = nxp;
+    a.nz = nzs; a.ny = plan->ny; a.nxp = nxp;
     a.tw_m = d_tw_m; a.tw_nx = d_tw_nx;
     switch (M) {
       case 32: LMVN_TRY(launch_rows_inv<32>(a, s)); break;
@@ -139,6 +158,18 @@ struct FastEngine : ConvEngine {
   template <int N, int MODE>
   int launch_strided(const fast::StridedArgs& a, dim3 grid, cudaStream_t s) {
     constexpr int COLS = fast::Cols<N>::V;
+    if (use_pipe && N >= 64) {
+      // persistent, double-buffered variant: grid = resident CTAs
+      const size_t tile_b = size_t(N) * COLS * sizeof(cplx);
+      const size_t psmem = tile_b * (MODE == fast::SM_FWD_MUL_INV ? 3 : 2);
+      const int per_sm = int(std::max<size_t>(1, std::min<size_t>(N >= 512 ? 1 : 2, (200 * 1024) / psmem)));
+      const int nchunks = int(grid.x), ntiles = int(grid.x * grid.y);
+      const int ctas = std::min(ntiles, num_sms * per_sm);
+      auto kp = fast::k_strided_pipe<N, MODE>;
+      LMVN_CUDA_TRY(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, int(psmem)));
+      LMVN_LAUNCH(kp, dim3(unsigned(ctas)), dim3(fast::PipeThreads<N>::V), psmem, s, a, nchunks, ntiles);
+      return 0;
+    }
     const size_t smem = size_t(N) * COLS * sizeof(cplx);
     auto kfn = fast::k_strided<N, MODE>;
     if (smem > 48 * 1024) {  // per device, cheap: set every time
@@ -158,9 +189,11 @@ struct FastEngine : ConvEngine {
   }
 
   // axis 1 = y, axis 0 = z
-  int strided(cplx* data, const cplx* khat, int axis, int mode, float scale, cudaStream_t s) {
+  int strided(cplx* data, const cplx* khat, int axis, int mode, float scale, cudaStream_t s, int z0 = 0,
+              int nzs = -1) {
     const FftPlan& p = *plan;
     fast::StridedArgs a;
+    if (axis == 1 && nzs >= 0) data += size_t(z0) * p.ny * nxp;  // y pass on a slab of planes
     a.data = data;
     a.khat = khat;
     a.ncols = nxc;
@@ -168,7 +201,7 @@ struct FastEngine : ConvEngine {
     int n;
     unsigned slow;
     if (axis == 1) {
-      n = p.ny; a.row_stride = nxp; a.tile_stride = (long long)p.ny * nxp; slow = unsigned(p.nz); a.tw = d_tw_y;
+      n = p.ny; a.row_stride = nxp; a.tile_stride = (long long)p.ny * nxp; slow = unsigned(nzs >= 0 ? nzs : p.nz); a.tw = d_tw_y;
     } else {
       n = p.nz; a.row_stride = (long long)p.ny * nxp; a.tile_stride = nxp; slow = unsigned(p.ny); a.tw = d_tw_z;
     }
@@ -207,11 +240,23 @@ struct FastEngine : ConvEngine {
   int convolve(const float* in, cplx* work, const cplx* khat, const gen::Epilogue& ep, float* out,
                cudaStream_t s) override {
     gen::RealSource src{in, 0, 0, 0, 0};
-    LMVN_TRY(rows_fwd(src, work, s));
-    LMVN_TRY(strided(work, nullptr, 1, fast::SM_FWD, 1.f, s));
+    static int slabs = -1;
+    if (slabs < 0) {
+      const char* e = getenv("LMVN_SLABS");
+      slabs = e ? atoi(e) : 1;
+      if (slabs < 1) slabs = 1;
+    }
+    const int ns = (plan->nz % slabs == 0) ? slabs : 1;
+    const int nzs = plan->nz / ns;
+    for (int i = 0; i < ns; ++i) {
+      LMVN_TRY(rows_fwd(src, work, s, i * nzs, nzs));
+      LMVN_TRY(strided(work, nullptr, 1, fast::SM_FWD, 1.f, s, i * nzs, nzs));
+    }
     LMVN_TRY(strided(work, khat, 0, fast::SM_FWD_MUL_INV, 1.f, s));
-    LMVN_TRY(strided(work, nullptr, 1, fast::SM_INV, 1.f, s));
-    LMVN_TRY(rows_inv(work, out, ep, s));
+    for (int i = 0; i < ns; ++i) {
+      LMVN_TRY(strided(work, nullptr, 1, fast::SM_INV, 1.f, s, i * nzs, nzs));
+      LMVN_TRY(rows_inv(work, out, ep, s, i * nzs, nzs));
+    }
     return 0;
   }
 };

@@ -29,8 +29,21 @@ namespace lmvn {
 typedef float2 cplx;
 
 __host__ __device__ __forceinline__ cplx cmake(float re, float im) { return make_float2(re, im); }
-__host__ __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_float2(a.x + b.x, a.y + b.y); }
-__host__ __device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_float2(a.x - b.x, a.y - b.y); }
+// complex add / sub: on sm_100 one packed FP32x2 instruction each (FADD2 / FFMA2)
+__host__ __device__ __forceinline__ cplx cadd(cplx a, cplx b) {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+  return __fadd2_rn(a, b);
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+__host__ __device__ __forceinline__ cplx csub(cplx a, cplx b) {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+  return __ffma2_rn(b, make_float2(-1.f, -1.f), a);
+#else
+  return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
 __host__ __device__ __forceinline__ cplx cmul(cplx a, cplx b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -43,6 +56,22 @@ __host__ __device__ __forceinline__ cplx cscale(cplx a, float s) { return make_f
 // multiply by -i (forward quarter turn) and +i
 __host__ __device__ __forceinline__ cplx cmul_mi(cplx a) { return make_float2(a.y, -a.x); }
 __host__ __device__ __forceinline__ cplx cmul_pi(cplx a) { return make_float2(-a.y, a.x); }
+
+// streaming global accesses: L2 only, keep L1 for the twiddle tables
+__device__ __forceinline__ cplx ld_stream(const cplx* p) {
+#ifdef LMVN_EMU
+  return *p;
+#else
+  return __ldcg(p);
+#endif
+}
+__device__ __forceinline__ void st_stream(cplx* p, cplx v) {
+#ifdef LMVN_EMU
+  *p = v;
+#else
+  __stcg(p, v);
+#endif
+}
 
 // ---- error plumbing: nothing in this library exits or throws across the ABI ----
 void set_last_error(const char* fmt, ...);
