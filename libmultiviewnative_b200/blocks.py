@@ -1,0 +1,89 @@
+"""Sharding of independent deconvolution blocks over the GPUs of one box.
+
+The reference has no multi-GPU path; Fiji tiles a large acquisition into blocks
+and calls ``inplace_gpu_deconvolve`` once per block.
+Blocks are independent units, so the multi-GPU path is pure sharding -- block b
+runs on GPU ``b mod G`` -- with NO collective on the data path.  Two drivers:
+
+* ``run_sharded``: one process per GPU (torchrun / torch.distributed), each rank
+  deconvolves its shard; results are optionally gathered on rank 0 for checking.
+* ``run_threads``: one process, one host thread per GPU (the C library is
+  re-entrant per device and ctypes releases the GIL during the call).
+"""
+from __future__ import annotations
+
+import threading
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+
+
+def shard(n_blocks: int, rank: int, world: int) -> List[int]:
+    """Indices of the blocks rank ``rank`` of ``world`` owns (round robin)."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("invalid rank/world")
+    return list(range(rank, n_blocks, world))
+
+
+def deconvolve_block(lib, block: dict, num_iterations: int, lam: float, min_value: float, device: int) -> np.ndarray:
+    """One block through the reference-facing entry point; returns the new psi."""
+    psi = np.array(block["psi0"], dtype=np.float32, copy=True)
+    lib.inplace_gpu_deconvolve(psi, block["views"], block["kernels1"], block["kernels2"], block["weights"],
+                               num_iterations, lam, min_value, device)
+    return psi
+
+
+def run_shard(lib, make_block: Callable[[int], dict], n_blocks: int, rank: int, world: int, num_iterations: int,
+              lam: float, min_value: float, device: int, keep: bool = True) -> Dict[int, Optional[np.ndarray]]:
+    out: Dict[int, Optional[np.ndarray]] = {}
+    for b in shard(n_blocks, rank, world):
+        res = deconvolve_block(lib, make_block(b), num_iterations, lam, min_value, device)
+        out[b] = res if keep else None
+    return out
+
+
+def run_sharded(lib, make_block: Callable[[int], dict], n_blocks: int, num_iterations: int, lam: float,
+                min_value: float, device: Optional[int] = None, gather: bool = False):
+    """Every rank of the initialised torch.distributed group processes its shard.
+    No data-path collective; ``gather=True`` collects the results on rank 0 (testing)."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(), dist.get_world_size()
+    else:
+        rank, world = 0, 1
+    dev = rank if device is None else device
+    mine = run_shard(lib, make_block, n_blocks, rank, world, num_iterations, lam, min_value, dev, keep=gather)
+    if not gather or world == 1:
+        return mine
+    gathered: List[Optional[dict]] = [None] * world
+    dist.gather_object(mine, gathered if rank == 0 else None, dst=0)
+    if rank != 0:
+        return None
+    merged: Dict[int, np.ndarray] = {}
+    for part in gathered:
+        merged.update(part)
+    return merged
+
+
+def run_threads(lib, blocks: Sequence[dict], devices: Sequence[int], num_iterations: int, lam: float,
+                min_value: float) -> List[np.ndarray]:
+    """Single process: block b on devices[b mod G], one host thread per device."""
+    results: List[Optional[np.ndarray]] = [None] * len(blocks)
+    errors: List[BaseException] = []
+
+    def worker(slot: int):
+        try:
+            for b in shard(len(blocks), slot, len(devices)):
+                results[b] = deconvolve_block(lib, blocks[b], num_iterations, lam, min_value, devices[slot])
+        except BaseException as exc:  # surfaced to the caller below
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(devices))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return results  # type: ignore[return-value]
