@@ -145,13 +145,14 @@ struct Bfly<16, INV> {
 enum StridedMode { SM_FWD = 0, SM_INV = 1, SM_FWD_MUL_INV = 2, SM_FWD_SCALE = 3 };
 
 struct StridedArgs {
-  cplx* data;          // spectrum, in place
-  const cplx* khat;    // SM_FWD_MUL_INV: same layout as data
-  long long row_stride;    // complex elements between consecutive transform rows
-  long long tile_stride;   // between consecutive tiles of the slow tile index (blockIdx.y)
-  int ncols;           // valid kx columns (nx/2+1)
-  const cplx* tw;      // w_N table, N entries
-  float scale;         // SM_FWD_SCALE
+  cplx* data;             // spectrum, in place
+  const cplx* khat;       // SM_FWD_MUL_INV: same layout as data
+  int row_stride;         // complex elements between consecutive transform rows (fits 32 bits)
+  long long tile_stride;  // between consecutive tiles of the slow tile index (blockIdx.y)
+  int ncols;              // valid kx columns (nx/2+1)
+  const cplx* tw1;        // stage-1 twiddles, [j][q] = w_N^{jq},      j < N/R1, q < R1
+  const cplx* tw2;        // stage-2 twiddles, [j][q] = w_{N/R1}^{jq}, j < N/(R1 R2), q < R2
+  float scale;            // SM_FWD_SCALE
 };
 
 // number of stages and the radix of stage s for N = R1*R2*R3
@@ -167,37 +168,57 @@ template <> struct Radix<16> { static const int S = 2, R1 = 4, R2 = 4, R3 = 1; }
 template <int N> struct Cols { static const int V = (N >= 256) ? 16 : (N >= 128 ? 32 : 64); };
 
 static const int kStridedThreads = 256;
-#ifndef LMVN_MIDDLE_UNROLL
-#define LMVN_MIDDLE_UNROLL 4
-#endif
-static const int kMiddleUnroll = LMVN_MIDDLE_UNROLL;
 #ifndef LMVN_ZMUL_BLOCKS
 #define LMVN_ZMUL_BLOCKS 2
 #endif
+#ifndef LMVN_ZMUL_UNROLL
+#define LMVN_ZMUL_UNROLL 1
+#endif
+#ifndef LMVN_Y_UNROLL
+#define LMVN_Y_UNROLL 8
+#endif
 
-// One DIF (forward) stage: load R inputs, butterfly, post-twiddle w_L^{jq}, store.
-// LOAD(row, col) / STORE(row, col, value) are functors over tile coordinates.
-template <int N, int R, int L, int COLS, bool INV, int NT = kStridedThreads, typename LoadF, typename StoreF>
-__device__ __forceinline__ void strided_stage(const cplx* __restrict__ tw, LoadF load, StoreF store) {
+enum Where { W_SMEM = 0, W_GLOBAL = 1, W_GLOBAL_SCALED = 2 };
+
+// One radix-R stage of span L on the thread's column.  Forward (INV = false) is a
+// decimation-in-frequency stage (butterfly, then twiddle w_L^{jq}); inverse is the
+// decimation-in-time mirror (conjugate twiddle, then butterfly).  `sm` and `g`
+// already point at this thread's column; rows are addressed with 32-bit offsets.
+template <int N, int R, int L, int COLS, bool INV, int SRC, int DST, int UNROLL = 8>
+__device__ __forceinline__ void strided_stage(cplx* __restrict__ sm, cplx* __restrict__ g, int rs,
+                                              const cplx* __restrict__ tws, float scale) {
   constexpr int M = L / R;
-  constexpr int PER_THREAD = (N / R) * COLS / NT;
+  constexpr int RG = kStridedThreads / COLS;   // row groups per block
+  constexpr int PER_THREAD = (N / R) / RG;
   static_assert(PER_THREAD >= 1, "tile too small for the block");
-#pragma unroll
+  const int rg = threadIdx.x / COLS;
+  // UNROLL bounds how many butterflies the compiler may interleave (register pressure)
+#pragma unroll(UNROLL)
   for (int i = 0; i < PER_THREAD; ++i) {
-    const int w = threadIdx.x + i * NT;
-    const int c = w % COLS;
-    const int bf = w / COLS;
+    const int bf = rg + i * RG;
     const int j = bf % M;
-    const int b = (bf / M) * L;
+    const int row0 = (bf / M) * L + j;
     cplx v[R];
+    if (SRC == W_SMEM) {
+      const cplx* p = sm + row0 * COLS;
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = load(b + j + r * M, c);
-    cplx t[R];  // twiddles w_L^{jq}, fetched before the butterfly so their latency hides behind it
-    if (M > 1) {
+      for (int r = 0; r < R; ++r) v[r] = p[r * M * COLS];
+    } else {
+      unsigned off = unsigned(row0 * rs);
+      const unsigned step = unsigned(M * rs);
 #pragma unroll
-      for (int q = 1; q < R; ++q) t[q] = __ldg(tw + j * q * (N / L));
+      for (int r = 0; r < R; ++r) {
+        v[r] = ld_stream(g + off);
+        off += step;
+      }
     }
-    if (INV && M > 1) {  // DIT: pre-twiddle with conj(w_L^{jq})
+    cplx t[R];  // fetched before the butterfly so that their latency hides behind it
+    if (M > 1) {
+      const cplx* tp = tws + j * R;
+#pragma unroll
+      for (int q = 1; q < R; ++q) t[q] = __ldg(tp + q);
+    }
+    if (INV && M > 1) {
 #pragma unroll
       for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], t[q]);
     }
@@ -206,217 +227,106 @@ __device__ __forceinline__ void strided_stage(const cplx* __restrict__ tw, LoadF
 #pragma unroll
       for (int q = 1; q < R; ++q) v[q] = cmul(v[q], t[q]);
     }
+    if (DST == W_SMEM) {
+      cplx* p = sm + row0 * COLS;
 #pragma unroll
-    for (int q = 0; q < R; ++q) store(b + j + q * M, c, v[q]);
+      for (int q = 0; q < R; ++q) p[q * M * COLS] = v[q];
+    } else {
+      unsigned off = unsigned(row0 * rs);
+      const unsigned step = unsigned(M * rs);
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        st_stream(g + off, DST == W_GLOBAL_SCALED ? cscale(v[q], scale) : v[q]);
+        off += step;
+      }
+    }
   }
 }
 
-// middle of the merged z pass: last forward stage, spectrum product, first inverse stage
-template <int N, int R, int COLS, int NT = kStridedThreads, typename LoadF, typename KF, typename StoreF>
-__device__ __forceinline__ void strided_middle(LoadF load, KF kload, StoreF store) {
-  constexpr int PER_THREAD = (N / R) * COLS / NT;
-#pragma unroll(kMiddleUnroll)
+// middle of the merged z pass: last forward stage (span R), spectrum product, first inverse stage
+template <int N, int R, int COLS, int UNROLL = 8>
+__device__ __forceinline__ void strided_middle(cplx* __restrict__ sm, const cplx* __restrict__ gk, int rs) {
+  constexpr int RG = kStridedThreads / COLS;
+  constexpr int PER_THREAD = (N / R) / RG;
+  const int rg = threadIdx.x / COLS;
+#pragma unroll(UNROLL)
   for (int i = 0; i < PER_THREAD; ++i) {
-    const int w = threadIdx.x + i * NT;
-    const int c = w % COLS;
-    const int b = (w / COLS) * R;
+    const int row0 = (rg + i * RG) * R;
     cplx v[R], k[R];
+    unsigned off = unsigned(row0 * rs);
 #pragma unroll
-    for (int r = 0; r < R; ++r) k[r] = kload(b + r, c);
+    for (int r = 0; r < R; ++r) {
+      k[r] = ld_stream(gk + off);
+      off += unsigned(rs);
+    }
+    cplx* p = sm + row0 * COLS;
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = load(b + r, c);
+    for (int r = 0; r < R; ++r) v[r] = p[r * COLS];
     Bfly<R, false>::run(v);
 #pragma unroll
     for (int r = 0; r < R; ++r) v[r] = cmul(v[r], k[r]);
     Bfly<R, true>::run(v);
 #pragma unroll
-    for (int r = 0; r < R; ++r) store(b + r, c, v[r]);
+    for (int r = 0; r < R; ++r) p[r * COLS] = v[r];
   }
 }
 
 template <int N, int MODE>
-static __global__ void __launch_bounds__(kStridedThreads, (MODE == SM_FWD_MUL_INV && N >= 64) ? LMVN_ZMUL_BLOCKS : 3) k_strided(StridedArgs A) {
+static __global__ void __launch_bounds__(kStridedThreads, (MODE == SM_FWD_MUL_INV && N >= 64) ? LMVN_ZMUL_BLOCKS : 3)
+    k_strided(StridedArgs A) {
   typedef Radix<N> RX;
   constexpr int COLS = Cols<N>::V;
-  constexpr int R1 = RX::R1, R2 = RX::R2, R3 = RX::R3;
-  constexpr int L2 = N / R1, L3 = N / (R1 * R2);
-  LMVN_DYN_SMEM(cplx, sm);  // [N][COLS]
-  const int col0 = blockIdx.x * COLS;
-  cplx* g = A.data + (long long)blockIdx.y * A.tile_stride + col0;
-  const cplx* gk = (MODE == SM_FWD_MUL_INV) ? A.khat + (long long)blockIdx.y * A.tile_stride + col0 : nullptr;
-  const int nvalid = A.ncols - col0;  // columns c < nvalid are real data
-  const long long rs = A.row_stride;
-  const cplx* tw = A.tw;
+  constexpr int R1 = RX::R1, R2 = RX::R2;
+  constexpr int R3 = (RX::R3 > 1 ? RX::R3 : 2);  // placeholder radix for the dead 3-stage code of 2-stage sizes
+  constexpr int L2 = N / R1, L3 = (RX::S == 3 ? N / (R1 * R2) : 2);
+  constexpr int DSTG = (MODE == SM_FWD_SCALE) ? W_GLOBAL_SCALED : W_GLOBAL;
+  LMVN_DYN_SMEM(cplx, smem);  // [N][COLS]
+  const int c = threadIdx.x % COLS;
+  const int col = blockIdx.x * COLS + c;
+  // ragged last tile: threads of the padding columns leave; barriers count live threads only
+  if (col >= A.ncols) return;
+  cplx* g = A.data + (long long)blockIdx.y * A.tile_stride + col;
+  const cplx* gk = A.khat + (long long)blockIdx.y * A.tile_stride + col;
+  cplx* sm = smem + c;
+  const int rs = A.row_stride;
 
-  auto gload = [&](int row, int c) -> cplx { return (c < nvalid) ? ld_stream(g + row * rs + c) : cmake(0.f, 0.f); };
-  auto gstore = [&](int row, int c, cplx v) { if (c < nvalid) st_stream(g + row * rs + c, v); };
-  auto gstore_scaled = [&](int row, int c, cplx v) { if (c < nvalid) st_stream(g + row * rs + c, cscale(v, A.scale)); };
-  auto kload = [&](int row, int c) -> cplx { return (c < nvalid) ? ld_stream(gk + row * rs + c) : cmake(0.f, 0.f); };
-  auto sload = [&](int row, int c) -> cplx { return sm[row * COLS + c]; };
-  auto sstore = [&](int row, int c, cplx v) { sm[row * COLS + c] = v; };
-
+  constexpr int UY = LMVN_Y_UNROLL;
   if (MODE == SM_FWD || MODE == SM_FWD_SCALE) {
-    strided_stage<N, R1, N, COLS, false>(tw, gload, sstore);
+    strided_stage<N, R1, N, COLS, false, W_GLOBAL, W_SMEM, UY>(sm, g, rs, A.tw1, 1.f);
     __syncthreads();
     if (RX::S == 3) {
-      strided_stage<N, R2, L2, COLS, false>(tw, sload, sstore);
+      strided_stage<N, R2, L2, COLS, false, W_SMEM, W_SMEM, UY>(sm, g, rs, A.tw2, 1.f);
       __syncthreads();
-      if (MODE == SM_FWD) strided_stage<N, (R3 > 1 ? R3 : 2), (R3 > 1 ? L3 : 2), COLS, false>(tw, sload, gstore);
-      else strided_stage<N, (R3 > 1 ? R3 : 2), (R3 > 1 ? L3 : 2), COLS, false>(tw, sload, gstore_scaled);
+      strided_stage<N, R3, L3, COLS, false, W_SMEM, DSTG, UY>(sm, g, rs, nullptr, A.scale);
     } else {
-      if (MODE == SM_FWD) strided_stage<N, R2, L2, COLS, false>(tw, sload, gstore);
-      else strided_stage<N, R2, L2, COLS, false>(tw, sload, gstore_scaled);
+      strided_stage<N, R2, L2, COLS, false, W_SMEM, DSTG, UY>(sm, g, rs, A.tw2, A.scale);
     }
   } else if (MODE == SM_INV) {
     if (RX::S == 3) {
-      strided_stage<N, (R3 > 1 ? R3 : 2), (R3 > 1 ? L3 : 2), COLS, true>(tw, gload, sstore);
+      strided_stage<N, R3, L3, COLS, true, W_GLOBAL, W_SMEM, UY>(sm, g, rs, nullptr, 1.f);
       __syncthreads();
-      strided_stage<N, R2, L2, COLS, true>(tw, sload, sstore);
+      strided_stage<N, R2, L2, COLS, true, W_SMEM, W_SMEM, UY>(sm, g, rs, A.tw2, 1.f);
     } else {
-      strided_stage<N, R2, L2, COLS, true>(tw, gload, sstore);
+      strided_stage<N, R2, L2, COLS, true, W_GLOBAL, W_SMEM, UY>(sm, g, rs, A.tw2, 1.f);
     }
     __syncthreads();
-    strided_stage<N, R1, N, COLS, true>(tw, sload, gstore);
+    strided_stage<N, R1, N, COLS, true, W_SMEM, W_GLOBAL, UY>(sm, g, rs, A.tw1, 1.f);
   } else {  // SM_FWD_MUL_INV
-    strided_stage<N, R1, N, COLS, false>(tw, gload, sstore);
+    constexpr int U = LMVN_ZMUL_UNROLL;
+    strided_stage<N, R1, N, COLS, false, W_GLOBAL, W_SMEM, U>(sm, g, rs, A.tw1, 1.f);
     __syncthreads();
     if (RX::S == 3) {
-      strided_stage<N, R2, L2, COLS, false>(tw, sload, sstore);
+      strided_stage<N, R2, L2, COLS, false, W_SMEM, W_SMEM, U>(sm, g, rs, A.tw2, 1.f);
       __syncthreads();
-      strided_middle<N, (R3 > 1 ? R3 : 2), COLS>(sload, kload, sstore);
+      strided_middle<N, R3, COLS, U>(sm, gk, rs);
       __syncthreads();
-      strided_stage<N, R2, L2, COLS, true>(tw, sload, sstore);
+      strided_stage<N, R2, L2, COLS, true, W_SMEM, W_SMEM, U>(sm, g, rs, A.tw2, 1.f);
     } else {
-      strided_middle<N, R2, COLS>(sload, kload, sstore);
+      strided_middle<N, R2, COLS, U>(sm, gk, rs);
     }
     __syncthreads();
-    strided_stage<N, R1, N, COLS, true>(tw, sload, gstore);
+    strided_stage<N, R1, N, COLS, true, W_SMEM, W_GLOBAL, U>(sm, g, rs, A.tw1, 1.f);
   }
-}
-
-// ------------------------------------------------------------------------------
-// asynchronous global -> shared copies (LDGSTS).  16 bytes per call, L2 only.
-// ------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-#ifdef LMVN_EMU
-  std::memcpy(smem_dst, gsrc, 16);
-#else
-  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
-#endif
-}
-__device__ __forceinline__ void cp_async_commit() {
-#ifndef LMVN_EMU
-  asm volatile("cp.async.commit_group;\n" ::: "memory");
-#endif
-}
-template <int PENDING>
-__device__ __forceinline__ void cp_async_wait() {
-#ifndef LMVN_EMU
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING) : "memory");
-#endif
-}
-
-// ------------------------------------------------------------------------------
-// pipelined strided pass: persistent CTAs, tile i+1 streams into the second
-// shared-memory buffer (cp.async) while tile i is transformed in place in the first.
-// For the merged z pass the K^ tile streams into a third buffer during the first
-// two forward stages.  One CTA per SM for N = 512 (3 x 64 KiB).
-// ------------------------------------------------------------------------------
-template <int N> struct PipeThreads { static const int V = (N >= 512) ? 512 : 256; };
-
-template <int N, int MODE>
-static __global__ void __launch_bounds__(PipeThreads<N>::V, (N >= 512) ? 1 : 2) k_strided_pipe(StridedArgs A, int nchunks, int ntiles) {
-  typedef Radix<N> RX;
-  constexpr int NT = PipeThreads<N>::V;
-  constexpr int COLS = Cols<N>::V;
-  constexpr int R1 = RX::R1, R2 = RX::R2, R3 = RX::R3;
-  constexpr int R3E = (R3 > 1 ? R3 : 2);
-  constexpr int L2 = N / R1, L3 = (R3 > 1 ? N / (R1 * R2) : 2);
-  constexpr int PIECES = COLS / 2;  // 16-byte pieces per tile row
-  LMVN_DYN_SMEM(cplx, sm);
-  cplx* const buf0 = sm;
-  cplx* const buf1 = sm + N * COLS;
-  cplx* const kbuf = sm + 2 * N * COLS;
-  const long long rs = A.row_stride;
-  const cplx* tw = A.tw;
-
-  auto issue_tile = [&](int tile, cplx* dst, const cplx* base) {
-    const int chunk = tile % nchunks, slow = tile / nchunks;
-    const cplx* g = base + (long long)slow * A.tile_stride + chunk * COLS;
-    for (int w = threadIdx.x; w < N * PIECES; w += NT) {
-      const int row = w / PIECES, pc = w % PIECES;
-      if (chunk * COLS + pc * 2 < A.ncols) cp_async16(dst + row * COLS + pc * 2, g + row * rs + pc * 2);
-    }
-  };
-
-  int tile = blockIdx.x;
-  if (tile < ntiles) issue_tile(tile, buf0, A.data);
-  cp_async_commit();
-  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
-    cplx* const cur = (it & 1) ? buf1 : buf0;
-    cplx* const nxt = (it & 1) ? buf0 : buf1;
-    if (MODE == SM_FWD_MUL_INV) {
-      issue_tile(tile, kbuf, A.khat);
-      cp_async_commit();
-    }
-    const int next = tile + gridDim.x;
-    if (next < ntiles) issue_tile(next, nxt, A.data);
-    cp_async_commit();
-    if (MODE == SM_FWD_MUL_INV) cp_async_wait<2>();
-    else cp_async_wait<1>();
-    __syncthreads();
-
-    const int chunk = tile % nchunks, slow = tile / nchunks;
-    cplx* g = A.data + (long long)slow * A.tile_stride + chunk * COLS;
-    const int nvalid = A.ncols - chunk * COLS;
-    auto gstore = [&](int row, int c, cplx v) { if (c < nvalid) st_stream(g + row * rs + c, v); };
-    auto gstore_scaled = [&](int row, int c, cplx v) { if (c < nvalid) st_stream(g + row * rs + c, cscale(v, A.scale)); };
-    auto sload = [&](int row, int c) -> cplx { return cur[row * COLS + c]; };
-    auto sstore = [&](int row, int c, cplx v) { cur[row * COLS + c] = v; };
-    auto kload = [&](int row, int c) -> cplx { return kbuf[row * COLS + c]; };
-
-    if (MODE == SM_FWD || MODE == SM_FWD_SCALE) {
-      strided_stage<N, R1, N, COLS, false, NT>(tw, sload, sstore);
-      __syncthreads();
-      if (RX::S == 3) {
-        strided_stage<N, R2, L2, COLS, false, NT>(tw, sload, sstore);
-        __syncthreads();
-        if (MODE == SM_FWD) strided_stage<N, R3E, L3, COLS, false, NT>(tw, sload, gstore);
-        else strided_stage<N, R3E, L3, COLS, false, NT>(tw, sload, gstore_scaled);
-      } else {
-        if (MODE == SM_FWD) strided_stage<N, R2, L2, COLS, false, NT>(tw, sload, gstore);
-        else strided_stage<N, R2, L2, COLS, false, NT>(tw, sload, gstore_scaled);
-      }
-    } else if (MODE == SM_INV) {
-      if (RX::S == 3) {
-        strided_stage<N, R3E, L3, COLS, true, NT>(tw, sload, sstore);
-        __syncthreads();
-      }
-      strided_stage<N, R2, L2, COLS, true, NT>(tw, sload, sstore);
-      __syncthreads();
-      strided_stage<N, R1, N, COLS, true, NT>(tw, sload, gstore);
-    } else {
-      strided_stage<N, R1, N, COLS, false, NT>(tw, sload, sstore);
-      __syncthreads();
-      if (RX::S == 3) {
-        strided_stage<N, R2, L2, COLS, false, NT>(tw, sload, sstore);
-        cp_async_wait<1>();  // the K^ tile has landed (only the next data tile may be pending)
-        __syncthreads();
-        strided_middle<N, R3E, COLS, NT>(sload, kload, sstore);
-        __syncthreads();
-        strided_stage<N, R2, L2, COLS, true, NT>(tw, sload, sstore);
-      } else {
-        cp_async_wait<1>();
-        __syncthreads();
-        strided_middle<N, R2, COLS, NT>(sload, kload, sstore);
-      }
-      __syncthreads();
-      strided_stage<N, R1, N, COLS, true, NT>(tw, sload, gstore);
-    }
-    __syncthreads();  // every read of `cur` (and kbuf) is done before the next prefetch overwrites it
-  }
-  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------
@@ -671,6 +581,244 @@ static __global__ void __launch_bounds__(kRowThreads) k_rows_inv(RowArgs A) {
 #pragma unroll
       for (int r = 0; r < R1; ++r) orow[j + 8 * r] = res[r];
     }
+  }
+}
+
+// ------------------------------------------------------------------------------
+// x passes, second generation: every global access is a full 128-byte line.
+// M = R1 * 16.  A group of 16 lanes works on RPG = 16 / R1 rows at a time:
+//   stage 1  lane j: radix-R1 butterflies over elements j + 16 r of each row, loaded
+//            straight from global memory (16 lanes x 8 B = one line per row);
+//   exchange through a padded slab, element (q, j) at q*17 + j;
+//   stage 2  lane t: ONE radix-16 block (block t % R1 of row t / R1), no twiddles;
+//   exchange: Z in natural order;
+//   split    lane l: pairs (k, M-k), k = l + 16 i -> X[k], X[M-k], stored line by line.
+// Stage-1 and split twiddles depend on the lane only and live in registers for the
+// whole row loop.  The inverse kernel is the exact mirror and ends in the fused
+// pointwise epilogue.
+// ------------------------------------------------------------------------------
+template <int M> struct Row2Cfg {
+  static const int R1 = M / 16;           // 2, 4, 8
+  static const int RPG = 16 / R1;         // rows per 16-lane group: 8, 4, 2
+  static const int RS = M + R1;           // slab row pitch (= 17 * R1), conflict free for both layouts
+  static const int GROUPS = kRowThreads / 16;
+  static const int ROWS = GROUPS * RPG;   // rows per block iteration
+  static const int PAIRS = M / 32;        // (k, M-k) pairs per lane and row
+};
+
+template <int M, bool WRAPPED>
+static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_fwd2(RowArgs A) {
+  typedef Row2Cfg<M> CF;
+  constexpr int R1 = CF::R1, RPG = CF::RPG, RS = CF::RS, PAIRS = CF::PAIRS;
+  constexpr int nx = 2 * M;
+  LMVN_DYN_SMEM(cplx, sm);
+  const int lane = threadIdx.x % 16;
+  const int group = threadIdx.x / 16;
+  cplx* slab = sm + group * (RPG * RS);
+  const long long rows = (long long)A.nz * A.ny;
+  // lane-constant twiddles
+  cplx tw1[R1];
+#pragma unroll
+  for (int q = 1; q < R1; ++q) tw1[q] = __ldg(A.tw_m + lane * q);
+  cplx twp[PAIRS];
+#pragma unroll
+  for (int i = 0; i < PAIRS; ++i) twp[i] = __ldg(A.tw_nx + lane + 16 * i);
+  const int q_blk = lane % R1, r_blk = lane / R1;
+
+  for (long long row0 = ((long long)blockIdx.x * CF::GROUPS + group) * RPG; row0 < rows;
+       row0 += (long long)gridDim.x * CF::ROWS) {
+    cplx v[16];
+    // ---- stage 1: loads + radix-R1 ----
+#pragma unroll
+    for (int a = 0; a < RPG; ++a) {
+      const long long row = row0 + a;
+      if (!WRAPPED) {
+        const float2* in = reinterpret_cast<const float2*>(A.src.data + row * nx);
+#pragma unroll
+        for (int r = 0; r < R1; ++r) v[a * R1 + r] = ld_stream(in + lane + 16 * r);
+      } else {
+        const int z = int(row / A.ny), y = int(row % A.ny);
+        const int sz = gen::wrap_src_index(z, A.nz, A.src.kz);
+        const int sy = gen::wrap_src_index(y, A.ny, A.src.ky);
+#pragma unroll
+        for (int r = 0; r < R1; ++r) {
+          const int n = lane + 16 * r;
+          float re = 0.f, im = 0.f;
+          if (sz >= 0 && sy >= 0) {
+            const float* kr = A.src.data + (size_t(sz) * A.src.ky + sy) * A.src.kx;
+            const int s0 = gen::wrap_src_index(2 * n, nx, A.src.kx);
+            const int s1 = gen::wrap_src_index(2 * n + 1, nx, A.src.kx);
+            if (s0 >= 0) re = kr[s0];
+            if (s1 >= 0) im = kr[s1];
+          }
+          v[a * R1 + r] = cmake(re, im);
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < RPG; ++a) {
+      Bfly<R1, false>::run(v + a * R1);
+#pragma unroll
+      for (int q = 0; q < R1; ++q) {
+        cplx x = v[a * R1 + q];
+        if (q > 0) x = cmul(x, tw1[q]);
+        slab[a * RS + q * 17 + lane] = x;
+      }
+    }
+    __syncwarp();
+    // ---- stage 2: one radix-16 block per lane ----
+    {
+      const cplx* p = slab + r_blk * RS + q_blk * 17;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = p[j];
+    }
+    Bfly<16, false>::run(v);
+    __syncwarp();
+    {
+      cplx* p = slab + r_blk * RS + q_blk;  // Z[q + R1 q2] in natural order
+#pragma unroll
+      for (int q2 = 0; q2 < 16; ++q2) p[R1 * q2] = v[q2];
+    }
+    __syncwarp();
+    // ---- real-transform split + full-line stores ----
+#pragma unroll
+    for (int a = 0; a < RPG; ++a) {
+      const cplx* zr = slab + a * RS;
+      cplx* orow = A.spec + (row0 + a) * A.nxp;
+#pragma unroll
+      for (int i = 0; i < PAIRS; ++i) {
+        const int k = lane + 16 * i;
+        if (k == 0) {
+          const cplx z0 = zr[0];
+          st_stream(orow, cmake(z0.x + z0.y, 0.f));
+          st_stream(orow + M, cmake(z0.x - z0.y, 0.f));
+          st_stream(orow + M / 2, cconj(zr[M / 2]));
+        } else {
+          cplx xk, xm;
+          r2c_pair(zr[k], zr[M - k], twp[i], xk, xm);
+          st_stream(orow + k, xk);
+          st_stream(orow + (M - k), xm);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int M>
+static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_inv2(RowArgs A) {
+  typedef Row2Cfg<M> CF;
+  constexpr int R1 = CF::R1, RPG = CF::RPG, RS = CF::RS, PAIRS = CF::PAIRS;
+  constexpr int nx = 2 * M;
+  LMVN_DYN_SMEM(cplx, sm);
+  const int lane = threadIdx.x % 16;
+  const int group = threadIdx.x / 16;
+  cplx* slab = sm + group * (RPG * RS);
+  const long long rows = (long long)A.nz * A.ny;
+  cplx tw1[R1];
+#pragma unroll
+  for (int q = 1; q < R1; ++q) tw1[q] = __ldg(A.tw_m + lane * q);
+  cplx twp[PAIRS];
+#pragma unroll
+  for (int i = 0; i < PAIRS; ++i) twp[i] = __ldg(A.tw_nx + lane + 16 * i);
+  const int q_blk = lane % R1, r_blk = lane / R1;
+  const int mode = A.ep.mode;
+
+  for (long long row0 = ((long long)blockIdx.x * CF::GROUPS + group) * RPG; row0 < rows;
+       row0 += (long long)gridDim.x * CF::ROWS) {
+    // ---- spectrum loads (full lines) + inverse split into the slab, natural order ----
+    cplx xs[RPG * PAIRS], xm[RPG * PAIRS];
+    cplx xh[RPG], xn[RPG];
+#pragma unroll
+    for (int a = 0; a < RPG; ++a) {
+      const cplx* irow = A.spec + (row0 + a) * A.nxp;
+#pragma unroll
+      for (int i = 0; i < PAIRS; ++i) {
+        const int k = lane + 16 * i;
+        xs[a * PAIRS + i] = ld_stream(irow + k);
+        xm[a * PAIRS + i] = ld_stream(irow + (M - k));  // k = 0 reads X[M]
+      }
+      if (lane == 0) xh[a] = ld_stream(irow + M / 2);
+    }
+    // epilogue operands: independent of the transform, fetched now so that their latency
+    // overlaps both exchanges (element n = lane + 16 r of each row = real samples 2n, 2n+1)
+    float2 oa[16], ob[16];
+    if (mode != gen::EPI_STORE) {
+      const float* pa = (mode == gen::EPI_QUOTIENT) ? A.ep.view : A.ep.psi;
+#pragma unroll
+      for (int a = 0; a < RPG; ++a) {
+        const float2* p2 = reinterpret_cast<const float2*>(pa + (row0 + a) * nx);
+#pragma unroll
+        for (int r = 0; r < R1; ++r) oa[a * R1 + r] = ld_stream(p2 + lane + 16 * r);
+      }
+      if (mode == gen::EPI_UPDATE) {
+#pragma unroll
+        for (int a = 0; a < RPG; ++a) {
+          const float2* p2 = reinterpret_cast<const float2*>(A.ep.weights + (row0 + a) * nx);
+#pragma unroll
+          for (int r = 0; r < R1; ++r) ob[a * R1 + r] = ld_stream(p2 + lane + 16 * r);
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < RPG; ++a) {
+      cplx* zr = slab + a * RS;
+#pragma unroll
+      for (int i = 0; i < PAIRS; ++i) {
+        const int k = lane + 16 * i;
+        if (k == 0) {
+          const float x0 = xs[a * PAIRS + i].x, xM = xm[a * PAIRS + i].x;  // imaginary parts ignored (c2r)
+          zr[0] = cmake(x0 + xM, x0 - xM);
+          zr[M / 2] = cmake(2.f * xh[a].x, -2.f * xh[a].y);
+        } else {
+          cplx zk, zm;
+          c2r_pair(xs[a * PAIRS + i], xm[a * PAIRS + i], twp[i], zk, zm);
+          zr[k] = zk;
+          zr[M - k] = zm;
+        }
+      }
+    }
+    (void)xn;
+    __syncwarp();
+    cplx v[16];
+    {
+      const cplx* p = slab + r_blk * RS + q_blk;
+#pragma unroll
+      for (int q2 = 0; q2 < 16; ++q2) v[q2] = p[R1 * q2];
+    }
+    Bfly<16, true>::run(v);
+    __syncwarp();
+    {
+      cplx* p = slab + r_blk * RS + q_blk * 17;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) p[j] = v[j];
+    }
+    __syncwarp();
+    float* obase = (mode == gen::EPI_UPDATE) ? A.ep.psi : A.out;
+#pragma unroll
+    for (int a = 0; a < RPG; ++a) {
+#pragma unroll
+      for (int q = 0; q < R1; ++q) {
+        cplx x = slab[a * RS + q * 17 + lane];
+        if (q > 0) x = cmulc(x, tw1[q]);
+        v[a * R1 + q] = x;
+      }
+      Bfly<R1, true>::run(v + a * R1);
+      float2* orow = reinterpret_cast<float2*>(obase + (row0 + a) * nx);
+#pragma unroll
+      for (int r = 0; r < R1; ++r) {
+        float2 val = make_float2(v[a * R1 + r].x * A.ep.scale, v[a * R1 + r].y * A.ep.scale);
+        if (mode == gen::EPI_QUOTIENT) {
+          val.x = quotient(oa[a * R1 + r].x, val.x);
+          val.y = quotient(oa[a * R1 + r].y, val.y);
+        } else if (mode == gen::EPI_UPDATE) {
+          val.x = rl_update(oa[a * R1 + r].x, val.x, ob[a * R1 + r].x, A.ep.up);
+          val.y = rl_update(oa[a * R1 + r].y, val.y, ob[a * R1 + r].y, A.ep.up);
+        }
+        st_stream(orow + lane + 16 * r, val);
+      }
+    }
+    __syncwarp();
   }
 }
 

@@ -25,17 +25,20 @@ bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 struct FastEngine : ConvEngine {
   int M = 0, nxc = 0, nxp = 0;
   int num_sms = 148;
-  bool use_pipe = false;
+  bool rows_v2 = true;
+  int rows_ctas_per_sm = 8;
   cplx* d_tw_m = nullptr;
   cplx* d_tw_nx = nullptr;
-  cplx* d_tw_y = nullptr;
-  cplx* d_tw_z = nullptr;
+  cplx* d_tw_y[2] = {nullptr, nullptr};  // per-stage tables of the y / z passes
+  cplx* d_tw_z[2] = {nullptr, nullptr};
 
   ~FastEngine() override {
     if (d_tw_m) cudaFree(d_tw_m);
     if (d_tw_nx) cudaFree(d_tw_nx);
-    if (d_tw_y) cudaFree(d_tw_y);
-    if (d_tw_z) cudaFree(d_tw_z);
+    for (int i = 0; i < 2; ++i) {
+      if (d_tw_y[i]) cudaFree(d_tw_y[i]);
+      if (d_tw_z[i]) cudaFree(d_tw_z[i]);
+    }
   }
   int strategy() const override { return 2; }
   size_t khat_elems() const override { return size_t(plan->nz) * plan->ny * nxp; }
@@ -62,16 +65,73 @@ struct FastEngine : ConvEngine {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, plan->device) == cudaSuccess && prop.multiProcessorCount > 0)
       num_sms = prop.multiProcessorCount;
-    const char* e = getenv("LMVN_PIPE");
-    use_pipe = (e && *e == '1');  // experimental persistent double-buffered variant, off by default
+    if (const char* e = getenv("LMVN_ROWS_V2")) rows_v2 = (*e != '0');
+    if (const char* e = getenv("LMVN_ROWS_CTAS")) rows_ctas_per_sm = std::max(1, atoi(e));
     LMVN_TRY(upload_table(&d_tw_m, M, M));
     LMVN_TRY(upload_table(&d_tw_nx, plan->nx, M + 1));
-    LMVN_TRY(upload_table(&d_tw_y, plan->ny, plan->ny));
-    LMVN_TRY(upload_table(&d_tw_z, plan->nz, plan->nz));
+    LMVN_TRY(upload_stage_tables(d_tw_y, plan->ny));
+    LMVN_TRY(upload_stage_tables(d_tw_z, plan->nz));
+    return 0;
+  }
+
+  // [j][q] = w_L^{jq} for the first two stages of the radix plan of length n
+  static int upload_stage_tables(cplx** dst, int n) {
+    int r1, r2;
+    switch (n) {
+      case 512: r1 = 8; r2 = 8; break;
+      case 256: r1 = 8; r2 = 8; break;
+      case 128: r1 = 8; r2 = 4; break;
+      case 64: r1 = 8; r2 = 8; break;
+      case 32: r1 = 8; r2 = 4; break;
+      case 16: r1 = 4; r2 = 4; break;
+      default: set_last_error("fused path: unsupported axis length %d", n); return -1;
+    }
+    const int spans[2] = {n, n / r1};
+    const int radix[2] = {r1, r2};
+    for (int s = 0; s < 2; ++s) {
+      const int L = spans[s], R = radix[s], M = L / R;
+      std::vector<cplx> h(size_t(M) * R);
+      for (int j = 0; j < M; ++j)
+        for (int q = 0; q < R; ++q) {
+          const double a = -2.0 * M_PI * double(j) * double(q) / double(L);
+          h[size_t(j) * R + q] = cmake(float(cos(a)), float(sin(a)));
+        }
+      LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&dst[s]), sizeof(cplx) * h.size()));
+      LMVN_CUDA_TRY(cudaMemcpy(dst[s], h.data(), sizeof(cplx) * h.size(), cudaMemcpyHostToDevice));
+    }
     return 0;
   }
 
   // ---- launches -------------------------------------------------------------
+  // second-generation rows kernels (full-line accesses, persistent row loop)
+  template <int MM>
+  int launch_rows_fwd2(const fast::RowArgs& a, bool wrapped, cudaStream_t s) {
+    typedef fast::Row2Cfg<MM> CF;
+    const size_t rows = size_t(a.nz) * plan->ny;
+    const size_t iters = ceil_div(rows, CF::ROWS);
+    const dim3 grid(unsigned(std::min<size_t>(iters, size_t(num_sms) * rows_ctas_per_sm)));
+    const size_t smem = size_t(CF::GROUPS) * CF::RPG * CF::RS * sizeof(cplx);
+    auto kw = fast::k_rows_fwd2<MM, true>;
+    auto kp = fast::k_rows_fwd2<MM, false>;
+    if (wrapped) {
+      LMVN_LAUNCH(kw, grid, dim3(fast::kRowThreads), smem, s, a);
+    } else {
+      LMVN_LAUNCH(kp, grid, dim3(fast::kRowThreads), smem, s, a);
+    }
+    return 0;
+  }
+  template <int MM>
+  int launch_rows_inv2(const fast::RowArgs& a, cudaStream_t s) {
+    typedef fast::Row2Cfg<MM> CF;
+    const size_t rows = size_t(a.nz) * plan->ny;
+    const size_t iters = ceil_div(rows, CF::ROWS);
+    const dim3 grid(unsigned(std::min<size_t>(iters, size_t(num_sms) * rows_ctas_per_sm)));
+    const size_t smem = size_t(CF::GROUPS) * CF::RPG * CF::RS * sizeof(cplx);
+    auto kfn = fast::k_rows_inv2<MM>;
+    LMVN_LAUNCH(kfn, grid, dim3(fast::kRowThreads), smem, s, a);
+    return 0;
+  }
+
   template <int MM>
   int launch_rows_fwd(const fast::RowArgs& a, bool wrapped, cudaStream_t s) {
     typedef fast::RowCfg<MM> CF;
@@ -117,6 +177,14 @@ struct FastEngine : ConvEngine {
     a.nz = nzs; a.ny = plan->ny; a.nxp = nxp;
     a.tw_m = d_tw_m; a.tw_nx = d_tw_nx;
     const bool w = src.wrapped != 0;
+    if (rows_v2) {
+      switch (M) {
+        case 32: LMVN_TRY(launch_rows_fwd2<32>(a, w, s)); break;
+        case 64: LMVN_TRY(launch_rows_fwd2<64>(a, w, s)); break;
+        case 128: LMVN_TRY(launch_rows_fwd2<128>(a, w, s)); break;
+        default: set_last_error("fused path: unsupported nx"); return -1;
+      }
+    } else
     switch (M) {
       case 32: LMVN_TRY(launch_rows_fwd<32>(a, w, s)); break;
       case 64: LMVN_TRY(launch_rows_fwd<64>(a, w, s)); break;
@@ -142,6 +210,14 @@ struct FastEngine : ConvEngine {
     a.ep = ep;
     a.nz = nzs; a.ny = plan->ny; a.nxp = nxp;
     a.tw_m = d_tw_m; a.tw_nx = d_tw_nx;
+    if (rows_v2) {
+      switch (M) {
+        case 32: LMVN_TRY(launch_rows_inv2<32>(a, s)); break;
+        case 64: LMVN_TRY(launch_rows_inv2<64>(a, s)); break;
+        case 128: LMVN_TRY(launch_rows_inv2<128>(a, s)); break;
+        default: set_last_error("fused path: unsupported nx"); return -1;
+      }
+    } else
     switch (M) {
       case 32: LMVN_TRY(launch_rows_inv<32>(a, s)); break;
       case 64: LMVN_TRY(launch_rows_inv<64>(a, s)); break;
@@ -158,18 +234,6 @@ struct FastEngine : ConvEngine {
   template <int N, int MODE>
   int launch_strided(const fast::StridedArgs& a, dim3 grid, cudaStream_t s) {
     constexpr int COLS = fast::Cols<N>::V;
-    if (use_pipe && N >= 64) {
-      // persistent, double-buffered variant: grid = resident CTAs
-      const size_t tile_b = size_t(N) * COLS * sizeof(cplx);
-      const size_t psmem = tile_b * (MODE == fast::SM_FWD_MUL_INV ? 3 : 2);
-      const int per_sm = int(std::max<size_t>(1, std::min<size_t>(N >= 512 ? 1 : 2, (200 * 1024) / psmem)));
-      const int nchunks = int(grid.x), ntiles = int(grid.x * grid.y);
-      const int ctas = std::min(ntiles, num_sms * per_sm);
-      auto kp = fast::k_strided_pipe<N, MODE>;
-      LMVN_CUDA_TRY(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, int(psmem)));
-      LMVN_LAUNCH(kp, dim3(unsigned(ctas)), dim3(fast::PipeThreads<N>::V), psmem, s, a, nchunks, ntiles);
-      return 0;
-    }
     const size_t smem = size_t(N) * COLS * sizeof(cplx);
     auto kfn = fast::k_strided<N, MODE>;
     if (smem > 48 * 1024) {  // per device, cheap: set every time
@@ -201,9 +265,11 @@ struct FastEngine : ConvEngine {
     int n;
     unsigned slow;
     if (axis == 1) {
-      n = p.ny; a.row_stride = nxp; a.tile_stride = (long long)p.ny * nxp; slow = unsigned(nzs >= 0 ? nzs : p.nz); a.tw = d_tw_y;
+      n = p.ny; a.row_stride = nxp; a.tile_stride = (long long)p.ny * nxp; slow = unsigned(nzs >= 0 ? nzs : p.nz);
+      a.tw1 = d_tw_y[0]; a.tw2 = d_tw_y[1];
     } else {
-      n = p.nz; a.row_stride = (long long)p.ny * nxp; a.tile_stride = nxp; slow = unsigned(p.ny); a.tw = d_tw_z;
+      n = p.nz; a.row_stride = p.ny * nxp; a.tile_stride = nxp; slow = unsigned(p.ny);
+      a.tw1 = d_tw_z[0]; a.tw2 = d_tw_z[1];
     }
     int rc;
 #define LMVN_STRIDED_CASE(NN)                                                                   \
