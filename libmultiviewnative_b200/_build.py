@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libmultiviewnative.so")
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
 EMU_PATH = os.path.join(EMU_DIR, "_lmvn_emu.so")
 
-CUDA_SOURCES = ["api.cu", "engine.cu"]
+CUDA_SOURCES = ["api.cu", "engine.cu", "fft_fused.cu", "fft_fused_xy.cu"]
 HOST_SOURCES = ["cpu_path.cpp"]
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -56,16 +56,13 @@ def build_cuda(force: bool = False, verbose: bool = False, out: str = None, defi
     if not force and not _stale(target):
         return target
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_ARCH, "-lineinfo", "-O3", "-std=c++17", "-shared",
+    cmd = [_nvcc(), *NVCC_ARCH, "--threads", "0", "-lineinfo", "-O3", "-std=c++17", "-shared",
            "-Xcompiler", "-fPIC,-fopenmp,-fvisibility=hidden,-Wall,-Wno-unknown-pragmas",
            "-I", os.path.join(ROOT, "include"), "-I", CSRC]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    fused = os.path.join(CSRC, "fft_fused.cu")
     srcs = list(CUDA_SOURCES)
-    if os.path.exists(fused):
-        srcs.append("fft_fused.cu")
-        cmd += ["-DLMVN_HAVE_FUSED"]
+    cmd += ["-DLMVN_HAVE_FUSED"]
     cmd += ["-D" + d for d in defines]
     cmd += [os.path.join(CSRC, s) for s in srcs + HOST_SOURCES]
     cmd += ["-o", target, "-lgomp"]
@@ -86,11 +83,8 @@ def build_emu(force: bool = False) -> str:
     cmd = [cxx, "-O2", "-g", "-std=c++17", "-shared", "-fPIC", "-fopenmp", "-DLMVN_EMU",
            "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function",
            "-I", EMU_DIR, "-I", os.path.join(ROOT, "include"), "-I", CSRC]
-    fused = os.path.join(CSRC, "fft_fused.cu")
     srcs = list(CUDA_SOURCES)
-    if os.path.exists(fused):
-        srcs.append("fft_fused.cu")
-        cmd += ["-DLMVN_HAVE_FUSED"]
+    cmd += ["-DLMVN_HAVE_FUSED"]
     for s in srcs:
         cmd += ["-x", "c++", os.path.join(CSRC, s)]
     cmd += ["-x", "c++", os.path.join(CSRC, "cpu_path.cpp"), os.path.join(EMU_DIR, "cuda_emu.cpp")]

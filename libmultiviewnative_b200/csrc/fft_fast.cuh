@@ -139,6 +139,57 @@ struct Bfly<16, INV> {
   }
 };
 
+// w_32^k (forward sign), k = 0..31, from first-octant constants; k is a compile-time constant
+// after unrolling, so this folds to immediates
+__device__ __forceinline__ cplx w32(int k) {
+  const float c[9] = {1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                      0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f,
+                      0.19509032201612826785f, 0.f};
+  // angle = -2 pi k / 32; quadrant folding on cos(a) = c[k], sin(a) = c[8-k] for k in 0..8
+  k &= 31;
+  const int quad = k >> 3, r = k & 7;
+  const float cr = c[r], sr = c[8 - r];     // cos, sin of 2 pi r / 32
+  // e^{-i (quad pi/2 + t)} = (-i)^quad (cos t - i sin t)
+  switch (quad) {
+    case 0: return cmake(cr, -sr);
+    case 1: return cmake(-sr, -cr);
+    case 2: return cmake(-cr, sr);
+    default: return cmake(sr, cr);
+  }
+}
+
+template <bool INV>
+struct Bfly<32, INV> {
+  static __device__ __forceinline__ void run(cplx* v) {
+    // 32 = 8 x 4 decimation in frequency: X[q + 8 q2] = sum_i (DFT8_r(v[i+4r])[q] * w32^{iq}) w4^{i q2}
+    cplx a[8][4];  // a[q][i]
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      cplx t[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) t[r] = v[i + 4 * r];
+      Bfly<8, INV>::run(t);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q][i] = t[q];
+    }
+#pragma unroll
+    for (int q = 1; q < 8; ++q)
+#pragma unroll
+      for (int i = 1; i < 4; ++i) {
+        const int k = i * q;
+        if (k == 8) a[q][i] = rot_q<INV>(a[q][i]);
+        else a[q][i] = mul_tw<INV>(a[q][i], w32(k));
+      }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      cplx t[4] = {a[q][0], a[q][1], a[q][2], a[q][3]};
+      Bfly<4, INV>::run(t);
+#pragma unroll
+      for (int q2 = 0; q2 < 4; ++q2) v[q + 8 * q2] = t[q2];
+    }
+  }
+};
+
 // ------------------------------------------------------------------------------
 // strided passes (y and z axes): tile = N rows x COLS adjacent kx columns.
 // ------------------------------------------------------------------------------
@@ -158,9 +209,16 @@ struct StridedArgs {
 // number of stages and the radix of stage s for N = R1*R2*R3
 template <int N>
 struct Radix;
+#ifndef LMVN_NARROW_RADIX
+// two stages, ONE shared-memory exchange: wide register butterflies
+template <> struct Radix<512> { static const int S = 2, R1 = 32, R2 = 16, R3 = 1; };
+template <> struct Radix<256> { static const int S = 2, R1 = 16, R2 = 16, R3 = 1; };
+template <> struct Radix<128> { static const int S = 2, R1 = 16, R2 = 8, R3 = 1; };
+#else
 template <> struct Radix<512> { static const int S = 3, R1 = 8, R2 = 8, R3 = 8; };
 template <> struct Radix<256> { static const int S = 3, R1 = 8, R2 = 8, R3 = 4; };
 template <> struct Radix<128> { static const int S = 3, R1 = 8, R2 = 4, R3 = 4; };
+#endif
 template <> struct Radix<64> { static const int S = 2, R1 = 8, R2 = 8, R3 = 1; };
 template <> struct Radix<32> { static const int S = 2, R1 = 8, R2 = 4, R3 = 1; };
 template <> struct Radix<16> { static const int S = 2, R1 = 4, R2 = 4, R3 = 1; };
@@ -177,6 +235,11 @@ static const int kStridedThreads = 256;
 #ifndef LMVN_Y_UNROLL
 #define LMVN_Y_UNROLL 8
 #endif
+
+// resident CTAs per SM the register budget is sized for
+template <int N, int MODE> struct StridedBlocks {
+  static const int V = (Radix<N>::R1 >= 32) ? 2 : ((MODE == SM_FWD_MUL_INV && N >= 64) ? LMVN_ZMUL_BLOCKS : 3);
+};
 
 enum Where { W_SMEM = 0, W_GLOBAL = 1, W_GLOBAL_SCALED = 2 };
 
@@ -271,82 +334,81 @@ __device__ __forceinline__ void strided_middle(cplx* __restrict__ sm, const cplx
   }
 }
 
-template <int N, int MODE>
-static __global__ void __launch_bounds__(kStridedThreads, (MODE == SM_FWD_MUL_INV && N >= 64) ? LMVN_ZMUL_BLOCKS : 3)
-    k_strided(StridedArgs A) {
+// One tile of a strided pass.  `sm`, `g`, `gk` already point at this thread's column; threads of
+// the padding columns of a ragged last tile pass live = false: they skip the stages (every stage
+// touches the thread's own column only) but still take part in the barriers.
+template <int N, int MODE, int U>
+__device__ __forceinline__ void strided_tile(const StridedArgs& A, cplx* sm, cplx* g, const cplx* gk, bool live) {
   typedef Radix<N> RX;
   constexpr int COLS = Cols<N>::V;
   constexpr int R1 = RX::R1, R2 = RX::R2;
   constexpr int R3 = (RX::R3 > 1 ? RX::R3 : 2);  // placeholder radix for the dead 3-stage code of 2-stage sizes
   constexpr int L2 = N / R1, L3 = (RX::S == 3 ? N / (R1 * R2) : 2);
   constexpr int DSTG = (MODE == SM_FWD_SCALE) ? W_GLOBAL_SCALED : W_GLOBAL;
-  LMVN_DYN_SMEM(cplx, smem);  // [N][COLS]
-  const int c = threadIdx.x % COLS;
-  const int col = blockIdx.x * COLS + c;
-  // ragged last tile: threads of the padding columns leave; barriers count live threads only
-  if (col >= A.ncols) return;
-  cplx* g = A.data + (long long)blockIdx.y * A.tile_stride + col;
-  const cplx* gk = A.khat + (long long)blockIdx.y * A.tile_stride + col;
-  cplx* sm = smem + c;
   const int rs = A.row_stride;
-
-  constexpr int UY = LMVN_Y_UNROLL;
   if (MODE == SM_FWD || MODE == SM_FWD_SCALE) {
-    strided_stage<N, R1, N, COLS, false, W_GLOBAL, W_SMEM, UY>(sm, g, rs, A.tw1, 1.f);
+    if (live) strided_stage<N, R1, N, COLS, false, W_GLOBAL, W_SMEM, U>(sm, g, rs, A.tw1, 1.f);
     __syncthreads();
     if (RX::S == 3) {
-      strided_stage<N, R2, L2, COLS, false, W_SMEM, W_SMEM, UY>(sm, g, rs, A.tw2, 1.f);
+      if (live) strided_stage<N, R2, L2, COLS, false, W_SMEM, W_SMEM, U>(sm, g, rs, A.tw2, 1.f);
       __syncthreads();
-      strided_stage<N, R3, L3, COLS, false, W_SMEM, DSTG, UY>(sm, g, rs, nullptr, A.scale);
+      if (live) strided_stage<N, R3, L3, COLS, false, W_SMEM, DSTG, U>(sm, g, rs, nullptr, A.scale);
     } else {
-      strided_stage<N, R2, L2, COLS, false, W_SMEM, DSTG, UY>(sm, g, rs, A.tw2, A.scale);
+      if (live) strided_stage<N, R2, L2, COLS, false, W_SMEM, DSTG, U>(sm, g, rs, A.tw2, A.scale);
     }
   } else if (MODE == SM_INV) {
     if (RX::S == 3) {
-      strided_stage<N, R3, L3, COLS, true, W_GLOBAL, W_SMEM, UY>(sm, g, rs, nullptr, 1.f);
+      if (live) strided_stage<N, R3, L3, COLS, true, W_GLOBAL, W_SMEM, U>(sm, g, rs, nullptr, 1.f);
       __syncthreads();
-      strided_stage<N, R2, L2, COLS, true, W_SMEM, W_SMEM, UY>(sm, g, rs, A.tw2, 1.f);
+      if (live) strided_stage<N, R2, L2, COLS, true, W_SMEM, W_SMEM, U>(sm, g, rs, A.tw2, 1.f);
     } else {
-      strided_stage<N, R2, L2, COLS, true, W_GLOBAL, W_SMEM, UY>(sm, g, rs, A.tw2, 1.f);
+      if (live) strided_stage<N, R2, L2, COLS, true, W_GLOBAL, W_SMEM, U>(sm, g, rs, A.tw2, 1.f);
     }
     __syncthreads();
-    strided_stage<N, R1, N, COLS, true, W_SMEM, W_GLOBAL, UY>(sm, g, rs, A.tw1, 1.f);
+    if (live) strided_stage<N, R1, N, COLS, true, W_SMEM, W_GLOBAL, U>(sm, g, rs, A.tw1, 1.f);
   } else {  // SM_FWD_MUL_INV
-    constexpr int U = LMVN_ZMUL_UNROLL;
-    strided_stage<N, R1, N, COLS, false, W_GLOBAL, W_SMEM, U>(sm, g, rs, A.tw1, 1.f);
+    if (live) strided_stage<N, R1, N, COLS, false, W_GLOBAL, W_SMEM, U>(sm, g, rs, A.tw1, 1.f);
     __syncthreads();
     if (RX::S == 3) {
-      strided_stage<N, R2, L2, COLS, false, W_SMEM, W_SMEM, U>(sm, g, rs, A.tw2, 1.f);
+      if (live) strided_stage<N, R2, L2, COLS, false, W_SMEM, W_SMEM, U>(sm, g, rs, A.tw2, 1.f);
       __syncthreads();
-      strided_middle<N, R3, COLS, U>(sm, gk, rs);
+      if (live) strided_middle<N, R3, COLS, U>(sm, gk, rs);
       __syncthreads();
-      strided_stage<N, R2, L2, COLS, true, W_SMEM, W_SMEM, U>(sm, g, rs, A.tw2, 1.f);
+      if (live) strided_stage<N, R2, L2, COLS, true, W_SMEM, W_SMEM, U>(sm, g, rs, A.tw2, 1.f);
     } else {
-      strided_middle<N, R2, COLS, U>(sm, gk, rs);
+      if (live) strided_middle<N, R2, COLS, U>(sm, gk, rs);
     }
     __syncthreads();
-    strided_stage<N, R1, N, COLS, true, W_SMEM, W_GLOBAL, U>(sm, g, rs, A.tw1, 1.f);
+    if (live) strided_stage<N, R1, N, COLS, true, W_SMEM, W_GLOBAL, U>(sm, g, rs, A.tw1, 1.f);
   }
 }
 
+template <int N, int MODE>
+static __global__ void __launch_bounds__(kStridedThreads, StridedBlocks<N, MODE>::V)
+    k_strided(StridedArgs A) {
+  constexpr int COLS = Cols<N>::V;
+  LMVN_DYN_SMEM(cplx, smem);  // [N][COLS]
+  const int c = threadIdx.x % COLS;
+  const int col = blockIdx.x * COLS + c;
+  const long long base = (long long)blockIdx.y * A.tile_stride + col;
+  constexpr int U = (MODE == SM_FWD_MUL_INV) ? LMVN_ZMUL_UNROLL : LMVN_Y_UNROLL;
+  strided_tile<N, MODE, U>(A, smem + c, A.data + base, A.khat + base, col < A.ncols);
+}
+
 // ------------------------------------------------------------------------------
-// x passes: one real row of nx = 2M samples <-> M+1 complex bins.
-// M = R1 * 8.  A row is handled by TPR = R1/2 threads holding 16 complex values
-// each; stage 1 = radix-R1 over elements j + 8r, one exchange through a padded
-// shared-memory slab, stage 2 = two radix-8 blocks (q and R1-q) per thread, which
-// puts every (k, M-k) pair of the real-transform split into ONE thread's registers.
+// x passes: one real row of nx = 2M samples <-> M+1 complex bins; every global access
+// is a full 128-byte line.  M = R1 * 16.  A group of 16 lanes works on RPG = 16 / R1
+// rows at a time:
+//   stage 1  lane j: radix-R1 butterflies over elements j + 16 r of each row, loaded
+//            straight from global memory (16 lanes x 8 B = one line per row);
+//   exchange through a padded slab, element (q, j) at q*17 + j;
+//   stage 2  lane t: ONE radix-16 block (block t % R1 of row t / R1), no twiddles;
+//   exchange: Z in natural order;
+//   split    lane l: pairs (k, M-k), k = l + 16 i -> X[k], X[M-k], stored line by line.
+// Stage-1 and split twiddles depend on the lane only and live in registers.  The
+// inverse is the exact mirror and ends in the fused pointwise epilogue.
 // ------------------------------------------------------------------------------
 static const int kRowThreads = 256;
-
-template <int M> struct RowCfg {
-  static const int R1 = M / 8;          // 4, 8, 16
-  static const int TPR = R1 / 2;        // threads per row: 2, 4, 8
-  static const int JPT = 16 / R1;       // stage-1 butterflies per thread
-  static const int ROWS = kRowThreads / TPR;  // rows per block pass
-  // exchange slab: element (q, j) at q*9 + j; 9-pitch makes both the j-contiguous writes
-  // and the q-strided reads conflict free; rows are offset by SLAB (= 8 mod 16)
-  static const int SLAB = ((R1 * 9 + 15) / 16) * 16 + 8;
-};
 
 struct RowArgs {
   gen::RealSource src;   // forward: real input (volume or wrapped kernel)
@@ -378,225 +440,6 @@ __device__ __forceinline__ void c2r_pair(cplx xk, cplx xm, cplx w, cplx& zk, cpl
   zm = cmake(e.x + o.y, -e.y + o.x);
 }
 
-template <int M, bool WRAPPED>
-static __global__ void __launch_bounds__(kRowThreads) k_rows_fwd(RowArgs A) {
-  typedef RowCfg<M> CF;
-  constexpr int R1 = CF::R1, TPR = CF::TPR, JPT = CF::JPT;
-  constexpr int nx = 2 * M;
-  LMVN_DYN_SMEM(cplx, sm);
-  const int t = threadIdx.x % TPR;
-  const int lrow = threadIdx.x / TPR;
-  const long long rows = (long long)A.nz * A.ny;
-  const long long row = (long long)blockIdx.x * CF::ROWS + lrow;
-  cplx* slab = sm + lrow * CF::SLAB;
-  const bool active = row < rows;
-  cplx v[16];
-  if (active) {
-    if (!WRAPPED) {
-      const float2* in = reinterpret_cast<const float2*>(A.src.data + row * nx);
-#pragma unroll
-      for (int jj = 0; jj < JPT; ++jj)
-#pragma unroll
-        for (int r = 0; r < R1; ++r) v[jj * R1 + r] = in[(t * JPT + jj) + 8 * r];
-    } else {
-      const int z = int(row / A.ny), y = int(row % A.ny);
-      const int sz = gen::wrap_src_index(z, A.nz, A.src.kz);
-      const int sy = gen::wrap_src_index(y, A.ny, A.src.ky);
-#pragma unroll
-      for (int jj = 0; jj < JPT; ++jj)
-#pragma unroll
-        for (int r = 0; r < R1; ++r) {
-          const int n = (t * JPT + jj) + 8 * r;
-          float a = 0.f, b = 0.f;
-          if (sz >= 0 && sy >= 0) {
-            const float* kr = A.src.data + (size_t(sz) * A.src.ky + sy) * A.src.kx;
-            const int s0 = gen::wrap_src_index(2 * n, nx, A.src.kx);
-            const int s1 = gen::wrap_src_index(2 * n + 1, nx, A.src.kx);
-            if (s0 >= 0) a = kr[s0];
-            if (s1 >= 0) b = kr[s1];
-          }
-          v[jj * R1 + r] = cmake(a, b);
-        }
-    }
-    // stage 1: radix-R1 over r, twiddle w_M^{jq}, to the slab at (q, j)
-#pragma unroll
-    for (int jj = 0; jj < JPT; ++jj) {
-      const int j = t * JPT + jj;
-      Bfly<R1, false>::run(v + jj * R1);
-#pragma unroll
-      for (int q = 0; q < R1; ++q) {
-        cplx x = v[jj * R1 + q];
-        if (q > 0) x = cmul(x, __ldg(A.tw_m + j * q));
-        slab[q * 9 + j] = x;
-      }
-    }
-  }
-  __syncwarp();
-  if (active) {
-    // stage 2: radix-8 on blocks qa, qb
-    const int qa = t, qb = (t == 0) ? R1 / 2 : R1 - t;
-#pragma unroll
-    for (int q2 = 0; q2 < 8; ++q2) {
-      v[q2] = slab[qa * 9 + q2];
-      v[8 + q2] = slab[qb * 9 + q2];
-    }
-    Bfly<8, false>::run(v);
-    Bfly<8, false>::run(v + 8);
-    // v[q2] = Z[qa + R1 q2], v[8+q2] = Z[qb + R1 q2]
-    cplx* orow = A.spec + row * A.nxp;
-    if (t != 0) {
-#pragma unroll
-      for (int q2 = 0; q2 < 8; ++q2) {
-        const int k = qa + R1 * q2;  // partner M-k = qb + R1 (7-q2)
-        cplx xk, xm;
-        r2c_pair(v[q2], v[8 + 7 - q2], __ldg(A.tw_nx + k), xk, xm);
-        orow[k] = xk;
-        orow[M - k] = xm;
-      }
-    } else {
-      // block 0: k = R1 q2 pairs with R1 (8 - q2); q2 = 0 -> DC / Nyquist, q2 = 4 -> k = M/2
-      orow[0] = cmake(v[0].x + v[0].y, 0.f);
-      orow[M] = cmake(v[0].x - v[0].y, 0.f);
-      orow[M / 2] = cconj(v[4]);
-#pragma unroll
-      for (int q2 = 1; q2 < 4; ++q2) {
-        const int k = R1 * q2;
-        cplx xk, xm;
-        r2c_pair(v[q2], v[8 - q2], __ldg(A.tw_nx + k), xk, xm);
-        orow[k] = xk;
-        orow[M - k] = xm;
-      }
-      // block R1/2: k = R1/2 + R1 q2 pairs with R1/2 + R1 (7 - q2)
-#pragma unroll
-      for (int q2 = 0; q2 < 4; ++q2) {
-        const int k = R1 / 2 + R1 * q2;
-        cplx xk, xm;
-        r2c_pair(v[8 + q2], v[8 + 7 - q2], __ldg(A.tw_nx + k), xk, xm);
-        orow[k] = xk;
-        orow[M - k] = xm;
-      }
-    }
-  }
-}
-
-template <int M>
-static __global__ void __launch_bounds__(kRowThreads) k_rows_inv(RowArgs A) {
-  typedef RowCfg<M> CF;
-  constexpr int R1 = CF::R1, TPR = CF::TPR, JPT = CF::JPT;
-  constexpr int nx = 2 * M;
-  LMVN_DYN_SMEM(cplx, sm);
-  const int t = threadIdx.x % TPR;
-  const int lrow = threadIdx.x / TPR;
-  const long long rows = (long long)A.nz * A.ny;
-  const long long row = (long long)blockIdx.x * CF::ROWS + lrow;
-  cplx* slab = sm + lrow * CF::SLAB;
-  const bool active = row < rows;
-  cplx v[16];
-  if (active) {
-    const cplx* irow = A.spec + row * A.nxp;
-    const int qa = t, qb = (t == 0) ? R1 / 2 : R1 - t;
-    if (t != 0) {
-#pragma unroll
-      for (int q2 = 0; q2 < 8; ++q2) {
-        const int k = qa + R1 * q2;
-        c2r_pair(irow[k], irow[M - k], __ldg(A.tw_nx + k), v[q2], v[8 + 7 - q2]);
-      }
-    } else {
-      const float x0 = irow[0].x, xm = irow[M].x;  // imaginary parts ignored like a c2r transform
-      v[0] = cmake(x0 + xm, x0 - xm);
-      const cplx xh = irow[M / 2];
-      v[4] = cmake(2.f * xh.x, -2.f * xh.y);
-#pragma unroll
-      for (int q2 = 1; q2 < 4; ++q2) {
-        const int k = R1 * q2;
-        c2r_pair(irow[k], irow[M - k], __ldg(A.tw_nx + k), v[q2], v[8 - q2]);
-      }
-#pragma unroll
-      for (int q2 = 0; q2 < 4; ++q2) {
-        const int k = R1 / 2 + R1 * q2;
-        c2r_pair(irow[k], irow[M - k], __ldg(A.tw_nx + k), v[8 + q2], v[8 + 7 - q2]);
-      }
-    }
-    Bfly<8, true>::run(v);
-    Bfly<8, true>::run(v + 8);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      slab[qa * 9 + j] = v[j];
-      slab[qb * 9 + j] = v[8 + j];
-    }
-  }
-  // Operands of the pointwise epilogue are fetched BEFORE the exchange barrier and the last
-  // butterfly so that their latency overlaps the transform (they do not depend on it); all
-  // loads of a group are issued back to back, all stores afterwards.
-  const size_t base = size_t(active ? row : 0) * nx;
-  const float2* __restrict__ op_a = nullptr;   // view (quotient) or psi (update)
-  const float2* __restrict__ op_b = nullptr;   // weights (update)
-  if (A.ep.mode == gen::EPI_QUOTIENT) op_a = reinterpret_cast<const float2*>(A.ep.view + base);
-  if (A.ep.mode == gen::EPI_UPDATE) {
-    op_a = reinterpret_cast<const float2*>(A.ep.psi + base);
-    op_b = reinterpret_cast<const float2*>(A.ep.weights + base);
-  }
-  float2 oa[R1], ob[R1];
-  auto fetch = [&](int jj) {
-    const int j = t * JPT + jj;
-    if (op_a) {
-#pragma unroll
-      for (int r = 0; r < R1; ++r) oa[r] = op_a[j + 8 * r];
-    }
-    if (op_b) {
-#pragma unroll
-      for (int r = 0; r < R1; ++r) ob[r] = op_b[j + 8 * r];
-    }
-  };
-  if (active) fetch(0);
-  __syncwarp();
-  if (active) {
-    float2* __restrict__ orow =
-        reinterpret_cast<float2*>((A.ep.mode == gen::EPI_UPDATE ? A.ep.psi : A.out) + base);
-#pragma unroll
-    for (int jj = 0; jj < JPT; ++jj) {
-      const int j = t * JPT + jj;
-#pragma unroll
-      for (int q = 0; q < R1; ++q) {
-        cplx x = slab[q * 9 + j];
-        if (q > 0) x = cmulc(x, __ldg(A.tw_m + j * q));
-        v[jj * R1 + q] = x;
-      }
-      Bfly<R1, true>::run(v + jj * R1);
-      float2 res[R1];
-#pragma unroll
-      for (int r = 0; r < R1; ++r) {
-        // complex sample n = j + 8 r holds the real samples 2n, 2n+1
-        float2 val = make_float2(v[jj * R1 + r].x * A.ep.scale, v[jj * R1 + r].y * A.ep.scale);
-        if (A.ep.mode == gen::EPI_QUOTIENT) {
-          val.x = quotient(oa[r].x, val.x);
-          val.y = quotient(oa[r].y, val.y);
-        } else if (A.ep.mode == gen::EPI_UPDATE) {
-          val.x = rl_update(oa[r].x, val.x, ob[r].x, A.ep.up);
-          val.y = rl_update(oa[r].y, val.y, ob[r].y, A.ep.up);
-        }
-        res[r] = val;
-      }
-      if (jj + 1 < JPT) fetch(jj + 1);
-#pragma unroll
-      for (int r = 0; r < R1; ++r) orow[j + 8 * r] = res[r];
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------
-// x passes, second generation: every global access is a full 128-byte line.
-// M = R1 * 16.  A group of 16 lanes works on RPG = 16 / R1 rows at a time:
-//   stage 1  lane j: radix-R1 butterflies over elements j + 16 r of each row, loaded
-//            straight from global memory (16 lanes x 8 B = one line per row);
-//   exchange through a padded slab, element (q, j) at q*17 + j;
-//   stage 2  lane t: ONE radix-16 block (block t % R1 of row t / R1), no twiddles;
-//   exchange: Z in natural order;
-//   split    lane l: pairs (k, M-k), k = l + 16 i -> X[k], X[M-k], stored line by line.
-// Stage-1 and split twiddles depend on the lane only and live in registers for the
-// whole row loop.  The inverse kernel is the exact mirror and ends in the fused
-// pointwise epilogue.
-// ------------------------------------------------------------------------------
 template <int M> struct Row2Cfg {
   static const int R1 = M / 16;           // 2, 4, 8
   static const int RPG = 16 / R1;         // rows per 16-lane group: 8, 4, 2
@@ -604,221 +447,344 @@ template <int M> struct Row2Cfg {
   static const int GROUPS = kRowThreads / 16;
   static const int ROWS = GROUPS * RPG;   // rows per block iteration
   static const int PAIRS = M / 32;        // (k, M-k) pairs per lane and row
+  static const int SMEM = GROUPS * RPG * RS * int(sizeof(cplx));
 };
+
+// lane-constant twiddles of the row transforms
+template <int M>
+struct RowTw {
+  cplx tw1[Row2Cfg<M>::R1];
+  cplx twp[Row2Cfg<M>::PAIRS];
+  __device__ __forceinline__ void load(const RowArgs& A, int lane) {
+#pragma unroll
+    for (int q = 1; q < Row2Cfg<M>::R1; ++q) tw1[q] = __ldg(A.tw_m + lane * q);
+#pragma unroll
+    for (int i = 0; i < Row2Cfg<M>::PAIRS; ++i) twp[i] = __ldg(A.tw_nx + lane + 16 * i);
+  }
+};
+
+// forward transform of rows row0 .. row0+RPG-1 by one 16-lane group (slab: the group's exchange area)
+template <int M, bool WRAPPED>
+__device__ __forceinline__ void rows_fwd_group(const RowArgs& A, cplx* slab, long long row0, int lane,
+                                               const RowTw<M>& T) {
+  typedef Row2Cfg<M> CF;
+  constexpr int R1 = CF::R1, RPG = CF::RPG, RS = CF::RS, PAIRS = CF::PAIRS;
+  constexpr int nx = 2 * M;
+  const int q_blk = lane % R1, r_blk = lane / R1;
+  cplx v[16];
+  // ---- stage 1: loads + radix-R1 ----
+#pragma unroll
+  for (int a = 0; a < RPG; ++a) {
+    const long long row = row0 + a;
+    if (!WRAPPED) {
+      const float2* in = reinterpret_cast<const float2*>(A.src.data + row * nx);
+#pragma unroll
+      for (int r = 0; r < R1; ++r) v[a * R1 + r] = ld_stream(in + lane + 16 * r);
+    } else {
+      const int z = int(row / A.ny), y = int(row % A.ny);
+      const int sz = gen::wrap_src_index(z, A.nz, A.src.kz);
+      const int sy = gen::wrap_src_index(y, A.ny, A.src.ky);
+#pragma unroll
+      for (int r = 0; r < R1; ++r) {
+        const int n = lane + 16 * r;
+        float re = 0.f, im = 0.f;
+        if (sz >= 0 && sy >= 0) {
+          const float* kr = A.src.data + (size_t(sz) * A.src.ky + sy) * A.src.kx;
+          const int s0 = gen::wrap_src_index(2 * n, nx, A.src.kx);
+          const int s1 = gen::wrap_src_index(2 * n + 1, nx, A.src.kx);
+          if (s0 >= 0) re = kr[s0];
+          if (s1 >= 0) im = kr[s1];
+        }
+        v[a * R1 + r] = cmake(re, im);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < RPG; ++a) {
+    Bfly<R1, false>::run(v + a * R1);
+#pragma unroll
+    for (int q = 0; q < R1; ++q) {
+      cplx x = v[a * R1 + q];
+      if (q > 0) x = cmul(x, T.tw1[q]);
+      slab[a * RS + q * 17 + lane] = x;
+    }
+  }
+  __syncwarp();
+  // ---- stage 2: one radix-16 block per lane ----
+  {
+    const cplx* p = slab + r_blk * RS + q_blk * 17;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = p[j];
+  }
+  Bfly<16, false>::run(v);
+  __syncwarp();
+  {
+    cplx* p = slab + r_blk * RS + q_blk;  // Z[q + R1 q2] in natural order
+#pragma unroll
+    for (int q2 = 0; q2 < 16; ++q2) p[R1 * q2] = v[q2];
+  }
+  __syncwarp();
+  // ---- real-transform split + full-line stores ----
+#pragma unroll
+  for (int a = 0; a < RPG; ++a) {
+    const cplx* zr = slab + a * RS;
+    cplx* orow = A.spec + (row0 + a) * A.nxp;
+#pragma unroll
+    for (int i = 0; i < PAIRS; ++i) {
+      const int k = lane + 16 * i;
+      if (k == 0) {
+        const cplx z0 = zr[0];
+        st_stream(orow, cmake(z0.x + z0.y, 0.f));
+        st_stream(orow + M, cmake(z0.x - z0.y, 0.f));
+        st_stream(orow + M / 2, cconj(zr[M / 2]));
+      } else {
+        cplx xk, xm;
+        r2c_pair(zr[k], zr[M - k], T.twp[i], xk, xm);
+        st_stream(orow + k, xk);
+        st_stream(orow + (M - k), xm);
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// inverse transform + pointwise epilogue of rows row0 .. row0+RPG-1 by one 16-lane group
+template <int M>
+__device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, long long row0, int lane,
+                                               const RowTw<M>& T) {
+  typedef Row2Cfg<M> CF;
+  constexpr int R1 = CF::R1, RPG = CF::RPG, RS = CF::RS, PAIRS = CF::PAIRS;
+  constexpr int nx = 2 * M;
+  const int q_blk = lane % R1, r_blk = lane / R1;
+  const int mode = A.ep.mode;
+  // ---- spectrum loads (full lines) ----
+  cplx xs[RPG * PAIRS], xm[RPG * PAIRS];
+  cplx xh[RPG];
+#pragma unroll
+  for (int a = 0; a < RPG; ++a) {
+    const cplx* irow = A.spec + (row0 + a) * A.nxp;
+#pragma unroll
+    for (int i = 0; i < PAIRS; ++i) {
+      const int k = lane + 16 * i;
+      xs[a * PAIRS + i] = ld_stream(irow + k);
+      xm[a * PAIRS + i] = ld_stream(irow + (M - k));  // k = 0 reads X[M]
+    }
+    if (lane == 0) xh[a] = ld_stream(irow + M / 2);
+  }
+  // epilogue operands: independent of the transform, fetched now so that their latency
+  // overlaps both exchanges (element n = lane + 16 r of each row = real samples 2n, 2n+1)
+  float2 oa[16], ob[16];
+  if (mode != gen::EPI_STORE) {
+    const float* pa = (mode == gen::EPI_QUOTIENT) ? A.ep.view : A.ep.psi;
+#pragma unroll
+    for (int a = 0; a < RPG; ++a) {
+      const float2* p2 = reinterpret_cast<const float2*>(pa + (row0 + a) * nx);
+#pragma unroll
+      for (int r = 0; r < R1; ++r) oa[a * R1 + r] = ld_stream(p2 + lane + 16 * r);
+    }
+    if (mode == gen::EPI_UPDATE) {
+#pragma unroll
+      for (int a = 0; a < RPG; ++a) {
+        const float2* p2 = reinterpret_cast<const float2*>(A.ep.weights + (row0 + a) * nx);
+#pragma unroll
+        for (int r = 0; r < R1; ++r) ob[a * R1 + r] = ld_stream(p2 + lane + 16 * r);
+      }
+    }
+  }
+  // ---- inverse split into the slab, natural order ----
+#pragma unroll
+  for (int a = 0; a < RPG; ++a) {
+    cplx* zr = slab + a * RS;
+#pragma unroll
+    for (int i = 0; i < PAIRS; ++i) {
+      const int k = lane + 16 * i;
+      if (k == 0) {
+        const float x0 = xs[a * PAIRS + i].x, xM = xm[a * PAIRS + i].x;  // imaginary parts ignored (c2r)
+        zr[0] = cmake(x0 + xM, x0 - xM);
+        zr[M / 2] = cmake(2.f * xh[a].x, -2.f * xh[a].y);
+      } else {
+        cplx zk, zm;
+        c2r_pair(xs[a * PAIRS + i], xm[a * PAIRS + i], T.twp[i], zk, zm);
+        zr[k] = zk;
+        zr[M - k] = zm;
+      }
+    }
+  }
+  __syncwarp();
+  cplx v[16];
+  {
+    const cplx* p = slab + r_blk * RS + q_blk;
+#pragma unroll
+    for (int q2 = 0; q2 < 16; ++q2) v[q2] = p[R1 * q2];
+  }
+  Bfly<16, true>::run(v);
+  __syncwarp();
+  {
+    cplx* p = slab + r_blk * RS + q_blk * 17;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) p[j] = v[j];
+  }
+  __syncwarp();
+  float* obase = (mode == gen::EPI_UPDATE) ? A.ep.psi : A.out;
+#pragma unroll
+  for (int a = 0; a < RPG; ++a) {
+#pragma unroll
+    for (int q = 0; q < R1; ++q) {
+      cplx x = slab[a * RS + q * 17 + lane];
+      if (q > 0) x = cmulc(x, T.tw1[q]);
+      v[a * R1 + q] = x;
+    }
+    Bfly<R1, true>::run(v + a * R1);
+    float2* orow = reinterpret_cast<float2*>(obase + (row0 + a) * nx);
+#pragma unroll
+    for (int r = 0; r < R1; ++r) {
+      float2 val = make_float2(v[a * R1 + r].x * A.ep.scale, v[a * R1 + r].y * A.ep.scale);
+      if (mode == gen::EPI_QUOTIENT) {
+        val.x = quotient(oa[a * R1 + r].x, val.x);
+        val.y = quotient(oa[a * R1 + r].y, val.y);
+      } else if (mode == gen::EPI_UPDATE) {
+        val.x = rl_update(oa[a * R1 + r].x, val.x, ob[a * R1 + r].x, A.ep.up);
+        val.y = rl_update(oa[a * R1 + r].y, val.y, ob[a * R1 + r].y, A.ep.up);
+      }
+      st_stream(orow + lane + 16 * r, val);
+    }
+  }
+  __syncwarp();
+}
 
 template <int M, bool WRAPPED>
 static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_fwd2(RowArgs A) {
   typedef Row2Cfg<M> CF;
-  constexpr int R1 = CF::R1, RPG = CF::RPG, RS = CF::RS, PAIRS = CF::PAIRS;
-  constexpr int nx = 2 * M;
   LMVN_DYN_SMEM(cplx, sm);
   const int lane = threadIdx.x % 16;
   const int group = threadIdx.x / 16;
-  cplx* slab = sm + group * (RPG * RS);
+  cplx* slab = sm + group * (CF::RPG * CF::RS);
   const long long rows = (long long)A.nz * A.ny;
-  // lane-constant twiddles
-  cplx tw1[R1];
-#pragma unroll
-  for (int q = 1; q < R1; ++q) tw1[q] = __ldg(A.tw_m + lane * q);
-  cplx twp[PAIRS];
-#pragma unroll
-  for (int i = 0; i < PAIRS; ++i) twp[i] = __ldg(A.tw_nx + lane + 16 * i);
-  const int q_blk = lane % R1, r_blk = lane / R1;
-
-  for (long long row0 = ((long long)blockIdx.x * CF::GROUPS + group) * RPG; row0 < rows;
-       row0 += (long long)gridDim.x * CF::ROWS) {
-    cplx v[16];
-    // ---- stage 1: loads + radix-R1 ----
-#pragma unroll
-    for (int a = 0; a < RPG; ++a) {
-      const long long row = row0 + a;
-      if (!WRAPPED) {
-        const float2* in = reinterpret_cast<const float2*>(A.src.data + row * nx);
-#pragma unroll
-        for (int r = 0; r < R1; ++r) v[a * R1 + r] = ld_stream(in + lane + 16 * r);
-      } else {
-        const int z = int(row / A.ny), y = int(row % A.ny);
-        const int sz = gen::wrap_src_index(z, A.nz, A.src.kz);
-        const int sy = gen::wrap_src_index(y, A.ny, A.src.ky);
-#pragma unroll
-        for (int r = 0; r < R1; ++r) {
-          const int n = lane + 16 * r;
-          float re = 0.f, im = 0.f;
-          if (sz >= 0 && sy >= 0) {
-            const float* kr = A.src.data + (size_t(sz) * A.src.ky + sy) * A.src.kx;
-            const int s0 = gen::wrap_src_index(2 * n, nx, A.src.kx);
-            const int s1 = gen::wrap_src_index(2 * n + 1, nx, A.src.kx);
-            if (s0 >= 0) re = kr[s0];
-            if (s1 >= 0) im = kr[s1];
-          }
-          v[a * R1 + r] = cmake(re, im);
-        }
-      }
-    }
-#pragma unroll
-    for (int a = 0; a < RPG; ++a) {
-      Bfly<R1, false>::run(v + a * R1);
-#pragma unroll
-      for (int q = 0; q < R1; ++q) {
-        cplx x = v[a * R1 + q];
-        if (q > 0) x = cmul(x, tw1[q]);
-        slab[a * RS + q * 17 + lane] = x;
-      }
-    }
-    __syncwarp();
-    // ---- stage 2: one radix-16 block per lane ----
-    {
-      const cplx* p = slab + r_blk * RS + q_blk * 17;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = p[j];
-    }
-    Bfly<16, false>::run(v);
-    __syncwarp();
-    {
-      cplx* p = slab + r_blk * RS + q_blk;  // Z[q + R1 q2] in natural order
-#pragma unroll
-      for (int q2 = 0; q2 < 16; ++q2) p[R1 * q2] = v[q2];
-    }
-    __syncwarp();
-    // ---- real-transform split + full-line stores ----
-#pragma unroll
-    for (int a = 0; a < RPG; ++a) {
-      const cplx* zr = slab + a * RS;
-      cplx* orow = A.spec + (row0 + a) * A.nxp;
-#pragma unroll
-      for (int i = 0; i < PAIRS; ++i) {
-        const int k = lane + 16 * i;
-        if (k == 0) {
-          const cplx z0 = zr[0];
-          st_stream(orow, cmake(z0.x + z0.y, 0.f));
-          st_stream(orow + M, cmake(z0.x - z0.y, 0.f));
-          st_stream(orow + M / 2, cconj(zr[M / 2]));
-        } else {
-          cplx xk, xm;
-          r2c_pair(zr[k], zr[M - k], twp[i], xk, xm);
-          st_stream(orow + k, xk);
-          st_stream(orow + (M - k), xm);
-        }
-      }
-    }
-    __syncwarp();
-  }
+  RowTw<M> T;
+  T.load(A, lane);
+  for (long long row0 = ((long long)blockIdx.x * CF::GROUPS + group) * CF::RPG; row0 < rows;
+       row0 += (long long)gridDim.x * CF::ROWS)
+    rows_fwd_group<M, WRAPPED>(A, slab, row0, lane, T);
 }
 
 template <int M>
 static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_inv2(RowArgs A) {
   typedef Row2Cfg<M> CF;
-  constexpr int R1 = CF::R1, RPG = CF::RPG, RS = CF::RS, PAIRS = CF::PAIRS;
-  constexpr int nx = 2 * M;
   LMVN_DYN_SMEM(cplx, sm);
   const int lane = threadIdx.x % 16;
   const int group = threadIdx.x / 16;
-  cplx* slab = sm + group * (RPG * RS);
+  cplx* slab = sm + group * (CF::RPG * CF::RS);
   const long long rows = (long long)A.nz * A.ny;
-  cplx tw1[R1];
-#pragma unroll
-  for (int q = 1; q < R1; ++q) tw1[q] = __ldg(A.tw_m + lane * q);
-  cplx twp[PAIRS];
-#pragma unroll
-  for (int i = 0; i < PAIRS; ++i) twp[i] = __ldg(A.tw_nx + lane + 16 * i);
-  const int q_blk = lane % R1, r_blk = lane / R1;
-  const int mode = A.ep.mode;
+  RowTw<M> T;
+  T.load(A, lane);
+  for (long long row0 = ((long long)blockIdx.x * CF::GROUPS + group) * CF::RPG; row0 < rows;
+       row0 += (long long)gridDim.x * CF::ROWS)
+    rows_inv_group<M>(A, slab, row0, lane, T);
+}
 
-  for (long long row0 = ((long long)blockIdx.x * CF::GROUPS + group) * RPG; row0 < rows;
-       row0 += (long long)gridDim.x * CF::ROWS) {
-    // ---- spectrum loads (full lines) + inverse split into the slab, natural order ----
-    cplx xs[RPG * PAIRS], xm[RPG * PAIRS];
-    cplx xh[RPG], xn[RPG];
-#pragma unroll
-    for (int a = 0; a < RPG; ++a) {
-      const cplx* irow = A.spec + (row0 + a) * A.nxp;
-#pragma unroll
-      for (int i = 0; i < PAIRS; ++i) {
-        const int k = lane + 16 * i;
-        xs[a * PAIRS + i] = ld_stream(irow + k);
-        xm[a * PAIRS + i] = ld_stream(irow + (M - k));  // k = 0 reads X[M]
-      }
-      if (lane == 0) xh[a] = ld_stream(irow + M / 2);
+// ------------------------------------------------------------------------------
+// x and y passes in ONE persistent launch, plane by plane, so that the x<->y
+// intermediate of a plane lives in the 126 MB L2 and never makes an HBM round trip
+// (HBM traffic of the launch: S + C instead of S + 3C).
+//
+// Work items are handed out by a global ticket counter in plane order:
+//   forward   step s:  row items of plane s (x transform, ROWS rows each), then the
+//                      y tiles of plane s - lag;
+//   inverse   step s:  y tiles of plane s, then the row items of plane s - lag.
+// A consumer item waits for its plane's completion counter.  An item only depends on
+// items with SMALLER tickets, and a ticket is only ever held by a running CTA, so the
+// waits cannot deadlock whatever the residency; `lag` is sized so that the producers of
+// a plane have normally finished by the time its consumers are handed out.
+// The sync block (ticket, error flag, per-plane counters) is zeroed by the PREVIOUS
+// launch of the ring (engine side), so no memset sits between launches.
+// ------------------------------------------------------------------------------
+struct XYArgs {
+  RowArgs rows;
+  StridedArgs y;          // data = spectrum base, row_stride = nxp, tile_stride = ny * nxp
+  unsigned* sync;         // this launch: [0] ticket, [1] error flag, [4 + p] plane counters
+  unsigned* sync_next;    // next launch's block, cleared here
+  int sync_words;
+  int lag;                // planes between producer and consumer hand-out
+};
+
+__device__ __forceinline__ void plane_signal(unsigned* counter) {
+  __threadfence();
+  atomicAdd(counter, 1u);
+}
+__device__ __forceinline__ void plane_wait(unsigned* counter, unsigned target, unsigned* err) {
+#ifdef LMVN_EMU
+  if (*counter < target) { std::fprintf(stderr, "emu: plane_wait would block\n"); std::abort(); }
+  (void)err;
+#else
+  unsigned v;
+  unsigned spins = 0;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    if (v >= target) break;
+    __nanosleep(64);
+    if (++spins > (1u << 24)) {  // ~seconds: a lost producer must not hang the device
+      *err = 1u;
+      break;
     }
-    // epilogue operands: independent of the transform, fetched now so that their latency
-    // overlaps both exchanges (element n = lane + 16 r of each row = real samples 2n, 2n+1)
-    float2 oa[16], ob[16];
-    if (mode != gen::EPI_STORE) {
-      const float* pa = (mode == gen::EPI_QUOTIENT) ? A.ep.view : A.ep.psi;
-#pragma unroll
-      for (int a = 0; a < RPG; ++a) {
-        const float2* p2 = reinterpret_cast<const float2*>(pa + (row0 + a) * nx);
-#pragma unroll
-        for (int r = 0; r < R1; ++r) oa[a * R1 + r] = ld_stream(p2 + lane + 16 * r);
-      }
-      if (mode == gen::EPI_UPDATE) {
-#pragma unroll
-        for (int a = 0; a < RPG; ++a) {
-          const float2* p2 = reinterpret_cast<const float2*>(A.ep.weights + (row0 + a) * nx);
-#pragma unroll
-          for (int r = 0; r < R1; ++r) ob[a * R1 + r] = ld_stream(p2 + lane + 16 * r);
-        }
-      }
+  }
+#endif
+}
+
+template <int M, int NY, bool INVERSE, bool WRAPPED>
+static __global__ void __launch_bounds__(kRowThreads, 2) k_xy(XYArgs A) {
+  typedef Row2Cfg<M> CF;
+  constexpr int COLS = Cols<NY>::V;
+  constexpr int MODE = INVERSE ? SM_INV : SM_FWD;
+  static_assert(kStridedThreads == kRowThreads, "one block shape for both item kinds");
+  LMVN_DYN_SMEM(cplx, sm);  // max(row slabs, [NY][COLS] tile)
+  __shared__ unsigned s_ticket;
+  const int lane = threadIdx.x % 16;
+  const int group = threadIdx.x / 16;
+  cplx* slab = sm + group * (CF::RPG * CF::RS);
+  const int c = threadIdx.x % COLS;
+  const int nz = A.rows.nz, ny = A.rows.ny;
+  const int n_r = ny / CF::ROWS;
+  const int n_y = (A.y.ncols + COLS - 1) / COLS;
+  const int per_step = n_r + n_y;
+  const unsigned total = unsigned(nz + A.lag) * unsigned(per_step);
+  unsigned* done = A.sync + 4;
+  // clear the next launch's sync block (nobody uses it while this launch runs)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.sync_words; i += gridDim.x * blockDim.x)
+    A.sync_next[i] = 0u;
+
+  for (;;) {
+    __syncthreads();  // everybody is done with s_ticket and the shared-memory tile
+    if (threadIdx.x == 0) s_ticket = atomicAdd(A.sync, 1u);
+    __syncthreads();
+    const unsigned tk = s_ticket;
+    if (tk >= total) break;
+    const int step = int(tk / unsigned(per_step));
+    const int r = int(tk % unsigned(per_step));
+    // first group of a step = producers of plane `step`, second = consumers of plane `step - lag`
+    const bool first = INVERSE ? (r < n_y) : (r < n_r);
+    const int plane = first ? step : step - A.lag;
+    if (plane < 0 || plane >= nz) continue;
+    const bool is_rows = (first != INVERSE);
+    const int idx = first ? r : r - (INVERSE ? n_y : n_r);
+    if (!first) {
+      if (threadIdx.x == 0) plane_wait(done + plane, unsigned(INVERSE ? n_y : n_r), A.sync + 1);
+      __syncthreads();
     }
-#pragma unroll
-    for (int a = 0; a < RPG; ++a) {
-      cplx* zr = slab + a * RS;
-#pragma unroll
-      for (int i = 0; i < PAIRS; ++i) {
-        const int k = lane + 16 * i;
-        if (k == 0) {
-          const float x0 = xs[a * PAIRS + i].x, xM = xm[a * PAIRS + i].x;  // imaginary parts ignored (c2r)
-          zr[0] = cmake(x0 + xM, x0 - xM);
-          zr[M / 2] = cmake(2.f * xh[a].x, -2.f * xh[a].y);
-        } else {
-          cplx zk, zm;
-          c2r_pair(xs[a * PAIRS + i], xm[a * PAIRS + i], twp[i], zk, zm);
-          zr[k] = zk;
-          zr[M - k] = zm;
-        }
-      }
+    if (is_rows) {
+      const long long row0 = (long long)plane * ny + (long long)idx * CF::ROWS + group * CF::RPG;
+      RowTw<M> T;  // per item: keeps them out of the registers of the y tiles
+      T.load(A.rows, lane);
+      if (INVERSE) rows_inv_group<M>(A.rows, slab, row0, lane, T);
+      else rows_fwd_group<M, WRAPPED>(A.rows, slab, row0, lane, T);
+    } else {
+      const int col = idx * COLS + c;
+      const long long base = (long long)plane * A.y.tile_stride + col;
+      strided_tile<NY, MODE, LMVN_Y_UNROLL>(A.y, sm + c, A.y.data + base, nullptr, col < A.y.ncols);
     }
-    (void)xn;
-    __syncwarp();
-    cplx v[16];
-    {
-      const cplx* p = slab + r_blk * RS + q_blk;
-#pragma unroll
-      for (int q2 = 0; q2 < 16; ++q2) v[q2] = p[R1 * q2];
+    if (first) {
+      __syncthreads();
+      if (threadIdx.x == 0) plane_signal(done + plane);
     }
-    Bfly<16, true>::run(v);
-    __syncwarp();
-    {
-      cplx* p = slab + r_blk * RS + q_blk * 17;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) p[j] = v[j];
-    }
-    __syncwarp();
-    float* obase = (mode == gen::EPI_UPDATE) ? A.ep.psi : A.out;
-#pragma unroll
-    for (int a = 0; a < RPG; ++a) {
-#pragma unroll
-      for (int q = 0; q < R1; ++q) {
-        cplx x = slab[a * RS + q * 17 + lane];
-        if (q > 0) x = cmulc(x, tw1[q]);
-        v[a * R1 + q] = x;
-      }
-      Bfly<R1, true>::run(v + a * R1);
-      float2* orow = reinterpret_cast<float2*>(obase + (row0 + a) * nx);
-#pragma unroll
-      for (int r = 0; r < R1; ++r) {
-        float2 val = make_float2(v[a * R1 + r].x * A.ep.scale, v[a * R1 + r].y * A.ep.scale);
-        if (mode == gen::EPI_QUOTIENT) {
-          val.x = quotient(oa[a * R1 + r].x, val.x);
-          val.y = quotient(oa[a * R1 + r].y, val.y);
-        } else if (mode == gen::EPI_UPDATE) {
-          val.x = rl_update(oa[a * R1 + r].x, val.x, ob[a * R1 + r].x, A.ep.up);
-          val.y = rl_update(oa[a * R1 + r].y, val.y, ob[a * R1 + r].y, A.ep.up);
-        }
-        st_stream(orow + lane + 16 * r, val);
-      }
-    }
-    __syncwarp();
   }
 }
 

@@ -15,6 +15,7 @@
 
 #include "engine.cuh"
 #include "fft_fast.cuh"
+#include "fft_fused_xy.cuh"
 
 namespace lmvn {
 
@@ -25,8 +26,13 @@ bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 struct FastEngine : ConvEngine {
   int M = 0, nxc = 0, nxp = 0;
   int num_sms = 148;
-  bool rows_v2 = true;
   int rows_ctas_per_sm = 8;
+  // fused x/y launches (fft_fused_xy.cu): ring of sync blocks, each cleared by the launch before it
+  bool xy_ok = false;
+  int xy_grid = 0, xy_lag = 0, xy_sync_words = 0;
+  unsigned xy_seq = 0;
+  unsigned* d_xy_sync = nullptr;
+  static const int kSyncRing = 4;
   cplx* d_tw_m = nullptr;
   cplx* d_tw_nx = nullptr;
   cplx* d_tw_y[2] = {nullptr, nullptr};  // per-stage tables of the y / z passes
@@ -35,6 +41,7 @@ struct FastEngine : ConvEngine {
   ~FastEngine() override {
     if (d_tw_m) cudaFree(d_tw_m);
     if (d_tw_nx) cudaFree(d_tw_nx);
+    if (d_xy_sync) cudaFree(d_xy_sync);
     for (int i = 0; i < 2; ++i) {
       if (d_tw_y[i]) cudaFree(d_tw_y[i]);
       if (d_tw_z[i]) cudaFree(d_tw_z[i]);
@@ -43,7 +50,7 @@ struct FastEngine : ConvEngine {
   int strategy() const override { return 2; }
   size_t khat_elems() const override { return size_t(plan->nz) * plan->ny * nxp; }
   size_t work_elems() const override { return khat_elems(); }
-  int launches_per_conv() const override { return 5; }
+  int launches_per_conv() const override { return xy_ok ? 3 : 5; }
   unsigned long long S() const { return plan->voxels() * sizeof(float); }
   unsigned long long C() const { return plan->spec_elems() * sizeof(cplx); }
 
@@ -61,16 +68,70 @@ struct FastEngine : ConvEngine {
   int init() {
     M = plan->nx / 2;
     nxc = plan->nxc;
-    nxp = (nxc + 15) / 16 * 16;
+    {
+      int align = 16;  // complex elements; 16 = one 128-byte line per tile row
+      if (const char* e = getenv("LMVN_NXP_ALIGN")) align = std::max(1, atoi(e));
+      nxp = (nxc + align - 1) / align * align;
+    }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, plan->device) == cudaSuccess && prop.multiProcessorCount > 0)
       num_sms = prop.multiProcessorCount;
-    if (const char* e = getenv("LMVN_ROWS_V2")) rows_v2 = (*e != '0');
     if (const char* e = getenv("LMVN_ROWS_CTAS")) rows_ctas_per_sm = std::max(1, atoi(e));
     LMVN_TRY(upload_table(&d_tw_m, M, M));
     LMVN_TRY(upload_table(&d_tw_nx, plan->nx, M + 1));
     LMVN_TRY(upload_stage_tables(d_tw_y, plan->ny));
     LMVN_TRY(upload_stage_tables(d_tw_z, plan->nz));
+    LMVN_TRY(init_xy());
+    return 0;
+  }
+
+  int init_xy() {
+    bool want = true;
+    if (const char* e = getenv("LMVN_XY_FUSED")) want = (*e != '0');
+    int ctas_per_sm = 0;
+    if (!want || !fast::xy_supported(M, plan->ny, &ctas_per_sm) || ctas_per_sm < 1) return 0;
+    xy_grid = num_sms * ctas_per_sm;
+    if (const char* e = getenv("LMVN_XY_GRID")) xy_grid = std::max(1, atoi(e));
+    const int per_step = fast::xy_items_per_plane(M, plan->ny, nxc);
+    xy_lag = (xy_grid + xy_grid / 4 + per_step - 1) / per_step + 1;
+    if (const char* e = getenv("LMVN_XY_LAG")) xy_lag = std::max(0, atoi(e));
+    xy_sync_words = (4 + plan->nz + 3) / 4 * 4;
+    const size_t bytes = sizeof(unsigned) * size_t(xy_sync_words) * kSyncRing;
+    LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_xy_sync), bytes));
+    LMVN_CUDA_TRY(cudaMemset(d_xy_sync, 0, bytes));
+    xy_ok = true;
+    return 0;
+  }
+
+  // x+y forward (src -> spec) or y+x inverse with epilogue (spec -> out / psi) in one persistent launch
+  int xy(const gen::RealSource* src, cplx* spec, float* out, const gen::Epilogue* ep, cudaStream_t s) {
+    const bool inverse = (src == nullptr);
+    fast::XYArgs a;
+    std::memset(&a, 0, sizeof(a));
+    if (src) a.rows.src = *src;
+    a.rows.spec = spec;
+    a.rows.out = out;
+    if (ep) a.rows.ep = *ep;
+    a.rows.nz = plan->nz; a.rows.ny = plan->ny; a.rows.nxp = nxp;
+    a.rows.tw_m = d_tw_m; a.rows.tw_nx = d_tw_nx;
+    a.y.data = spec;
+    a.y.khat = nullptr;
+    a.y.row_stride = nxp;
+    a.y.tile_stride = (long long)plan->ny * nxp;
+    a.y.ncols = nxc;
+    a.y.tw1 = d_tw_y[0]; a.y.tw2 = d_tw_y[1];
+    a.y.scale = 1.f;
+    a.sync = d_xy_sync + size_t(xy_seq % kSyncRing) * xy_sync_words;
+    a.sync_next = d_xy_sync + size_t((xy_seq + 1) % kSyncRing) * xy_sync_words;
+    a.sync_words = xy_sync_words;
+    a.lag = xy_lag;
+    ++xy_seq;
+    LMVN_TRY(fast::launch_xy(M, plan->ny, inverse, a, xy_grid, s));
+    LMVN_CUDA_TRY(cudaGetLastError());
+    if (!inverse) mark("fast_xy_fwd", S() + C(), s);
+    else mark(ep->mode == gen::EPI_UPDATE ? "fast_yx_inv_update"
+                                          : (ep->mode == gen::EPI_QUOTIENT ? "fast_yx_inv_quotient" : "fast_yx_inv"),
+              C() + S() * (ep->mode == gen::EPI_UPDATE ? 3 : (ep->mode == gen::EPI_QUOTIENT ? 2 : 1)), s);
     return 0;
   }
 
@@ -78,12 +139,12 @@ struct FastEngine : ConvEngine {
   static int upload_stage_tables(cplx** dst, int n) {
     int r1, r2;
     switch (n) {
-      case 512: r1 = 8; r2 = 8; break;
-      case 256: r1 = 8; r2 = 8; break;
-      case 128: r1 = 8; r2 = 4; break;
-      case 64: r1 = 8; r2 = 8; break;
-      case 32: r1 = 8; r2 = 4; break;
-      case 16: r1 = 4; r2 = 4; break;
+      case 512: r1 = fast::Radix<512>::R1; r2 = fast::Radix<512>::R2; break;
+      case 256: r1 = fast::Radix<256>::R1; r2 = fast::Radix<256>::R2; break;
+      case 128: r1 = fast::Radix<128>::R1; r2 = fast::Radix<128>::R2; break;
+      case 64: r1 = fast::Radix<64>::R1; r2 = fast::Radix<64>::R2; break;
+      case 32: r1 = fast::Radix<32>::R1; r2 = fast::Radix<32>::R2; break;
+      case 16: r1 = fast::Radix<16>::R1; r2 = fast::Radix<16>::R2; break;
       default: set_last_error("fused path: unsupported axis length %d", n); return -1;
     }
     const int spans[2] = {n, n / r1};
@@ -132,39 +193,6 @@ struct FastEngine : ConvEngine {
     return 0;
   }
 
-  template <int MM>
-  int launch_rows_fwd(const fast::RowArgs& a, bool wrapped, cudaStream_t s) {
-    typedef fast::RowCfg<MM> CF;
-    const size_t rows = size_t(a.nz) * plan->ny;
-    const dim3 grid(unsigned(ceil_div(rows, CF::ROWS)));
-    const size_t smem = size_t(CF::ROWS) * CF::SLAB * sizeof(cplx);
-    auto kw = fast::k_rows_fwd<MM, true>;
-    auto kp = fast::k_rows_fwd<MM, false>;
-    if (smem > 48 * 1024) {
-      LMVN_CUDA_TRY(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      LMVN_CUDA_TRY(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    }
-    if (wrapped) {
-      LMVN_LAUNCH(kw, grid, dim3(fast::kRowThreads), smem, s, a);
-    } else {
-      LMVN_LAUNCH(kp, grid, dim3(fast::kRowThreads), smem, s, a);
-    }
-    return 0;
-  }
-  template <int MM>
-  int launch_rows_inv(const fast::RowArgs& a, cudaStream_t s) {
-    typedef fast::RowCfg<MM> CF;
-    const size_t rows = size_t(a.nz) * plan->ny;
-    const dim3 grid(unsigned(ceil_div(rows, CF::ROWS)));
-    const size_t smem = size_t(CF::ROWS) * CF::SLAB * sizeof(cplx);
-    auto kfn = fast::k_rows_inv<MM>;
-    if (smem > 48 * 1024) {
-      LMVN_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    }
-    LMVN_LAUNCH(kfn, grid, dim3(fast::kRowThreads), smem, s, a);
-    return 0;
-  }
-
   // z0/nzs select a slab of planes (whole volume by default); wrapped sources are whole-volume only
   int rows_fwd(const gen::RealSource& src_in, cplx* spec, cudaStream_t s, int z0 = 0, int nzs = -1) {
     if (nzs < 0) nzs = plan->nz;
@@ -177,18 +205,10 @@ struct FastEngine : ConvEngine {
     a.nz = nzs; a.ny = plan->ny; a.nxp = nxp;
     a.tw_m = d_tw_m; a.tw_nx = d_tw_nx;
     const bool w = src.wrapped != 0;
-    if (rows_v2) {
-      switch (M) {
-        case 32: LMVN_TRY(launch_rows_fwd2<32>(a, w, s)); break;
-        case 64: LMVN_TRY(launch_rows_fwd2<64>(a, w, s)); break;
-        case 128: LMVN_TRY(launch_rows_fwd2<128>(a, w, s)); break;
-        default: set_last_error("fused path: unsupported nx"); return -1;
-      }
-    } else
     switch (M) {
-      case 32: LMVN_TRY(launch_rows_fwd<32>(a, w, s)); break;
-      case 64: LMVN_TRY(launch_rows_fwd<64>(a, w, s)); break;
-      case 128: LMVN_TRY(launch_rows_fwd<128>(a, w, s)); break;
+      case 32: LMVN_TRY(launch_rows_fwd2<32>(a, w, s)); break;
+      case 64: LMVN_TRY(launch_rows_fwd2<64>(a, w, s)); break;
+      case 128: LMVN_TRY(launch_rows_fwd2<128>(a, w, s)); break;
       default: set_last_error("fused path: unsupported nx"); return -1;
     }
     LMVN_CUDA_TRY(cudaGetLastError());
@@ -210,18 +230,10 @@ struct FastEngine : ConvEngine {
     a.ep = ep;
     a.nz = nzs; a.ny = plan->ny; a.nxp = nxp;
     a.tw_m = d_tw_m; a.tw_nx = d_tw_nx;
-    if (rows_v2) {
-      switch (M) {
-        case 32: LMVN_TRY(launch_rows_inv2<32>(a, s)); break;
-        case 64: LMVN_TRY(launch_rows_inv2<64>(a, s)); break;
-        case 128: LMVN_TRY(launch_rows_inv2<128>(a, s)); break;
-        default: set_last_error("fused path: unsupported nx"); return -1;
-      }
-    } else
     switch (M) {
-      case 32: LMVN_TRY(launch_rows_inv<32>(a, s)); break;
-      case 64: LMVN_TRY(launch_rows_inv<64>(a, s)); break;
-      case 128: LMVN_TRY(launch_rows_inv<128>(a, s)); break;
+      case 32: LMVN_TRY(launch_rows_inv2<32>(a, s)); break;
+      case 64: LMVN_TRY(launch_rows_inv2<64>(a, s)); break;
+      case 128: LMVN_TRY(launch_rows_inv2<128>(a, s)); break;
       default: set_last_error("fused path: unsupported nx"); return -1;
     }
     LMVN_CUDA_TRY(cudaGetLastError());
@@ -306,6 +318,12 @@ struct FastEngine : ConvEngine {
   int convolve(const float* in, cplx* work, const cplx* khat, const gen::Epilogue& ep, float* out,
                cudaStream_t s) override {
     gen::RealSource src{in, 0, 0, 0, 0};
+    if (xy_ok) {
+      LMVN_TRY(xy(&src, work, nullptr, nullptr, s));
+      LMVN_TRY(strided(work, khat, 0, fast::SM_FWD_MUL_INV, 1.f, s));
+      LMVN_TRY(xy(nullptr, work, out, &ep, s));
+      return 0;
+    }
     static int slabs = -1;
     if (slabs < 0) {
       const char* e = getenv("LMVN_SLABS");

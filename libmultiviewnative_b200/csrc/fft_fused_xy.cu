@@ -1,0 +1,110 @@
+// fft_fused_xy.cu -- instantiations and launchers of fast::k_xy (x and y passes of a plane in one
+// persistent, ticket-ordered launch; the intermediate stays in L2).  See fft_fast.cuh.
+#include <algorithm>
+
+#include "fft_fused_xy.cuh"
+
+namespace lmvn {
+namespace fast {
+
+namespace {
+
+template <int M, int NY>
+struct XY {
+  static size_t smem() {
+    return std::max(size_t(Row2Cfg<M>::SMEM), size_t(NY) * Cols<NY>::V * sizeof(cplx));
+  }
+  static int occupancy() {
+#ifdef LMVN_EMU
+    return 1;
+#else
+    int n_f = 0, n_i = 0;
+    auto kf = k_xy<M, NY, false, false>;
+    auto ki = k_xy<M, NY, true, false>;
+    if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem())) != cudaSuccess) return 0;
+    if (cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem())) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n_f, kf, kRowThreads, smem()) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n_i, ki, kRowThreads, smem()) != cudaSuccess) return 0;
+    return std::min(n_f, n_i);
+#endif
+  }
+  static int launch(bool inverse, const XYArgs& a, int grid, cudaStream_t s) {
+    auto kf = k_xy<M, NY, false, false>;
+    auto ki = k_xy<M, NY, true, false>;
+    if (inverse) {
+      LMVN_LAUNCH(ki, dim3(unsigned(grid)), dim3(kRowThreads), smem(), s, a);
+    } else {
+      LMVN_LAUNCH(kf, dim3(unsigned(grid)), dim3(kRowThreads), smem(), s, a);
+    }
+    return 0;
+  }
+};
+
+}  // namespace
+
+#define LMVN_XY_DISPATCH(EXPR)                                     \
+  switch (M) {                                                     \
+    case 32:                                                       \
+      switch (ny) {                                                \
+        case 128: { typedef XY<32, 128> K; EXPR; } break;          \
+        case 256: { typedef XY<32, 256> K; EXPR; } break;          \
+        case 512: { typedef XY<32, 512> K; EXPR; } break;          \
+        default: break;                                            \
+      }                                                            \
+      break;                                                       \
+    case 64:                                                       \
+      switch (ny) {                                                \
+        case 128: { typedef XY<64, 128> K; EXPR; } break;          \
+        case 256: { typedef XY<64, 256> K; EXPR; } break;          \
+        case 512: { typedef XY<64, 512> K; EXPR; } break;          \
+        default: break;                                            \
+      }                                                            \
+      break;                                                       \
+    case 128:                                                      \
+      switch (ny) {                                                \
+        case 128: { typedef XY<128, 128> K; EXPR; } break;         \
+        case 256: { typedef XY<128, 256> K; EXPR; } break;         \
+        case 512: { typedef XY<128, 512> K; EXPR; } break;         \
+        default: break;                                            \
+      }                                                            \
+      break;                                                       \
+    default: break;                                                \
+  }
+
+bool xy_supported(int M, int ny, int* ctas_per_sm) {
+  int occ = -1;
+  LMVN_XY_DISPATCH(occ = K::occupancy())
+  if (occ < 0) return false;
+  *ctas_per_sm = occ;
+  return true;
+}
+
+int xy_items_per_plane(int M, int ny, int ncols) {
+  int rows_per_item = 0, cols = 0;
+  switch (M) {
+    case 32: rows_per_item = Row2Cfg<32>::ROWS; break;
+    case 64: rows_per_item = Row2Cfg<64>::ROWS; break;
+    case 128: rows_per_item = Row2Cfg<128>::ROWS; break;
+    default: return 1;
+  }
+  switch (ny) {
+    case 128: cols = Cols<128>::V; break;
+    case 256: cols = Cols<256>::V; break;
+    case 512: cols = Cols<512>::V; break;
+    default: return 1;
+  }
+  return ny / rows_per_item + (ncols + cols - 1) / cols;
+}
+
+int launch_xy(int M, int ny, bool inverse, const XYArgs& a, int grid, cudaStream_t s) {
+  int rc = -2;
+  LMVN_XY_DISPATCH(rc = K::launch(inverse, a, grid, s))
+  if (rc == -2) {
+    set_last_error("fused x/y pass: unsupported shape (nx = %d, ny = %d)", 2 * M, ny);
+    return -1;
+  }
+  return rc;
+}
+
+}  // namespace fast
+}  // namespace lmvn

@@ -42,6 +42,10 @@ def main():
                     best[name] = a
         total = sum(a[0] for a in best.values())
         alg = info.alg_bytes_per_view_iteration
+        loop = min(p.iterate(10, 0.006, 1e-4) for _ in range(3)) / 10.0
+        print("lib=%s dims=%s  LOOP (no per-launch events) %.4f ms per view-iteration -> %.1f%% of 6450 GB/s (7S+10C), %.1f Gvox/s" % (
+            os.path.basename(lib.path), dims, loop, 100 * alg / (loop * 1e-3) / 1e9 / 6450,
+            np.prod(dims) / (loop * 1e-3) / 1e9))
         print("lib=%s dims=%s strategy=%d  view-iteration %.4f ms  -> %.1f%% of 6450 GB/s roofline (7S+10C)" % (
             os.path.basename(lib.path), dims, info.strategy, total, 100 * alg / (total * 1e-3) / 1e9 / 6450))
         for name in order:
