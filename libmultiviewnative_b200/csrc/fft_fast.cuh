@@ -204,6 +204,8 @@ struct StridedArgs {
   const cplx* tw1;        // stage-1 twiddles, [j][q] = w_N^{jq},      j < N/R1, q < R1
   const cplx* tw2;        // stage-2 twiddles, [j][q] = w_{N/R1}^{jq}, j < N/(R1 R2), q < R2
   float scale;            // SM_FWD_SCALE
+  int prefetch;           // > 0: every CTA first pulls the tile of block (id + prefetch) into L2
+  int prefetch_khat;      // SM_FWD_MUL_INV: pull the CTA's own K^ tile into L2 at kernel entry
 };
 
 // number of stages and the radix of stage s for N = R1*R2*R3
@@ -392,6 +394,25 @@ static __global__ void __launch_bounds__(kStridedThreads, StridedBlocks<N, MODE>
   const int col = blockIdx.x * COLS + c;
   const long long base = (long long)blockIdx.y * A.tile_stride + col;
   constexpr int U = (MODE == SM_FWD_MUL_INV) ? LMVN_ZMUL_UNROLL : LMVN_Y_UNROLL;
+  if (MODE == SM_FWD_MUL_INV && A.prefetch_khat) {
+    // K^ is first needed two stages from now: start its trip from HBM to L2 right away
+    constexpr int LINES = COLS / 16;
+    const long long tb = (long long)blockIdx.y * A.tile_stride + blockIdx.x * COLS;
+    for (int i = threadIdx.x; i < N * LINES; i += kStridedThreads)
+      prefetch_l2(A.khat + tb + (long long)(i / LINES) * A.row_stride + (i % LINES) * 16);
+  }
+  if (A.prefetch > 0) {
+    // the block that will take this CTA's slot next: its loads then hit L2 instead of waiting for HBM
+    const long long id = (long long)blockIdx.y * gridDim.x + blockIdx.x + A.prefetch;
+    if (id < (long long)gridDim.x * gridDim.y) {
+      const long long fb = (id / gridDim.x) * A.tile_stride + (id % gridDim.x) * COLS;
+      constexpr int LINES = COLS / 16;  // 128-byte lines per tile row
+      for (int i = threadIdx.x; i < N * LINES; i += kStridedThreads) {
+        const long long off = fb + (long long)(i / LINES) * A.row_stride + (i % LINES) * 16;
+        prefetch_l2(A.data + off);
+      }
+    }
+  }
   strided_tile<N, MODE, U>(A, smem + c, A.data + base, A.khat + base, col < A.ncols);
 }
 
@@ -419,6 +440,7 @@ struct RowArgs {
   int nxp;               // spectrum row pitch (complex)
   const cplx* tw_m;      // w_M table (M entries)
   const cplx* tw_nx;     // w_nx^k, k = 0..M
+  int prefetch;          // pull the next loop iteration's rows into L2 one iteration ahead
 };
 
 // real-transform split for one (k, M-k) pair:  X[k] = E + w^k O,  X[M-k] = conj(E - w^k O)
@@ -452,21 +474,39 @@ template <int M> struct Row2Cfg {
 
 // lane-constant twiddles of the row transforms
 template <int M>
-struct RowTw {
-  cplx tw1[Row2Cfg<M>::R1];
-  cplx twp[Row2Cfg<M>::PAIRS];
+struct RowTw {  // in registers
+  cplx t1[Row2Cfg<M>::R1];
+  cplx tp[Row2Cfg<M>::PAIRS];
   __device__ __forceinline__ void load(const RowArgs& A, int lane) {
 #pragma unroll
-    for (int q = 1; q < Row2Cfg<M>::R1; ++q) tw1[q] = __ldg(A.tw_m + lane * q);
+    for (int q = 1; q < Row2Cfg<M>::R1; ++q) t1[q] = __ldg(A.tw_m + lane * q);
 #pragma unroll
-    for (int i = 0; i < Row2Cfg<M>::PAIRS; ++i) twp[i] = __ldg(A.tw_nx + lane + 16 * i);
+    for (int i = 0; i < Row2Cfg<M>::PAIRS; ++i) tp[i] = __ldg(A.tw_nx + lane + 16 * i);
   }
+  __device__ __forceinline__ cplx tw1(int q) const { return t1[q]; }
+  __device__ __forceinline__ cplx twp(int i) const { return tp[i]; }
+};
+// The same table in shared memory, [entry][lane], read at the point of use: frees 2 (R1 + PAIRS)
+// registers where the epilogue operands need them.
+template <int M>
+struct RowTwShared {
+  static const int ENTRIES = Row2Cfg<M>::R1 + Row2Cfg<M>::PAIRS;
+  const cplx* base;  // + lane
+  // all threads of the block call fill(), then __syncthreads()
+  static __device__ __forceinline__ void fill(cplx* table, const RowArgs& A) {
+    for (int i = threadIdx.x; i < ENTRIES * 16; i += kRowThreads) {
+      const int e = i / 16, l = i % 16;
+      table[i] = (e < Row2Cfg<M>::R1) ? __ldg(A.tw_m + l * e) : __ldg(A.tw_nx + l + 16 * (e - Row2Cfg<M>::R1));
+    }
+  }
+  __device__ __forceinline__ cplx tw1(int q) const { return base[q * 16]; }
+  __device__ __forceinline__ cplx twp(int i) const { return base[(Row2Cfg<M>::R1 + i) * 16]; }
 };
 
 // forward transform of rows row0 .. row0+RPG-1 by one 16-lane group (slab: the group's exchange area)
-template <int M, bool WRAPPED>
+template <int M, bool WRAPPED, typename TW>
 __device__ __forceinline__ void rows_fwd_group(const RowArgs& A, cplx* slab, long long row0, int lane,
-                                               const RowTw<M>& T) {
+                                               const TW& T) {
   typedef Row2Cfg<M> CF;
   constexpr int R1 = CF::R1, RPG = CF::RPG, RS = CF::RS, PAIRS = CF::PAIRS;
   constexpr int nx = 2 * M;
@@ -505,7 +545,7 @@ __device__ __forceinline__ void rows_fwd_group(const RowArgs& A, cplx* slab, lon
 #pragma unroll
     for (int q = 0; q < R1; ++q) {
       cplx x = v[a * R1 + q];
-      if (q > 0) x = cmul(x, T.tw1[q]);
+      if (q > 0) x = cmul(x, T.tw1(q));
       slab[a * RS + q * 17 + lane] = x;
     }
   }
@@ -539,7 +579,7 @@ __device__ __forceinline__ void rows_fwd_group(const RowArgs& A, cplx* slab, lon
         st_stream(orow + M / 2, cconj(zr[M / 2]));
       } else {
         cplx xk, xm;
-        r2c_pair(zr[k], zr[M - k], T.twp[i], xk, xm);
+        r2c_pair(zr[k], zr[M - k], T.twp(i), xk, xm);
         st_stream(orow + k, xk);
         st_stream(orow + (M - k), xm);
       }
@@ -549,14 +589,14 @@ __device__ __forceinline__ void rows_fwd_group(const RowArgs& A, cplx* slab, lon
 }
 
 // inverse transform + pointwise epilogue of rows row0 .. row0+RPG-1 by one 16-lane group
-template <int M>
+template <int M, int EPI, typename TW>
 __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, long long row0, int lane,
-                                               const RowTw<M>& T) {
+                                               const TW& T) {
   typedef Row2Cfg<M> CF;
   constexpr int R1 = CF::R1, RPG = CF::RPG, RS = CF::RS, PAIRS = CF::PAIRS;
   constexpr int nx = 2 * M;
   const int q_blk = lane % R1, r_blk = lane / R1;
-  const int mode = A.ep.mode;
+  constexpr int mode = EPI;  // compile time: no branches, no dead operand registers
   // ---- spectrum loads (full lines) ----
   cplx xs[RPG * PAIRS], xm[RPG * PAIRS];
   cplx xh[RPG];
@@ -582,14 +622,6 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
 #pragma unroll
       for (int r = 0; r < R1; ++r) oa[a * R1 + r] = ld_stream(p2 + lane + 16 * r);
     }
-    if (mode == gen::EPI_UPDATE) {
-#pragma unroll
-      for (int a = 0; a < RPG; ++a) {
-        const float2* p2 = reinterpret_cast<const float2*>(A.ep.weights + (row0 + a) * nx);
-#pragma unroll
-        for (int r = 0; r < R1; ++r) ob[a * R1 + r] = ld_stream(p2 + lane + 16 * r);
-      }
-    }
   }
   // ---- inverse split into the slab, natural order ----
 #pragma unroll
@@ -604,13 +636,23 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
         zr[M / 2] = cmake(2.f * xh[a].x, -2.f * xh[a].y);
       } else {
         cplx zk, zm;
-        c2r_pair(xs[a * PAIRS + i], xm[a * PAIRS + i], T.twp[i], zk, zm);
+        c2r_pair(xs[a * PAIRS + i], xm[a * PAIRS + i], T.twp(i), zk, zm);
         zr[k] = zk;
         zr[M - k] = zm;
       }
     }
   }
   __syncwarp();
+  if (mode == gen::EPI_UPDATE) {
+    // the second operand is fetched once the spectrum registers are free (no spills at 128 registers);
+    // its latency still overlaps the radix-16 stage and the second exchange
+#pragma unroll
+    for (int a = 0; a < RPG; ++a) {
+      const float2* p2 = reinterpret_cast<const float2*>(A.ep.weights + (row0 + a) * nx);
+#pragma unroll
+      for (int r = 0; r < R1; ++r) ob[a * R1 + r] = ld_stream(p2 + lane + 16 * r);
+    }
+  }
   cplx v[16];
   {
     const cplx* p = slab + r_blk * RS + q_blk;
@@ -631,7 +673,7 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
 #pragma unroll
     for (int q = 0; q < R1; ++q) {
       cplx x = slab[a * RS + q * 17 + lane];
-      if (q > 0) x = cmulc(x, T.tw1[q]);
+      if (q > 0) x = cmulc(x, T.tw1(q));
       v[a * R1 + q] = x;
     }
     Bfly<R1, true>::run(v + a * R1);
@@ -662,24 +704,44 @@ static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_fwd2(RowArgs A) 
   const long long rows = (long long)A.nz * A.ny;
   RowTw<M> T;
   T.load(A, lane);
-  for (long long row0 = ((long long)blockIdx.x * CF::GROUPS + group) * CF::RPG; row0 < rows;
-       row0 += (long long)gridDim.x * CF::ROWS)
+  const long long stride = (long long)gridDim.x * CF::ROWS;
+  for (long long row0 = ((long long)blockIdx.x * CF::GROUPS + group) * CF::RPG; row0 < rows; row0 += stride) {
+    if (!WRAPPED && A.prefetch && row0 + stride < rows)  // next iteration's RPG rows = 16 lines
+      prefetch_l2(reinterpret_cast<const char*>(A.src.data + (row0 + stride) * (2 * M)) + lane * (CF::RPG * M / 2));
     rows_fwd_group<M, WRAPPED>(A, slab, row0, lane, T);
+  }
 }
 
-template <int M>
+template <int M, int EPI>
 static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_inv2(RowArgs A) {
   typedef Row2Cfg<M> CF;
   LMVN_DYN_SMEM(cplx, sm);
+  __shared__ cplx s_tw[RowTwShared<M>::ENTRIES * 16];
   const int lane = threadIdx.x % 16;
   const int group = threadIdx.x / 16;
   cplx* slab = sm + group * (CF::RPG * CF::RS);
   const long long rows = (long long)A.nz * A.ny;
-  RowTw<M> T;
-  T.load(A, lane);
-  for (long long row0 = ((long long)blockIdx.x * CF::GROUPS + group) * CF::RPG; row0 < rows;
-       row0 += (long long)gridDim.x * CF::ROWS)
-    rows_inv_group<M>(A, slab, row0, lane, T);
+  RowTwShared<M>::fill(s_tw, A);
+  __syncthreads();
+  RowTwShared<M> T;
+  T.base = s_tw + lane;
+  const long long stride = (long long)gridDim.x * CF::ROWS;
+  for (long long row0 = ((long long)blockIdx.x * CF::GROUPS + group) * CF::RPG; row0 < rows; row0 += stride) {
+    if (A.prefetch && row0 + stride < rows) {
+      // next iteration: RPG spectrum rows (RPG * nxp * 8 bytes) and RPG operand rows (16 lines each)
+      const long long nr = row0 + stride;
+      const char* sp = reinterpret_cast<const char*>(A.spec + nr * A.nxp);
+      const int spec_bytes = CF::RPG * A.nxp * int(sizeof(cplx));
+      for (int b = lane * 128; b < spec_bytes; b += 16 * 128) prefetch_l2(sp + b);
+      const int ob = lane * (CF::RPG * M / 2);
+      if (EPI == gen::EPI_QUOTIENT) prefetch_l2(reinterpret_cast<const char*>(A.ep.view + nr * (2 * M)) + ob);
+      if (EPI == gen::EPI_UPDATE) {
+        prefetch_l2(reinterpret_cast<const char*>(A.ep.psi + nr * (2 * M)) + ob);
+        prefetch_l2(reinterpret_cast<const char*>(A.ep.weights + nr * (2 * M)) + ob);
+      }
+    }
+    rows_inv_group<M, EPI>(A, slab, row0, lane, T);
+  }
 }
 
 // ------------------------------------------------------------------------------
@@ -730,14 +792,25 @@ __device__ __forceinline__ void plane_wait(unsigned* counter, unsigned target, u
 #endif
 }
 
-template <int M, int NY, bool INVERSE, bool WRAPPED>
+// decoded work item of the x/y kernel
+struct XYItem {
+  int plane;      // < 0: nothing to do (padding ticket at either end of the schedule)
+  int idx;        // row item or y tile within the plane
+  bool first;     // producer group of its step
+  bool is_rows;
+};
+
+template <int M, int NY, bool INVERSE, int EPI>
 static __global__ void __launch_bounds__(kRowThreads, 2) k_xy(XYArgs A) {
+  constexpr bool WRAPPED = false;
   typedef Row2Cfg<M> CF;
   constexpr int COLS = Cols<NY>::V;
   constexpr int MODE = INVERSE ? SM_INV : SM_FWD;
   static_assert(kStridedThreads == kRowThreads, "one block shape for both item kinds");
   LMVN_DYN_SMEM(cplx, sm);  // max(row slabs, [NY][COLS] tile)
   __shared__ unsigned s_ticket;
+  __shared__ cplx s_tw[RowTwShared<M>::ENTRIES * 16];
+  RowTwShared<M>::fill(s_tw, A.rows);
   const int lane = threadIdx.x % 16;
   const int group = threadIdx.x / 16;
   cplx* slab = sm + group * (CF::RPG * CF::RS);
@@ -752,38 +825,78 @@ static __global__ void __launch_bounds__(kRowThreads, 2) k_xy(XYArgs A) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.sync_words; i += gridDim.x * blockDim.x)
     A.sync_next[i] = 0u;
 
-  for (;;) {
-    __syncthreads();  // everybody is done with s_ticket and the shared-memory tile
-    if (threadIdx.x == 0) s_ticket = atomicAdd(A.sync, 1u);
-    __syncthreads();
-    const unsigned tk = s_ticket;
-    if (tk >= total) break;
+  auto decode = [&](unsigned tk) {
+    XYItem it;
+    it.plane = -1; it.idx = 0; it.first = false; it.is_rows = false;
+    if (tk >= total) return it;
     const int step = int(tk / unsigned(per_step));
     const int r = int(tk % unsigned(per_step));
     // first group of a step = producers of plane `step`, second = consumers of plane `step - lag`
-    const bool first = INVERSE ? (r < n_y) : (r < n_r);
-    const int plane = first ? step : step - A.lag;
-    if (plane < 0 || plane >= nz) continue;
-    const bool is_rows = (first != INVERSE);
-    const int idx = first ? r : r - (INVERSE ? n_y : n_r);
-    if (!first) {
-      if (threadIdx.x == 0) plane_wait(done + plane, unsigned(INVERSE ? n_y : n_r), A.sync + 1);
+    it.first = INVERSE ? (r < n_y) : (r < n_r);
+    const int plane = it.first ? step : step - A.lag;
+    it.is_rows = (it.first != INVERSE);
+    it.idx = it.first ? r : r - (INVERSE ? n_y : n_r);
+    it.plane = (plane >= 0 && plane < nz) ? plane : -1;
+    return it;
+  };
+  // Pull the HBM-resident inputs of an item into L2 one item ahead of its use; the x<->y
+  // intermediate is in L2 anyway, so every load of the item itself then has L2 latency.
+  auto prefetch = [&](const XYItem& it) {
+    if (it.plane < 0) return;
+    if (it.is_rows) {
+      const size_t first_row = size_t(it.plane) * ny + size_t(it.idx) * CF::ROWS;
+      const size_t off = first_row * (2 * M) * sizeof(float) + size_t(threadIdx.x) * 128;
+      constexpr int BYTES = CF::ROWS * 2 * M * int(sizeof(float));  // contiguous rows of one item
+      if (!INVERSE) {
+        if (!WRAPPED)
+          for (int b = 0; b < BYTES; b += kRowThreads * 128)
+            prefetch_l2(reinterpret_cast<const char*>(A.rows.src.data) + off + b);
+      } else if (EPI != gen::EPI_STORE) {
+        const float* pa = (EPI == gen::EPI_QUOTIENT) ? A.rows.ep.view : A.rows.ep.psi;
+        for (int b = 0; b < BYTES; b += kRowThreads * 128) {
+          prefetch_l2(reinterpret_cast<const char*>(pa) + off + b);
+          if (EPI == gen::EPI_UPDATE)
+            prefetch_l2(reinterpret_cast<const char*>(A.rows.ep.weights) + off + b);
+        }
+      }
+    } else if (INVERSE) {
+      constexpr int LINES = COLS / 16;
+      const cplx* tb = A.y.data + (long long)it.plane * A.y.tile_stride + it.idx * COLS;
+      for (int i = threadIdx.x; i < NY * LINES; i += kRowThreads)
+        prefetch_l2(tb + (long long)(i / LINES) * A.y.row_stride + (i % LINES) * 16);
+    }
+  };
+
+  if (threadIdx.x == 0) s_ticket = atomicAdd(A.sync, 1u);
+  __syncthreads();
+  unsigned tk = s_ticket;
+  while (tk < total) {
+    __syncthreads();  // everybody has read s_ticket and is done with the shared-memory tile
+    if (threadIdx.x == 0) s_ticket = atomicAdd(A.sync, 1u);
+    __syncthreads();
+    const unsigned tk_next = s_ticket;
+    const XYItem it = decode(tk);
+    prefetch(decode(tk_next));
+    tk = tk_next;
+    if (it.plane < 0) continue;
+    if (!it.first) {
+      if (threadIdx.x == 0) plane_wait(done + it.plane, unsigned(INVERSE ? n_y : n_r), A.sync + 1);
       __syncthreads();
     }
-    if (is_rows) {
-      const long long row0 = (long long)plane * ny + (long long)idx * CF::ROWS + group * CF::RPG;
-      RowTw<M> T;  // per item: keeps them out of the registers of the y tiles
-      T.load(A.rows, lane);
-      if (INVERSE) rows_inv_group<M>(A.rows, slab, row0, lane, T);
+    if (it.is_rows) {
+      const long long row0 = (long long)it.plane * ny + (long long)it.idx * CF::ROWS + group * CF::RPG;
+      RowTwShared<M> T;
+      T.base = s_tw + lane;
+      if (INVERSE) rows_inv_group<M, EPI>(A.rows, slab, row0, lane, T);
       else rows_fwd_group<M, WRAPPED>(A.rows, slab, row0, lane, T);
     } else {
-      const int col = idx * COLS + c;
-      const long long base = (long long)plane * A.y.tile_stride + col;
+      const int col = it.idx * COLS + c;
+      const long long base = (long long)it.plane * A.y.tile_stride + col;
       strided_tile<NY, MODE, LMVN_Y_UNROLL>(A.y, sm + c, A.y.data + base, nullptr, col < A.y.ncols);
     }
-    if (first) {
+    if (it.first) {
       __syncthreads();
-      if (threadIdx.x == 0) plane_signal(done + plane);
+      if (threadIdx.x == 0) plane_signal(done + it.plane);
     }
   }
 }

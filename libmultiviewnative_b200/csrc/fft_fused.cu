@@ -27,6 +27,9 @@ struct FastEngine : ConvEngine {
   int M = 0, nxc = 0, nxp = 0;
   int num_sms = 148;
   int rows_ctas_per_sm = 8;
+  int y_fwd_prefetch = 148;  // blocks of look-ahead of the L2 prefetch in the forward y pass
+  int khat_prefetch = 0;  // measured: hurts the z pass (plane-strided lines), kept as a knob
+  int rows_prefetch = 1;
   // fused x/y launches (fft_fused_xy.cu): ring of sync blocks, each cleared by the launch before it
   bool xy_ok = false;
   int xy_grid = 0, xy_lag = 0, xy_sync_words = 0;
@@ -76,6 +79,9 @@ struct FastEngine : ConvEngine {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, plan->device) == cudaSuccess && prop.multiProcessorCount > 0)
       num_sms = prop.multiProcessorCount;
+    if (const char* e = getenv("LMVN_PREFETCH")) y_fwd_prefetch = std::max(0, atoi(e));
+    if (const char* e = getenv("LMVN_PREFETCH_KHAT")) khat_prefetch = atoi(e);
+    if (const char* e = getenv("LMVN_PREFETCH_ROWS")) rows_prefetch = atoi(e);
     if (const char* e = getenv("LMVN_ROWS_CTAS")) rows_ctas_per_sm = std::max(1, atoi(e));
     LMVN_TRY(upload_table(&d_tw_m, M, M));
     LMVN_TRY(upload_table(&d_tw_nx, plan->nx, M + 1));
@@ -86,7 +92,9 @@ struct FastEngine : ConvEngine {
   }
 
   int init_xy() {
-    bool want = true;
+    // Off by default: measured on B200, the L2-resident intermediate halves the HBM traffic of the
+    // x/y passes but not their time -- the L2 <-> SM fabric (~6.3 TB/s), not HBM, is what they saturate.
+    bool want = false;
     if (const char* e = getenv("LMVN_XY_FUSED")) want = (*e != '0');
     int ctas_per_sm = 0;
     if (!want || !fast::xy_supported(M, plan->ny, &ctas_per_sm) || ctas_per_sm < 1) return 0;
@@ -121,6 +129,8 @@ struct FastEngine : ConvEngine {
     a.y.ncols = nxc;
     a.y.tw1 = d_tw_y[0]; a.y.tw2 = d_tw_y[1];
     a.y.scale = 1.f;
+    a.y.prefetch = 0;
+    a.y.prefetch_khat = 0;
     a.sync = d_xy_sync + size_t(xy_seq % kSyncRing) * xy_sync_words;
     a.sync_next = d_xy_sync + size_t((xy_seq + 1) % kSyncRing) * xy_sync_words;
     a.sync_words = xy_sync_words;
@@ -188,8 +198,14 @@ struct FastEngine : ConvEngine {
     const size_t iters = ceil_div(rows, CF::ROWS);
     const dim3 grid(unsigned(std::min<size_t>(iters, size_t(num_sms) * rows_ctas_per_sm)));
     const size_t smem = size_t(CF::GROUPS) * CF::RPG * CF::RS * sizeof(cplx);
-    auto kfn = fast::k_rows_inv2<MM>;
-    LMVN_LAUNCH(kfn, grid, dim3(fast::kRowThreads), smem, s, a);
+    auto k0 = fast::k_rows_inv2<MM, gen::EPI_STORE>;
+    auto k1 = fast::k_rows_inv2<MM, gen::EPI_QUOTIENT>;
+    auto k2 = fast::k_rows_inv2<MM, gen::EPI_UPDATE>;
+    switch (a.ep.mode) {
+      case gen::EPI_QUOTIENT: LMVN_LAUNCH(k1, grid, dim3(fast::kRowThreads), smem, s, a); break;
+      case gen::EPI_UPDATE: LMVN_LAUNCH(k2, grid, dim3(fast::kRowThreads), smem, s, a); break;
+      default: LMVN_LAUNCH(k0, grid, dim3(fast::kRowThreads), smem, s, a); break;
+    }
     return 0;
   }
 
@@ -204,6 +220,7 @@ struct FastEngine : ConvEngine {
     a.spec = spec + size_t(z0) * plan->ny * nxp;
     a.nz = nzs; a.ny = plan->ny; a.nxp = nxp;
     a.tw_m = d_tw_m; a.tw_nx = d_tw_nx;
+    a.prefetch = rows_prefetch;
     const bool w = src.wrapped != 0;
     switch (M) {
       case 32: LMVN_TRY(launch_rows_fwd2<32>(a, w, s)); break;
@@ -230,6 +247,7 @@ struct FastEngine : ConvEngine {
     a.ep = ep;
     a.nz = nzs; a.ny = plan->ny; a.nxp = nxp;
     a.tw_m = d_tw_m; a.tw_nx = d_tw_nx;
+    a.prefetch = rows_prefetch;
     switch (M) {
       case 32: LMVN_TRY(launch_rows_inv2<32>(a, s)); break;
       case 64: LMVN_TRY(launch_rows_inv2<64>(a, s)); break;
@@ -274,6 +292,8 @@ struct FastEngine : ConvEngine {
     a.khat = khat;
     a.ncols = nxc;
     a.scale = scale;
+    a.prefetch = (axis == 1 && mode == fast::SM_FWD) ? y_fwd_prefetch : 0;
+    a.prefetch_khat = khat_prefetch;
     int n;
     unsigned slow;
     if (axis == 1) {

@@ -18,23 +18,32 @@ struct XY {
 #ifdef LMVN_EMU
     return 1;
 #else
-    int n_f = 0, n_i = 0;
-    auto kf = k_xy<M, NY, false, false>;
-    auto ki = k_xy<M, NY, true, false>;
-    if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem())) != cudaSuccess) return 0;
-    if (cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem())) != cudaSuccess) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n_f, kf, kRowThreads, smem()) != cudaSuccess) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n_i, ki, kRowThreads, smem()) != cudaSuccess) return 0;
-    return std::min(n_f, n_i);
+    int occ = 1 << 30;
+    void (*ks[4])(XYArgs) = {k_xy<M, NY, false, gen::EPI_STORE>, k_xy<M, NY, true, gen::EPI_STORE>,
+                             k_xy<M, NY, true, gen::EPI_QUOTIENT>, k_xy<M, NY, true, gen::EPI_UPDATE>};
+    for (auto k : ks) {
+      int n = 0;
+      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem())) != cudaSuccess) return 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, kRowThreads, smem()) != cudaSuccess) return 0;
+      occ = std::min(occ, n);
+    }
+    return occ;
 #endif
   }
   static int launch(bool inverse, const XYArgs& a, int grid, cudaStream_t s) {
-    auto kf = k_xy<M, NY, false, false>;
-    auto ki = k_xy<M, NY, true, false>;
-    if (inverse) {
-      LMVN_LAUNCH(ki, dim3(unsigned(grid)), dim3(kRowThreads), smem(), s, a);
+    auto kf = k_xy<M, NY, false, gen::EPI_STORE>;
+    auto k0 = k_xy<M, NY, true, gen::EPI_STORE>;
+    auto k1 = k_xy<M, NY, true, gen::EPI_QUOTIENT>;
+    auto k2 = k_xy<M, NY, true, gen::EPI_UPDATE>;
+    const dim3 g{unsigned(grid)}, b{unsigned(kRowThreads)};
+    if (!inverse) {
+      LMVN_LAUNCH(kf, g, b, smem(), s, a);
+    } else if (a.rows.ep.mode == gen::EPI_QUOTIENT) {
+      LMVN_LAUNCH(k1, g, b, smem(), s, a);
+    } else if (a.rows.ep.mode == gen::EPI_UPDATE) {
+      LMVN_LAUNCH(k2, g, b, smem(), s, a);
     } else {
-      LMVN_LAUNCH(kf, dim3(unsigned(grid)), dim3(kRowThreads), smem(), s, a);
+      LMVN_LAUNCH(k0, g, b, smem(), s, a);
     }
     return 0;
   }

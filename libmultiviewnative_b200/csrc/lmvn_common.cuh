@@ -73,6 +73,15 @@ __device__ __forceinline__ void st_stream(cplx* p, cplx v) {
 #endif
 }
 
+// L2 prefetch of the 128-byte line holding p (no register, no scoreboard entry)
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#ifndef LMVN_EMU
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
 // ---- error plumbing: nothing in this library exits or throws across the ABI ----
 void set_last_error(const char* fmt, ...);
 const char* last_error();
