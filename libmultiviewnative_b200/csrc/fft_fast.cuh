@@ -308,33 +308,43 @@ __device__ __forceinline__ void strided_stage(cplx* __restrict__ sm, cplx* __res
   }
 }
 
-// middle of the merged z pass: last forward stage (span R), spectrum product, first inverse stage
-template <int N, int R, int COLS, int UNROLL = 8>
-__device__ __forceinline__ void strided_middle(cplx* __restrict__ sm, const cplx* __restrict__ gk, int rs) {
-  constexpr int RG = kStridedThreads / COLS;
-  constexpr int PER_THREAD = (N / R) / RG;
-  const int rg = threadIdx.x / COLS;
-#pragma unroll(UNROLL)
-  for (int i = 0; i < PER_THREAD; ++i) {
-    const int row0 = (rg + i * RG) * R;
-    cplx v[R], k[R];
-    unsigned off = unsigned(row0 * rs);
+// middle of the merged z pass: last forward stage (span R), spectrum product, first inverse stage.
+// The K^ operands come straight from HBM; middle_load() is called BEFORE the barrier that precedes
+// the middle so that their latency overlaps the barrier wait and the shared-memory reads.
+template <int N, int R, int COLS>
+struct Middle {
+  static const int RG = kStridedThreads / COLS;
+  static const int PT = (N / R) / RG;  // butterflies per thread: 1 or 2 in every plan that is used
+  struct K { cplx k[PT][R]; };
+  static __device__ __forceinline__ void load(K& o, const cplx* __restrict__ gk, int rs) {
+    const int rg = threadIdx.x / COLS;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      k[r] = ld_stream(gk + off);
-      off += unsigned(rs);
+    for (int i = 0; i < PT; ++i) {
+      unsigned off = unsigned((rg + i * RG) * R * rs);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        o.k[i][r] = ld_stream(gk + off);
+        off += unsigned(rs);
+      }
     }
-    cplx* p = sm + row0 * COLS;
-#pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = p[r * COLS];
-    Bfly<R, false>::run(v);
-#pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = cmul(v[r], k[r]);
-    Bfly<R, true>::run(v);
-#pragma unroll
-    for (int r = 0; r < R; ++r) p[r * COLS] = v[r];
   }
-}
+  static __device__ __forceinline__ void run(cplx* __restrict__ sm, const K& o) {
+    const int rg = threadIdx.x / COLS;
+#pragma unroll
+    for (int i = 0; i < PT; ++i) {
+      cplx* p = sm + (rg + i * RG) * R * COLS;
+      cplx v[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = p[r * COLS];
+      Bfly<R, false>::run(v);
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = cmul(v[r], o.k[i][r]);
+      Bfly<R, true>::run(v);
+#pragma unroll
+      for (int r = 0; r < R; ++r) p[r * COLS] = v[r];
+    }
+  }
+};
 
 // One tile of a strided pass.  `sm`, `g`, `gk` already point at this thread's column; threads of
 // the padding columns of a ragged last tile pass live = false: they skip the stages (every stage
@@ -370,15 +380,22 @@ __device__ __forceinline__ void strided_tile(const StridedArgs& A, cplx* sm, cpl
     if (live) strided_stage<N, R1, N, COLS, true, W_SMEM, W_GLOBAL, U>(sm, g, rs, A.tw1, 1.f);
   } else {  // SM_FWD_MUL_INV
     if (live) strided_stage<N, R1, N, COLS, false, W_GLOBAL, W_SMEM, U>(sm, g, rs, A.tw1, 1.f);
-    __syncthreads();
     if (RX::S == 3) {
-      if (live) strided_stage<N, R2, L2, COLS, false, W_SMEM, W_SMEM, U>(sm, g, rs, A.tw2, 1.f);
+      typedef Middle<N, R3, COLS> MID;
+      typename MID::K kk;
       __syncthreads();
-      if (live) strided_middle<N, R3, COLS, U>(sm, gk, rs);
+      if (live) strided_stage<N, R2, L2, COLS, false, W_SMEM, W_SMEM, U>(sm, g, rs, A.tw2, 1.f);
+      if (live) MID::load(kk, gk, rs);
+      __syncthreads();
+      if (live) MID::run(sm, kk);
       __syncthreads();
       if (live) strided_stage<N, R2, L2, COLS, true, W_SMEM, W_SMEM, U>(sm, g, rs, A.tw2, 1.f);
     } else {
-      if (live) strided_middle<N, R2, COLS, U>(sm, gk, rs);
+      typedef Middle<N, R2, COLS> MID;
+      typename MID::K kk;
+      if (live) MID::load(kk, gk, rs);
+      __syncthreads();
+      if (live) MID::run(sm, kk);
     }
     __syncthreads();
     if (live) strided_stage<N, R1, N, COLS, true, W_SMEM, W_GLOBAL, U>(sm, g, rs, A.tw1, 1.f);
