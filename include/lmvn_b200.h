@@ -81,6 +81,59 @@ LMVN_EXPORT int lmvn_plan_profile(lmvn_plan* plan, double lambda, float min_valu
 /* blocks until everything queued on the plan's stream is done */
 LMVN_EXPORT int lmvn_plan_synchronize(lmvn_plan* plan);
 
+/* ---------------------------------------------------------------------------------------------
+ * ONE volume over several GPUs (BASELINE config 5; the reference has no such path): slabs of
+ * nz/G planes in real space, pencils of ny/G rows for the z pass, both all-to-all exchanges of a
+ * convolution fused into the transform kernels as stores into peer memory over NVLink.
+ * Power-of-two fast-path shapes only (nx in {64,128,256}; ny, nz in {16..512}); G a power of two <= 8.
+ *
+ * One handle per rank.  Ranks are separate processes (one per GPU: exchange the 64-byte handles of
+ * lmvn_dist_export_handle with any transport and pass them to lmvn_dist_connect_ipc, then use
+ * lmvn_dist_iterate) or several handles of one process (lmvn_dist_connect_local; the caller issues
+ * lmvn_dist_*_phase for every rank and synchronises between phases).
+ * Every rank must make the same sequence of calls.  Slab buffers are host pointers to the rank's
+ * nz/G planes ([nz/G][ny][nx] floats). */
+typedef struct lmvn_dist lmvn_dist;
+
+typedef struct lmvn_dist_info {
+  int dims[3];
+  int num_views;
+  int rank, world, device;
+  int planes_per_rank;                 /* nz / G */
+  int rows_per_rank;                   /* ny / G */
+  int spectrum_pitch;                  /* complex elements per spectrum row */
+  unsigned long long arena_bytes;      /* device memory held by this rank */
+  unsigned long long exchange_bytes;   /* size of the peer-visible region */
+  unsigned long long alg_bytes_per_view_iteration;      /* 7S + 10C of the WHOLE volume */
+  unsigned long long exchange_bytes_per_view_iteration; /* 4 C (G-1)/G, all ranks together */
+} lmvn_dist_info;
+
+LMVN_EXPORT int lmvn_dist_create(lmvn_dist** out, const int* dims_zyx, int num_views, int rank, int world,
+                                 int device);
+LMVN_EXPORT void lmvn_dist_destroy(lmvn_dist* plan);
+LMVN_EXPORT int lmvn_dist_get_info(const lmvn_dist* plan, lmvn_dist_info* info);
+LMVN_EXPORT int lmvn_dist_export_handle(lmvn_dist* plan, void* handle64);
+LMVN_EXPORT int lmvn_dist_connect_ipc(lmvn_dist* plan, int peer_rank, const void* handle64);
+LMVN_EXPORT int lmvn_dist_connect_local(lmvn_dist* plan, int peer_rank, lmvn_dist* peer);
+LMVN_EXPORT int lmvn_dist_set_view_slab(lmvn_dist* plan, int view, const float* image_slab,
+                                        const float* weights_slab);
+LMVN_EXPORT int lmvn_dist_set_psi_slab(lmvn_dist* plan, const float* psi_slab);
+LMVN_EXPORT int lmvn_dist_get_psi_slab(lmvn_dist* plan, float* psi_slab);
+/* PSF spectrum of kernel 1 / 2 of a view, straight into the pencil layout.  phase 0: wrap-around +
+ * x,y forward + scatter (needs the whole kernel, host pointer); [barrier]; phase 1: z forward, 1/N. */
+LMVN_EXPORT int lmvn_dist_psf_phase(lmvn_dist* plan, int view, int which_kernel, int phase,
+                                    const float* kernel, const int* kernel_dims);
+/* One phase of convolution 1 (psi (*) kernel1 -> quotient) or 2 (integral (*) kernel2 -> update):
+ * 0: x,y forward + scatter; [barrier]; 1: z forward * K^ * z inverse + scatter; [barrier]; 2: y,x inverse + pointwise. */
+LMVN_EXPORT int lmvn_dist_conv_phase(lmvn_dist* plan, int view, int which_conv, int phase, double lambda,
+                                     float min_value);
+/* device-side cross-GPU barrier on the plan's stream (no-op for in-process groups) */
+LMVN_EXPORT int lmvn_dist_barrier(lmvn_dist* plan);
+/* the whole loop, barriers on the device, no host round trip (one process per rank) */
+LMVN_EXPORT int lmvn_dist_iterate(lmvn_dist* plan, int iterations, double lambda, float min_value,
+                                  float* device_ms);
+LMVN_EXPORT int lmvn_dist_synchronize(lmvn_dist* plan);
+
 /* r2c / c2r of a host volume through the generic passes, natural layout:
  * spectrum = nz*ny*(nx/2+1) interleaved (re,im) pairs.  c2r is unnormalised. */
 LMVN_EXPORT int lmvn_debug_rfftn(const float* in, const int* dims_zyx, float* spectrum, int device);

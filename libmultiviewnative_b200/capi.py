@@ -47,6 +47,16 @@ class PlanInfo(C.Structure):
     ]
 
 
+class DistInfo(C.Structure):
+    """struct lmvn_dist_info (include/lmvn_b200.h)."""
+    _fields_ = [
+        ("dims", C.c_int * 3), ("num_views", C.c_int), ("rank", C.c_int), ("world", C.c_int), ("device", C.c_int),
+        ("planes_per_rank", C.c_int), ("rows_per_rank", C.c_int), ("spectrum_pitch", C.c_int),
+        ("arena_bytes", C.c_ulonglong), ("exchange_bytes", C.c_ulonglong),
+        ("alg_bytes_per_view_iteration", C.c_ulonglong), ("exchange_bytes_per_view_iteration", C.c_ulonglong),
+    ]
+
+
 assert C.sizeof(ViewData) == 64 and C.sizeof(Workspace) == 32
 
 # every symbol include/multiviewnative.h and include/lmvn_b200.h declare
@@ -61,6 +71,9 @@ EXTENSION_SYMBOLS = [
     "lmvn_last_error", "lmvn_clear_error", "lmvn_version", "lmvn_set_default_strategy", "lmvn_plan_create",
     "lmvn_plan_destroy", "lmvn_plan_get_info", "lmvn_plan_set_view", "lmvn_plan_set_psi", "lmvn_plan_get_psi",
     "lmvn_plan_iterate", "lmvn_plan_convolve", "lmvn_plan_profile", "lmvn_plan_synchronize", "lmvn_debug_rfftn", "lmvn_debug_irfftn",
+    "lmvn_dist_create", "lmvn_dist_destroy", "lmvn_dist_get_info", "lmvn_dist_export_handle", "lmvn_dist_connect_ipc",
+    "lmvn_dist_connect_local", "lmvn_dist_set_view_slab", "lmvn_dist_set_psi_slab", "lmvn_dist_get_psi_slab",
+    "lmvn_dist_psf_phase", "lmvn_dist_conv_phase", "lmvn_dist_barrier", "lmvn_dist_iterate", "lmvn_dist_synchronize",
 ]
 
 STRATEGY_AUTO, STRATEGY_GENERIC, STRATEGY_FUSED = 0, 1, 2
@@ -133,6 +146,21 @@ class Library:
         L.lmvn_plan_synchronize.argtypes = [C.c_void_p]
         L.lmvn_plan_profile.argtypes = [C.c_void_p, C.c_double, C.c_float, C.c_int, C.c_char_p, c_float_p,
                                         C.POINTER(C.c_ulonglong), c_int_p]
+        L.lmvn_dist_create.argtypes = [C.POINTER(C.c_void_p), c_int_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.lmvn_dist_destroy.argtypes = [C.c_void_p]
+        L.lmvn_dist_destroy.restype = None
+        L.lmvn_dist_get_info.argtypes = [C.c_void_p, C.POINTER(DistInfo)]
+        L.lmvn_dist_export_handle.argtypes = [C.c_void_p, C.c_char_p]
+        L.lmvn_dist_connect_ipc.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+        L.lmvn_dist_connect_local.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.lmvn_dist_set_view_slab.argtypes = [C.c_void_p, C.c_int, c_float_p, c_float_p]
+        L.lmvn_dist_set_psi_slab.argtypes = [C.c_void_p, c_float_p]
+        L.lmvn_dist_get_psi_slab.argtypes = [C.c_void_p, c_float_p]
+        L.lmvn_dist_psf_phase.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p, c_int_p]
+        L.lmvn_dist_conv_phase.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_float]
+        L.lmvn_dist_barrier.argtypes = [C.c_void_p]
+        L.lmvn_dist_iterate.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_float, c_float_p]
+        L.lmvn_dist_synchronize.argtypes = [C.c_void_p]
         L.lmvn_debug_rfftn.argtypes = [c_float_p, c_int_p, c_float_p, C.c_int]
         L.lmvn_debug_irfftn.argtypes = [c_float_p, c_int_p, c_float_p, C.c_int]
 

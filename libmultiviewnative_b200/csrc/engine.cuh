@@ -68,6 +68,32 @@ struct ConvEngine {
                        float* out, cudaStream_t s) = 0;
 };
 
+// What the slab-decomposed (multi-GPU) engine needs from the power-of-two fast path: the same
+// kernels with explicit geometry.  All pointers are device pointers; spectra use row pitch nxp().
+struct StridedGeom {
+  cplx* data = nullptr;        // transformed in place (except for scattered final stores)
+  const cplx* khat = nullptr;  // merged z pass only
+  int n = 0;                   // transform length (the axis whose twiddle tables are used: tw_axis)
+  int tw_axis = 1;             // 1: tables of the plan's ny, 0: tables of the plan's nz
+  int row_stride = 0;          // complex elements between consecutive rows of the transform axis
+  long long tile_stride = 0;   // between consecutive slow indices
+  unsigned slow = 1;           // number of slow indices (grid.y)
+  int mode = 0;                // fast::StridedMode
+  float scale = 1.f;
+  Scatter sc{};                // SM_*_SCATTER
+};
+struct FastOps {
+  virtual ~FastOps() {}
+  virtual int nxp_pitch() const = 0;
+  // x transform of nz_local planes: src -> spec.  Wrapped (PSF) sources take the global plane offset / count.
+  virtual int rows_fwd_planes(const gen::RealSource& src, cplx* spec, int nz_local, int z0_global, int nz_global,
+                              cudaStream_t s) = 0;
+  virtual int rows_inv_planes(const cplx* spec, float* out, const gen::Epilogue& ep, int nz_local, cudaStream_t s) = 0;
+  virtual int strided_geom(const StridedGeom& g, cudaStream_t s) = 0;
+};
+// nullptr (last error set) when the global shape is not eligible for the fast path
+std::unique_ptr<FastOps> make_fast_ops(std::shared_ptr<FftPlan> plan_global);
+
 std::unique_ptr<ConvEngine> make_generic_engine(std::shared_ptr<FftPlan> plan);
 // nullptr when the shape is not eligible (no error set)
 std::unique_ptr<ConvEngine> make_fused_engine(std::shared_ptr<FftPlan> plan);

@@ -193,7 +193,11 @@ struct Bfly<32, INV> {
 // ------------------------------------------------------------------------------
 // strided passes (y and z axes): tile = N rows x COLS adjacent kx columns.
 // ------------------------------------------------------------------------------
-enum StridedMode { SM_FWD = 0, SM_INV = 1, SM_FWD_MUL_INV = 2, SM_FWD_SCALE = 3 };
+enum StridedMode {
+  SM_FWD = 0, SM_INV = 1, SM_FWD_MUL_INV = 2, SM_FWD_SCALE = 3,
+  SM_FWD_SCATTER = 4,          // SM_FWD whose final stores go to the per-destination buffers of A.sc
+  SM_FWD_MUL_INV_SCATTER = 5   // SM_FWD_MUL_INV likewise
+};
 
 struct StridedArgs {
   cplx* data;             // spectrum, in place
@@ -206,6 +210,7 @@ struct StridedArgs {
   float scale;            // SM_FWD_SCALE
   int prefetch;           // > 0: every CTA first pulls the tile of block (id + prefetch) into L2
   int prefetch_khat;      // SM_FWD_MUL_INV: pull the CTA's own K^ tile into L2 at kernel entry
+  Scatter sc;             // SM_*_SCATTER
 };
 
 // number of stages and the radix of stage s for N = R1*R2*R3
@@ -240,10 +245,11 @@ static const int kStridedThreads = 256;
 
 // resident CTAs per SM the register budget is sized for
 template <int N, int MODE> struct StridedBlocks {
-  static const int V = (Radix<N>::R1 >= 32) ? 2 : ((MODE == SM_FWD_MUL_INV && N >= 64) ? LMVN_ZMUL_BLOCKS : 3);
+  static const int V = (Radix<N>::R1 >= 32) ? 2
+                       : (((MODE == SM_FWD_MUL_INV || MODE == SM_FWD_MUL_INV_SCATTER) && N >= 64) ? LMVN_ZMUL_BLOCKS : 3);
 };
 
-enum Where { W_SMEM = 0, W_GLOBAL = 1, W_GLOBAL_SCALED = 2 };
+enum Where { W_SMEM = 0, W_GLOBAL = 1, W_GLOBAL_SCALED = 2, W_SCATTER = 3 };
 
 // One radix-R stage of span L on the thread's column.  Forward (INV = false) is a
 // decimation-in-frequency stage (butterfly, then twiddle w_L^{jq}); inverse is the
@@ -251,7 +257,8 @@ enum Where { W_SMEM = 0, W_GLOBAL = 1, W_GLOBAL_SCALED = 2 };
 // already point at this thread's column; rows are addressed with 32-bit offsets.
 template <int N, int R, int L, int COLS, bool INV, int SRC, int DST, int UNROLL = 8>
 __device__ __forceinline__ void strided_stage(cplx* __restrict__ sm, cplx* __restrict__ g, int rs,
-                                              const cplx* __restrict__ tws, float scale) {
+                                              const cplx* __restrict__ tws, float scale,
+                                              const Scatter* sc = nullptr, long long sc_tile = 0) {
   constexpr int M = L / R;
   constexpr int RG = kStridedThreads / COLS;   // row groups per block
   constexpr int PER_THREAD = (N / R) / RG;
@@ -296,6 +303,13 @@ __device__ __forceinline__ void strided_stage(cplx* __restrict__ sm, cplx* __res
       cplx* p = sm + row0 * COLS;
 #pragma unroll
       for (int q = 0; q < R; ++q) p[q * M * COLS] = v[q];
+    } else if (DST == W_SCATTER) {
+      const int mask = (1 << sc->shift) - 1;
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const int row = row0 + q * M;
+        st_stream(sc->base[row >> sc->shift] + sc_tile + (long long)(row & mask) * sc->row_stride, v[q]);
+      }
     } else {
       unsigned off = unsigned(row0 * rs);
       const unsigned step = unsigned(M * rs);
@@ -349,14 +363,18 @@ struct Middle {
 // One tile of a strided pass.  `sm`, `g`, `gk` already point at this thread's column; threads of
 // the padding columns of a ragged last tile pass live = false: they skip the stages (every stage
 // touches the thread's own column only) but still take part in the barriers.
-template <int N, int MODE, int U>
-__device__ __forceinline__ void strided_tile(const StridedArgs& A, cplx* sm, cplx* g, const cplx* gk, bool live) {
+template <int N, int MODE_, int U>
+__device__ __forceinline__ void strided_tile(const StridedArgs& A, cplx* sm, cplx* g, const cplx* gk, bool live,
+                                             long long sc_tile = 0) {
   typedef Radix<N> RX;
   constexpr int COLS = Cols<N>::V;
   constexpr int R1 = RX::R1, R2 = RX::R2;
   constexpr int R3 = (RX::R3 > 1 ? RX::R3 : 2);  // placeholder radix for the dead 3-stage code of 2-stage sizes
   constexpr int L2 = N / R1, L3 = (RX::S == 3 ? N / (R1 * R2) : 2);
-  constexpr int DSTG = (MODE == SM_FWD_SCALE) ? W_GLOBAL_SCALED : W_GLOBAL;
+  constexpr bool SCAT = (MODE_ == SM_FWD_SCATTER || MODE_ == SM_FWD_MUL_INV_SCATTER);
+  constexpr int MODE = (MODE_ == SM_FWD_SCATTER) ? SM_FWD : (MODE_ == SM_FWD_MUL_INV_SCATTER ? SM_FWD_MUL_INV : MODE_);
+  constexpr int DSTG = SCAT ? W_SCATTER : ((MODE == SM_FWD_SCALE) ? W_GLOBAL_SCALED : W_GLOBAL);
+  const Scatter* sc = &A.sc;
   const int rs = A.row_stride;
   if (MODE == SM_FWD || MODE == SM_FWD_SCALE) {
     if (live) strided_stage<N, R1, N, COLS, false, W_GLOBAL, W_SMEM, U>(sm, g, rs, A.tw1, 1.f);
@@ -364,9 +382,9 @@ __device__ __forceinline__ void strided_tile(const StridedArgs& A, cplx* sm, cpl
     if (RX::S == 3) {
       if (live) strided_stage<N, R2, L2, COLS, false, W_SMEM, W_SMEM, U>(sm, g, rs, A.tw2, 1.f);
       __syncthreads();
-      if (live) strided_stage<N, R3, L3, COLS, false, W_SMEM, DSTG, U>(sm, g, rs, nullptr, A.scale);
+      if (live) strided_stage<N, R3, L3, COLS, false, W_SMEM, DSTG, U>(sm, g, rs, nullptr, A.scale, sc, sc_tile);
     } else {
-      if (live) strided_stage<N, R2, L2, COLS, false, W_SMEM, DSTG, U>(sm, g, rs, A.tw2, A.scale);
+      if (live) strided_stage<N, R2, L2, COLS, false, W_SMEM, DSTG, U>(sm, g, rs, A.tw2, A.scale, sc, sc_tile);
     }
   } else if (MODE == SM_INV) {
     if (RX::S == 3) {
@@ -398,7 +416,7 @@ __device__ __forceinline__ void strided_tile(const StridedArgs& A, cplx* sm, cpl
       if (live) MID::run(sm, kk);
     }
     __syncthreads();
-    if (live) strided_stage<N, R1, N, COLS, true, W_SMEM, W_GLOBAL, U>(sm, g, rs, A.tw1, 1.f);
+    if (live) strided_stage<N, R1, N, COLS, true, W_SMEM, DSTG, U>(sm, g, rs, A.tw1, 1.f, sc, sc_tile);
   }
 }
 
@@ -410,8 +428,9 @@ static __global__ void __launch_bounds__(kStridedThreads, StridedBlocks<N, MODE>
   const int c = threadIdx.x % COLS;
   const int col = blockIdx.x * COLS + c;
   const long long base = (long long)blockIdx.y * A.tile_stride + col;
-  constexpr int U = (MODE == SM_FWD_MUL_INV) ? LMVN_ZMUL_UNROLL : LMVN_Y_UNROLL;
-  if (MODE == SM_FWD_MUL_INV && A.prefetch_khat) {
+  constexpr bool ZMUL = (MODE == SM_FWD_MUL_INV || MODE == SM_FWD_MUL_INV_SCATTER);
+  constexpr int U = ZMUL ? LMVN_ZMUL_UNROLL : LMVN_Y_UNROLL;
+  if (ZMUL && A.prefetch_khat) {
     // K^ is first needed two stages from now: start its trip from HBM to L2 right away
     constexpr int LINES = COLS / 16;
     const long long tb = (long long)blockIdx.y * A.tile_stride + blockIdx.x * COLS;
@@ -430,7 +449,8 @@ static __global__ void __launch_bounds__(kStridedThreads, StridedBlocks<N, MODE>
       }
     }
   }
-  strided_tile<N, MODE, U>(A, smem + c, A.data + base, A.khat + base, col < A.ncols);
+  const long long sc_tile = A.sc.offset + (long long)blockIdx.y * A.sc.tile_stride + col;
+  strided_tile<N, MODE, U>(A, smem + c, A.data + base, A.khat + base, col < A.ncols, sc_tile);
 }
 
 // ------------------------------------------------------------------------------
@@ -458,6 +478,7 @@ struct RowArgs {
   const cplx* tw_m;      // w_M table (M entries)
   const cplx* tw_nx;     // w_nx^k, k = 0..M
   int prefetch;          // pull the next loop iteration's rows into L2 one iteration ahead
+  int z0, nz_wrap;       // wrapped source on a slab of planes: global index of plane 0, global nz
 };
 
 // real-transform split for one (k, M-k) pair:  X[k] = E + w^k O,  X[M-k] = conj(E - w^k O)
@@ -538,8 +559,8 @@ __device__ __forceinline__ void rows_fwd_group(const RowArgs& A, cplx* slab, lon
 #pragma unroll
       for (int r = 0; r < R1; ++r) v[a * R1 + r] = ld_stream(in + lane + 16 * r);
     } else {
-      const int z = int(row / A.ny), y = int(row % A.ny);
-      const int sz = gen::wrap_src_index(z, A.nz, A.src.kz);
+      const int z = int(row / A.ny) + A.z0, y = int(row % A.ny);
+      const int sz = gen::wrap_src_index(z, A.nz_wrap, A.src.kz);
       const int sy = gen::wrap_src_index(y, A.ny, A.src.ky);
 #pragma unroll
       for (int r = 0; r < R1; ++r) {

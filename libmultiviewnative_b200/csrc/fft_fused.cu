@@ -23,7 +23,7 @@ namespace {
 
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
-struct FastEngine : ConvEngine {
+struct FastEngine : ConvEngine, FastOps {
   int M = 0, nxc = 0, nxp = 0;
   int num_sms = 148;
   int rows_ctas_per_sm = 8;
@@ -210,7 +210,8 @@ struct FastEngine : ConvEngine {
   }
 
   // z0/nzs select a slab of planes (whole volume by default); wrapped sources are whole-volume only
-  int rows_fwd(const gen::RealSource& src_in, cplx* spec, cudaStream_t s, int z0 = 0, int nzs = -1) {
+  int rows_fwd(const gen::RealSource& src_in, cplx* spec, cudaStream_t s, int z0 = 0, int nzs = -1, int wrap_z0 = 0,
+               int wrap_nz = 0) {
     if (nzs < 0) nzs = plan->nz;
     fast::RowArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -221,6 +222,7 @@ struct FastEngine : ConvEngine {
     a.nz = nzs; a.ny = plan->ny; a.nxp = nxp;
     a.tw_m = d_tw_m; a.tw_nx = d_tw_nx;
     a.prefetch = rows_prefetch;
+    a.z0 = wrap_z0; a.nz_wrap = wrap_nz > 0 ? wrap_nz : plan->nz;
     const bool w = src.wrapped != 0;
     switch (M) {
       case 32: LMVN_TRY(launch_rows_fwd2<32>(a, w, s)); break;
@@ -278,6 +280,8 @@ struct FastEngine : ConvEngine {
       case fast::SM_FWD: return launch_strided<N, fast::SM_FWD>(a, grid, s);
       case fast::SM_INV: return launch_strided<N, fast::SM_INV>(a, grid, s);
       case fast::SM_FWD_MUL_INV: return launch_strided<N, fast::SM_FWD_MUL_INV>(a, grid, s);
+      case fast::SM_FWD_SCATTER: return launch_strided<N, fast::SM_FWD_SCATTER>(a, grid, s);
+      case fast::SM_FWD_MUL_INV_SCATTER: return launch_strided<N, fast::SM_FWD_MUL_INV_SCATTER>(a, grid, s);
       default: return launch_strided<N, fast::SM_FWD_SCALE>(a, grid, s);
     }
   }
@@ -286,44 +290,74 @@ struct FastEngine : ConvEngine {
   int strided(cplx* data, const cplx* khat, int axis, int mode, float scale, cudaStream_t s, int z0 = 0,
               int nzs = -1) {
     const FftPlan& p = *plan;
-    fast::StridedArgs a;
+    StridedGeom g;
     if (axis == 1 && nzs >= 0) data += size_t(z0) * p.ny * nxp;  // y pass on a slab of planes
-    a.data = data;
-    a.khat = khat;
-    a.ncols = nxc;
-    a.scale = scale;
-    a.prefetch = (axis == 1 && mode == fast::SM_FWD) ? y_fwd_prefetch : 0;
-    a.prefetch_khat = khat_prefetch;
-    int n;
-    unsigned slow;
+    g.data = data;
+    g.khat = khat;
+    g.mode = mode;
+    g.scale = scale;
+    g.tw_axis = axis;
     if (axis == 1) {
-      n = p.ny; a.row_stride = nxp; a.tile_stride = (long long)p.ny * nxp; slow = unsigned(nzs >= 0 ? nzs : p.nz);
-      a.tw1 = d_tw_y[0]; a.tw2 = d_tw_y[1];
+      g.n = p.ny; g.row_stride = nxp; g.tile_stride = (long long)p.ny * nxp; g.slow = unsigned(nzs >= 0 ? nzs : p.nz);
     } else {
-      n = p.nz; a.row_stride = p.ny * nxp; a.tile_stride = nxp; slow = unsigned(p.ny);
-      a.tw1 = d_tw_z[0]; a.tw2 = d_tw_z[1];
+      g.n = p.nz; g.row_stride = p.ny * nxp; g.tile_stride = nxp; g.slow = unsigned(p.ny);
     }
+    return strided_geom(g, s);
+  }
+
+  int strided_geom(const StridedGeom& g, cudaStream_t s) override {
+    fast::StridedArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.data = g.data;
+    a.khat = g.khat;
+    a.ncols = nxc;
+    a.scale = g.scale;
+    a.row_stride = g.row_stride;
+    a.tile_stride = g.tile_stride;
+    a.sc = g.sc;
+    const int mode = g.mode;
+    a.prefetch = (g.tw_axis == 1 && mode == fast::SM_FWD) ? y_fwd_prefetch : 0;
+    a.prefetch_khat = khat_prefetch;
+    if (g.tw_axis == 1) { a.tw1 = d_tw_y[0]; a.tw2 = d_tw_y[1]; }
+    else { a.tw1 = d_tw_z[0]; a.tw2 = d_tw_z[1]; }
+    if (g.n != (g.tw_axis == 1 ? plan->ny : plan->nz)) {
+      set_last_error("strided pass: length %d does not match the plan's axis", g.n);
+      return -1;
+    }
+    const unsigned slow = g.slow;
     int rc;
 #define LMVN_STRIDED_CASE(NN)                                                                   \
   case NN: {                                                                                    \
     const dim3 grid(unsigned(ceil_div(size_t(nxc), size_t(fast::Cols<NN>::V))), slow);          \
     rc = launch_strided_mode<NN>(a, mode, grid, s);                                             \
   } break;
-    switch (n) {
+    switch (g.n) {
       LMVN_STRIDED_CASE(16)
       LMVN_STRIDED_CASE(32)
       LMVN_STRIDED_CASE(64)
       LMVN_STRIDED_CASE(128)
       LMVN_STRIDED_CASE(256)
       LMVN_STRIDED_CASE(512)
-      default: set_last_error("fused path: unsupported axis length %d", n); return -1;
+      default: set_last_error("fused path: unsupported axis length %d", g.n); return -1;
     }
 #undef LMVN_STRIDED_CASE
     if (rc != 0) return rc;
     LMVN_CUDA_TRY(cudaGetLastError());
-    if (mode == fast::SM_FWD_MUL_INV) mark("fast_z_mul", 3 * C(), s);
-    else mark(axis == 1 ? (mode == fast::SM_INV ? "fast_y_inv" : "fast_y_fwd") : "fast_z", 2 * C(), s);
+    const bool zmul = (mode == fast::SM_FWD_MUL_INV || mode == fast::SM_FWD_MUL_INV_SCATTER);
+    if (zmul) mark("fast_z_mul", 3 * C(), s);
+    else mark(g.tw_axis == 1 ? (mode == fast::SM_INV ? "fast_y_inv" : "fast_y_fwd") : "fast_z", 2 * C(), s);
     return 0;
+  }
+
+  // ---- FastOps (slab-decomposed engine) ----
+  int nxp_pitch() const override { return nxp; }
+  int rows_fwd_planes(const gen::RealSource& src, cplx* spec, int nz_local, int z0_global, int nz_global,
+                      cudaStream_t s) override {
+    // spec / src.data already point at the first local plane
+    return rows_fwd(src, spec, s, 0, nz_local, z0_global, nz_global);
+  }
+  int rows_inv_planes(const cplx* spec, float* out, const gen::Epilogue& ep, int nz_local, cudaStream_t s) override {
+    return rows_inv(spec, out, ep, s, 0, nz_local);
   }
 
   int kernel_spectrum(const float* d_kernel, const int kd[3], cplx* khat, cplx*, cudaStream_t s) override {
@@ -368,6 +402,20 @@ struct FastEngine : ConvEngine {
 bool axis_ok(int n) { return n == 16 || n == 32 || n == 64 || n == 128 || n == 256 || n == 512; }
 
 }  // namespace
+
+std::unique_ptr<FastOps> make_fast_ops(std::shared_ptr<FftPlan> plan) {
+  const int nx = plan->nx;
+  if (!(nx == 64 || nx == 128 || nx == 256) || !axis_ok(plan->ny) || !axis_ok(plan->nz)) {
+    set_last_error("slab-decomposed engine: dims %dx%dx%d are not supported by the power-of-two fast path",
+                   plan->nz, plan->ny, plan->nx);
+    return nullptr;
+  }
+  std::unique_ptr<FastEngine> e(new FastEngine());
+  e->plan = plan;
+  if (cudaSetDevice(plan->device) != cudaSuccess) return nullptr;
+  if (e->init() != 0) return nullptr;
+  return std::unique_ptr<FastOps>(e.release());
+}
 
 std::unique_ptr<ConvEngine> make_fused_engine(std::shared_ptr<FftPlan> plan) {
   const int nx = plan->nx;

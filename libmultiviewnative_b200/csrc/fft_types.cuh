@@ -28,6 +28,15 @@ static inline UpdateParams make_update_params(double lambda, float min_value) {
   return p;
 }
 
+// Destination of a scattered final store (slab-decomposed transform over several GPUs): output
+// row r of the transform axis goes to device r >> shift, whose buffer may be peer memory reached
+// over NVLink.  address = base[r >> shift] + offset + (r & mask) * row_stride + slow * tile_stride + col.
+struct Scatter {
+  float2* base[8];
+  int shift;
+  long long row_stride, tile_stride, offset;
+};
+
 namespace gen {
 
 struct AxisPlan {

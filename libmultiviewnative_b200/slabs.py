@@ -1,0 +1,203 @@
+"""One volume over several GPUs: host side of the slab-decomposed plans
+(include/lmvn_b200.h, lmvn_dist_*; csrc/dist.cu).
+
+Real space is cut into slabs of nz/G planes, the z pass works on pencils of ny/G
+rows, and both all-to-all exchanges of a convolution are stores into peer memory
+issued by the transform kernels themselves.  Two ways to form the group:
+
+* ``LocalSlabGroup``  -- every rank is a handle of THIS process (all on one GPU for
+  tests, or one GPU each when a single process drives the box, like Fiji's Java
+  threads drive the reference).  Phases are issued rank by rank and the host
+  synchronises between phases.
+* ``ProcessSlabPlan`` -- one process per GPU (``torchrun``): the 64-byte CUDA IPC
+  handles of the exchange regions travel through ``torch.distributed``; afterwards
+  the whole loop runs on the device with flag barriers in peer memory and no host
+  round trip.  An NCCL ``all_to_all_single`` variant of the same exchange is kept
+  as the comparator (``iterate_nccl``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .capi import DistInfo, Library, _dims, _f32, _fp, c_int_p
+
+
+def slab_of(volume: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """The rank's planes of a {z, y, x} stack (a view when the stack is contiguous)."""
+    nz = volume.shape[0]
+    if nz % world:
+        raise ValueError("nz must be divisible by the world size")
+    n = nz // world
+    return np.ascontiguousarray(volume[rank * n:(rank + 1) * n])
+
+
+class SlabPlan:
+    """One rank's handle."""
+
+    def __init__(self, library: Library, dims, num_views: int, rank: int, world: int, device: int = -1):
+        self.L = library
+        self.dims = tuple(int(d) for d in dims)
+        self.rank, self.world, self.num_views = int(rank), int(world), int(num_views)
+        self.handle = C.c_void_p()
+        library._check(library.lib.lmvn_dist_create(C.byref(self.handle), C.cast(_dims(self.dims), c_int_p),
+                                                    int(num_views), int(rank), int(world), int(device)),
+                       "lmvn_dist_create")
+        self.slab_shape = (self.dims[0] // self.world, self.dims[1], self.dims[2])
+
+    def close(self):
+        if self.handle:
+            self.L.lib.lmvn_dist_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> DistInfo:
+        info = DistInfo()
+        self.L._check(self.L.lib.lmvn_dist_get_info(self.handle, C.byref(info)), "lmvn_dist_get_info")
+        return info
+
+    def export_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self.L._check(self.L.lib.lmvn_dist_export_handle(self.handle, buf), "lmvn_dist_export_handle")
+        return buf.raw
+
+    def connect_ipc(self, peer: int, handle: bytes):
+        self.L._check(self.L.lib.lmvn_dist_connect_ipc(self.handle, int(peer), handle), "lmvn_dist_connect_ipc")
+
+    def connect_local(self, peer: "SlabPlan"):
+        self.L._check(self.L.lib.lmvn_dist_connect_local(self.handle, peer.rank, peer.handle), "lmvn_dist_connect_local")
+
+    def _slab(self, a, name):
+        a = _f32(a, name)
+        if a.shape != self.slab_shape:
+            raise ValueError(f"{name}: expected the rank's slab {self.slab_shape}, got {a.shape}")
+        return a
+
+    def set_view_slab(self, v: int, image_slab, weights_slab):
+        image_slab, weights_slab = self._slab(image_slab, "image"), self._slab(weights_slab, "weights")
+        self.L._check(self.L.lib.lmvn_dist_set_view_slab(self.handle, int(v), _fp(image_slab), _fp(weights_slab)),
+                      "lmvn_dist_set_view_slab")
+
+    def set_psi_slab(self, psi_slab):
+        self.L._check(self.L.lib.lmvn_dist_set_psi_slab(self.handle, _fp(self._slab(psi_slab, "psi"))),
+                      "lmvn_dist_set_psi_slab")
+
+    def get_psi_slab(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.slab_shape, dtype=np.float32)
+        self.L._check(self.L.lib.lmvn_dist_get_psi_slab(self.handle, _fp(self._slab(out, "psi"))),
+                      "lmvn_dist_get_psi_slab")
+        return out
+
+    def psf_phase(self, v: int, which: int, phase: int, kernel=None):
+        if kernel is not None:
+            kernel = _f32(kernel, "kernel")
+            rc = self.L.lib.lmvn_dist_psf_phase(self.handle, int(v), int(which), int(phase), _fp(kernel),
+                                                C.cast(_dims(kernel.shape), c_int_p))
+        else:
+            rc = self.L.lib.lmvn_dist_psf_phase(self.handle, int(v), int(which), int(phase), None, None)
+        self.L._check(rc, "lmvn_dist_psf_phase")
+
+    def conv_phase(self, v: int, which: int, phase: int, lam: float, min_value: float):
+        self.L._check(self.L.lib.lmvn_dist_conv_phase(self.handle, int(v), int(which), int(phase), float(lam),
+                                                      float(min_value)), "lmvn_dist_conv_phase")
+
+    def barrier(self):
+        self.L._check(self.L.lib.lmvn_dist_barrier(self.handle), "lmvn_dist_barrier")
+
+    def iterate(self, iterations: int, lam: float = 0.0, min_value: float = 1e-4) -> float:
+        ms = C.c_float(0.0)
+        self.L._check(self.L.lib.lmvn_dist_iterate(self.handle, int(iterations), float(lam), float(min_value),
+                                                   C.byref(ms)), "lmvn_dist_iterate")
+        return float(ms.value)
+
+    def synchronize(self):
+        self.L._check(self.L.lib.lmvn_dist_synchronize(self.handle), "lmvn_dist_synchronize")
+
+
+class LocalSlabGroup:
+    """All ranks in this process.  ``devices[r]`` is rank r's GPU (default: all on one device)."""
+
+    def __init__(self, library: Library, dims, num_views: int, world: int, devices: Optional[Sequence[int]] = None):
+        self.dims = tuple(int(d) for d in dims)
+        self.world, self.num_views = int(world), int(num_views)
+        devices = list(devices) if devices is not None else [0] * self.world
+        self.ranks: List[SlabPlan] = [SlabPlan(library, dims, num_views, r, world, devices[r]) for r in range(world)]
+        for a in self.ranks:
+            for b in self.ranks:
+                if a is not b:
+                    a.connect_local(b)
+
+    def close(self):
+        for r in self.ranks:
+            r.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _sync(self):
+        for r in self.ranks:
+            r.synchronize()
+
+    def set_view(self, v: int, image, weights, kernel1, kernel2):
+        for r in self.ranks:
+            r.set_view_slab(v, slab_of(image, r.rank, self.world), slab_of(weights, r.rank, self.world))
+        for which, k in ((1, kernel1), (2, kernel2)):
+            k = np.ascontiguousarray(k, dtype=np.float32)
+            for r in self.ranks:
+                r.psf_phase(v, which, 0, k)
+            self._sync()
+            for r in self.ranks:
+                r.psf_phase(v, which, 1)
+            self._sync()
+
+    def set_psi(self, psi):
+        for r in self.ranks:
+            r.set_psi_slab(slab_of(psi, r.rank, self.world))
+
+    def get_psi(self) -> np.ndarray:
+        return np.concatenate([r.get_psi_slab() for r in self.ranks], axis=0)
+
+    def iterate(self, iterations: int, lam: float = 0.0, min_value: float = 1e-4):
+        for _ in range(int(iterations)):
+            for v in range(self.num_views):
+                for which in (1, 2):
+                    for phase in (0, 1, 2):
+                        for r in self.ranks:
+                            r.conv_phase(v, which, phase, lam, min_value)
+                        self._sync()
+
+
+class ProcessSlabPlan(SlabPlan):
+    """One process per GPU.  ``dist`` is an initialised ``torch.distributed`` (any backend that can
+    all_gather_object; the data path itself never goes through it)."""
+
+    def __init__(self, library: Library, dims, num_views: int, dist, device: int):
+        super().__init__(library, dims, num_views, dist.get_rank(), dist.get_world_size(), device)
+        self.dist = dist
+        handles: List[Optional[bytes]] = [None] * self.world
+        dist.all_gather_object(handles, self.export_handle())
+        for peer, h in enumerate(handles):
+            if peer != self.rank:
+                self.connect_ipc(peer, h)
+        dist.barrier()
+
+    def set_view(self, v: int, image_slab, weights_slab, kernel1, kernel2):
+        """Collective: every rank passes its slab of the view and the whole (small) kernels."""
+        self.set_view_slab(v, image_slab, weights_slab)
+        for which, k in ((1, kernel1), (2, kernel2)):
+            self.barrier()  # the previous reader of the exchange buffers is done everywhere
+            self.psf_phase(v, which, 0, np.ascontiguousarray(k, dtype=np.float32))
+            self.barrier()
+            self.psf_phase(v, which, 1)
+        self.synchronize()

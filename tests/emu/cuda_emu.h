@@ -198,6 +198,9 @@ static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent
 static inline cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = *t = size_t(8) << 30; return 0; }
 template <typename F>
 static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
+enum { cudaErrorPeerAccessAlreadyEnabled = 704 };
+static inline cudaError_t cudaIpcCloseMemHandle(void*) { return 0; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return 0; }
 
 namespace emu {
 // arguments are evaluated by the caller and captured BY VALUE, like a real launch

@@ -195,3 +195,42 @@ def test_xy_kernel_conv_vs_oracle(LXY, dims, kdims):
 
 def test_xy_kernel_deconvolve_config1(LXY):
     pc.case_deconvolve_vs_oracle(LXY, (128, 128, 128), 3, 31, 0.006, iters_list=(1, 10), n_sources=200)
+
+
+# ---- one volume over several ranks (slab-decomposed plans), all ranks on this GPU ------------
+@pytest.mark.parametrize("dims,world", [((64, 64, 64), 2), ((128, 128, 128), 4), ((256, 256, 256), 8)])
+def test_slab_group_equals_single_plan(L, dims, world):
+    """parity of the multi-GPU code path against the single-GPU path (256^3 case
+    included).  Same butterflies on the same data => bit-identical."""
+    from libmultiviewnative_b200.slabs import LocalSlabGroup
+    from libmultiviewnative_b200.synthetic import make_views
+
+    nv, iters, lam = 2, 2, 0.006
+    d = make_views(dims, num_views=nv, kernel_size=15, n_sources=50, workers=4)
+    with LocalSlabGroup(L, dims, nv, world) as g:
+        for v in range(nv):
+            g.set_view(v, d["views"][v], d["weights"][v], d["kernels1"][v], d["kernels2"][v])
+        g.set_psi(d["psi0"])
+        g.iterate(iters, lam, 1e-4)
+        got = g.get_psi()
+    single = d["psi0"].copy()
+    L.inplace_gpu_deconvolve(single, d["views"], d["kernels1"], d["kernels2"], d["weights"], iters, lam, 1e-4)
+    np.testing.assert_array_equal(got, single)
+
+
+def test_slab_group_vs_oracle(L):
+    from libmultiviewnative_b200.slabs import LocalSlabGroup
+    from libmultiviewnative_b200.synthetic import make_views
+    from oracle import mvn_oracle as orc
+
+    dims, nv, lam = (128, 128, 128), 3, 0.006
+    d = make_views(dims, num_views=nv, kernel_size=31, n_sources=200, workers=4)
+    with LocalSlabGroup(L, dims, nv, 4) as g:
+        for v in range(nv):
+            g.set_view(v, d["views"][v], d["weights"][v], d["kernels1"][v], d["kernels2"][v])
+        g.set_psi(d["psi0"])
+        g.iterate(1, lam, 1e-4)
+        got = g.get_psi()
+    exp = orc.inplace_cpu_deconvolve(d["psi0"], d["views"], d["kernels1"], d["kernels2"], d["weights"], 1, lam, 1e-4,
+                                     nthreads=4)
+    assert pc.max_rel(got, exp) < pc.PER_VOXEL_TOL_1_ITER
