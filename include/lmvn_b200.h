@@ -52,6 +52,10 @@ LMVN_EXPORT const char* lmvn_version(void);
 /* process-wide default used by plans created afterwards (also env LMVN_STRATEGY=generic|fused) */
 LMVN_EXPORT int lmvn_set_default_strategy(int strategy);
 
+/* A destroyed plan (and every one-shot inplace_gpu_* call) parks its device arena for the next plan on
+ * that device instead of returning it to the driver (env LMVN_CACHE_ARENA=0 disables).  This frees it. */
+LMVN_EXPORT void lmvn_release_cached_memory(void);
+
 LMVN_EXPORT int lmvn_plan_create(lmvn_plan** out, const int* dims_zyx, int num_views, int device);
 LMVN_EXPORT void lmvn_plan_destroy(lmvn_plan* plan);
 LMVN_EXPORT int lmvn_plan_get_info(const lmvn_plan* plan, lmvn_plan_info* info);

@@ -68,7 +68,8 @@ REFERENCE_SYMBOLS = [
     "getNameDeviceCUDA", "getMemDeviceCUDA",
 ]
 EXTENSION_SYMBOLS = [
-    "lmvn_last_error", "lmvn_clear_error", "lmvn_version", "lmvn_set_default_strategy", "lmvn_plan_create",
+    "lmvn_last_error", "lmvn_clear_error", "lmvn_version", "lmvn_set_default_strategy", "lmvn_release_cached_memory",
+    "lmvn_plan_create",
     "lmvn_plan_destroy", "lmvn_plan_get_info", "lmvn_plan_set_view", "lmvn_plan_set_psi", "lmvn_plan_get_psi",
     "lmvn_plan_iterate", "lmvn_plan_convolve", "lmvn_plan_profile", "lmvn_plan_synchronize", "lmvn_debug_rfftn", "lmvn_debug_irfftn",
     "lmvn_dist_create", "lmvn_dist_destroy", "lmvn_dist_get_info", "lmvn_dist_export_handle", "lmvn_dist_connect_ipc",
@@ -115,6 +116,7 @@ class Library:
         L.lmvn_last_error.restype = C.c_char_p
         L.lmvn_version.restype = C.c_char_p
         L.lmvn_clear_error.restype = None
+        L.lmvn_release_cached_memory.restype = None
         L.inplace_gpu_deconvolve.argtypes = [c_float_p, Workspace, C.c_int]
         L.inplace_gpu_deconvolve.restype = None
         L.inplace_cpu_deconvolve.argtypes = [c_float_p, Workspace, C.c_int]
@@ -163,6 +165,9 @@ class Library:
         L.lmvn_dist_synchronize.argtypes = [C.c_void_p]
         L.lmvn_debug_rfftn.argtypes = [c_float_p, c_int_p, c_float_p, C.c_int]
         L.lmvn_debug_irfftn.argtypes = [c_float_p, c_int_p, c_float_p, C.c_int]
+
+    def release_cached_memory(self):
+        self.lib.lmvn_release_cached_memory()
 
     # -- error plumbing ----------------------------------------------------
     def last_error(self) -> str:

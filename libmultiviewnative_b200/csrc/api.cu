@@ -42,6 +42,8 @@ extern "C" int lmvn_set_default_strategy(int s) {
   return 0;
 }
 
+extern "C" void lmvn_release_cached_memory(void) { release_cached_memory(); }
+
 extern "C" int lmvn_plan_create(lmvn_plan** out, const int* dims_zyx, int num_views, int device) {
   if (!out) {
     set_last_error("out is null");

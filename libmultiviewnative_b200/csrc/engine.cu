@@ -255,13 +255,64 @@ std::unique_ptr<ConvEngine> make_fused_engine(std::shared_ptr<FftPlan>) { return
 // ------------------------------------------------------------------------------
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// One parked arena per device.  Fiji calls inplace_gpu_deconvolve once per block with identical
+// shapes (ref: bench/bench_gpu_deconvolve.cu:48-49); returning several GiB to the driver and asking
+// for them again costs tens to hundreds of milliseconds per call (fresh pages are scrubbed).  A
+// destroyed handle parks its arena here, the next handle on that device takes it when it is large
+// enough.  lmvn_release_cached_memory() / LMVN_CACHE_ARENA=0 give the memory back.
+namespace {
+struct ParkedArena { unsigned char* p = nullptr; size_t bytes = 0; };
+std::mutex g_arena_mu;
+std::map<int, ParkedArena> g_parked;
+bool arena_cache_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LMVN_CACHE_ARENA");
+    v = (e && *e == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+unsigned char* take_parked(int device, size_t bytes, size_t* capacity) {
+  std::lock_guard<std::mutex> lk(g_arena_mu);
+  auto it = g_parked.find(device);
+  if (it == g_parked.end() || !it->second.p) return nullptr;
+  if (it->second.bytes < bytes || it->second.bytes > bytes + bytes / 2 + (size_t(64) << 20)) {
+    cudaFree(it->second.p);  // too small, or wastefully large for this request
+    g_parked.erase(it);
+    return nullptr;
+  }
+  unsigned char* p = it->second.p;
+  *capacity = it->second.bytes;
+  g_parked.erase(it);
+  return p;
+}
+void park(int device, unsigned char* p, size_t bytes) {
+  if (!arena_cache_enabled()) { cudaFree(p); return; }
+  std::lock_guard<std::mutex> lk(g_arena_mu);
+  ParkedArena& slot = g_parked[device];
+  if (slot.p) cudaFree(slot.p);
+  slot.p = p;
+  slot.bytes = bytes;
+}
+}  // namespace
+
+void release_cached_memory() {
+  std::lock_guard<std::mutex> lk(g_arena_mu);
+  for (auto& kv : g_parked)
+    if (kv.second.p) {
+      cudaSetDevice(kv.first);
+      cudaFree(kv.second.p);
+    }
+  g_parked.clear();
+}
+
 Deconv::~Deconv() {
   if (arena || stream) cudaSetDevice(device);
   if (stream) cudaStreamSynchronize(stream);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   if (stream) cudaStreamDestroy(stream);
-  if (arena) cudaFree(arena);
+  if (arena) park(device, arena, arena_capacity);
 }
 
 static const size_t kMaxKernelVoxels = size_t(1) << 24;
@@ -298,15 +349,19 @@ int Deconv::init(const int* d, int nviews, int dev, int strategy) {
   kernel_stage_elems = std::min(kMaxKernelVoxels, fp->voxels());
   const size_t KS = align_up(kernel_stage_elems * sizeof(float), 256);
   arena_bytes = 2 * S + W + KS + size_t(nviews) * (2 * S + 2 * K);
-  size_t free_b = 0, total_b = 0;
-  LMVN_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-  if (arena_bytes > free_b) {
-    // ref: src/multiviewnative.cu:138-141 prints and returns with psi untouched
-    set_last_error("deconvolution of %dx%dx%d with %d views needs %.2f GiB of device memory, %.2f GiB free",
-                   d[0], d[1], d[2], nviews, arena_bytes / 1073741824.0, free_b / 1073741824.0);
-    return -1;
+  arena = take_parked(device, arena_bytes, &arena_capacity);
+  if (!arena) {
+    size_t free_b = 0, total_b = 0;
+    LMVN_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    if (arena_bytes > free_b) {
+      // ref: src/multiviewnative.cu:138-141 prints and returns with psi untouched
+      set_last_error("deconvolution of %dx%dx%d with %d views needs %.2f GiB of device memory, %.2f GiB free",
+                     d[0], d[1], d[2], nviews, arena_bytes / 1073741824.0, free_b / 1073741824.0);
+      return -1;
+    }
+    LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&arena), arena_bytes));
+    arena_capacity = arena_bytes;
   }
-  LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&arena), arena_bytes));
   unsigned char* p = arena;
   auto take = [&](size_t bytes) { unsigned char* r = p; p += bytes; return r; };
   psi = reinterpret_cast<float*>(take(S));

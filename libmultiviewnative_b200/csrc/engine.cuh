@@ -110,6 +110,7 @@ struct Deconv {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   unsigned char* arena = nullptr;
   size_t arena_bytes = 0;
+  size_t arena_capacity = 0;  // bytes of the underlying allocation (>= arena_bytes when taken from the park)
   float* psi = nullptr;
   float* integral = nullptr;
   cplx* work = nullptr;
@@ -134,6 +135,7 @@ struct Deconv {
               std::vector<unsigned long long>& alg_bytes);
 };
 
+void release_cached_memory();  // frees the arenas parked by destroyed handles
 int resolve_device(int device);  // < 0 -> highest compute capability; validates range
 
 // debug hooks / legacy single-step entry points (host pointers unless noted)

@@ -226,11 +226,14 @@ template <> struct Radix<512> { static const int S = 3, R1 = 8, R2 = 8, R3 = 8; 
 template <> struct Radix<256> { static const int S = 3, R1 = 8, R2 = 8, R3 = 4; };
 template <> struct Radix<128> { static const int S = 3, R1 = 8, R2 = 4, R3 = 4; };
 #endif
+// 1024 keeps three stages: a 32 x 32 plan would need 64 registers of K^ next to 64 of data in the merged z pass
+template <> struct Radix<1024> { static const int S = 3, R1 = 16, R2 = 16, R3 = 4; };
 template <> struct Radix<64> { static const int S = 2, R1 = 8, R2 = 8, R3 = 1; };
 template <> struct Radix<32> { static const int S = 2, R1 = 8, R2 = 4, R3 = 1; };
 template <> struct Radix<16> { static const int S = 2, R1 = 4, R2 = 4, R3 = 1; };
 
-template <int N> struct Cols { static const int V = (N >= 256) ? 16 : (N >= 128 ? 32 : 64); };
+// tile width in kx columns: N x COLS x 8 bytes of shared memory; 1024 rows take half lines (64 KB tiles)
+template <int N> struct Cols { static const int V = (N >= 1024) ? 8 : ((N >= 256) ? 16 : (N >= 128 ? 32 : 64)); };
 
 static const int kStridedThreads = 256;
 #ifndef LMVN_ZMUL_BLOCKS
@@ -245,7 +248,7 @@ static const int kStridedThreads = 256;
 
 // resident CTAs per SM the register budget is sized for
 template <int N, int MODE> struct StridedBlocks {
-  static const int V = (Radix<N>::R1 >= 32) ? 2
+  static const int V = (Radix<N>::R1 >= 32 || N >= 1024) ? 2
                        : (((MODE == SM_FWD_MUL_INV || MODE == SM_FWD_MUL_INV_SCATTER) && N >= 64) ? LMVN_ZMUL_BLOCKS : 3);
 };
 
@@ -432,7 +435,7 @@ static __global__ void __launch_bounds__(kStridedThreads, StridedBlocks<N, MODE>
   constexpr int U = ZMUL ? LMVN_ZMUL_UNROLL : LMVN_Y_UNROLL;
   if (ZMUL && A.prefetch_khat) {
     // K^ is first needed two stages from now: start its trip from HBM to L2 right away
-    constexpr int LINES = COLS / 16;
+    constexpr int LINES = (COLS + 15) / 16;
     const long long tb = (long long)blockIdx.y * A.tile_stride + blockIdx.x * COLS;
     for (int i = threadIdx.x; i < N * LINES; i += kStridedThreads)
       prefetch_l2(A.khat + tb + (long long)(i / LINES) * A.row_stride + (i % LINES) * 16);
@@ -442,7 +445,7 @@ static __global__ void __launch_bounds__(kStridedThreads, StridedBlocks<N, MODE>
     const long long id = (long long)blockIdx.y * gridDim.x + blockIdx.x + A.prefetch;
     if (id < (long long)gridDim.x * gridDim.y) {
       const long long fb = (id / gridDim.x) * A.tile_stride + (id % gridDim.x) * COLS;
-      constexpr int LINES = COLS / 16;  // 128-byte lines per tile row
+      constexpr int LINES = (COLS + 15) / 16;  // 128-byte lines per tile row
       for (int i = threadIdx.x; i < N * LINES; i += kStridedThreads) {
         const long long off = fb + (long long)(i / LINES) * A.row_stride + (i % LINES) * 16;
         prefetch_l2(A.data + off);

@@ -149,6 +149,7 @@ struct FastEngine : ConvEngine, FastOps {
   static int upload_stage_tables(cplx** dst, int n) {
     int r1, r2;
     switch (n) {
+      case 1024: r1 = fast::Radix<1024>::R1; r2 = fast::Radix<1024>::R2; break;
       case 512: r1 = fast::Radix<512>::R1; r2 = fast::Radix<512>::R2; break;
       case 256: r1 = fast::Radix<256>::R1; r2 = fast::Radix<256>::R2; break;
       case 128: r1 = fast::Radix<128>::R1; r2 = fast::Radix<128>::R2; break;
@@ -228,6 +229,7 @@ struct FastEngine : ConvEngine, FastOps {
       case 32: LMVN_TRY(launch_rows_fwd2<32>(a, w, s)); break;
       case 64: LMVN_TRY(launch_rows_fwd2<64>(a, w, s)); break;
       case 128: LMVN_TRY(launch_rows_fwd2<128>(a, w, s)); break;
+      case 256: LMVN_TRY(launch_rows_fwd2<256>(a, w, s)); break;
       default: set_last_error("fused path: unsupported nx"); return -1;
     }
     LMVN_CUDA_TRY(cudaGetLastError());
@@ -254,6 +256,7 @@ struct FastEngine : ConvEngine, FastOps {
       case 32: LMVN_TRY(launch_rows_inv2<32>(a, s)); break;
       case 64: LMVN_TRY(launch_rows_inv2<64>(a, s)); break;
       case 128: LMVN_TRY(launch_rows_inv2<128>(a, s)); break;
+      case 256: LMVN_TRY(launch_rows_inv2<256>(a, s)); break;
       default: set_last_error("fused path: unsupported nx"); return -1;
     }
     LMVN_CUDA_TRY(cudaGetLastError());
@@ -338,6 +341,7 @@ struct FastEngine : ConvEngine, FastOps {
       LMVN_STRIDED_CASE(128)
       LMVN_STRIDED_CASE(256)
       LMVN_STRIDED_CASE(512)
+      LMVN_STRIDED_CASE(1024)
       default: set_last_error("fused path: unsupported axis length %d", g.n); return -1;
     }
 #undef LMVN_STRIDED_CASE
@@ -399,13 +403,14 @@ struct FastEngine : ConvEngine, FastOps {
   }
 };
 
-bool axis_ok(int n) { return n == 16 || n == 32 || n == 64 || n == 128 || n == 256 || n == 512; }
+bool axis_ok(int n) { return n == 16 || n == 32 || n == 64 || n == 128 || n == 256 || n == 512 || n == 1024; }
+bool nx_ok(int nx) { return nx == 64 || nx == 128 || nx == 256 || nx == 512; }
 
 }  // namespace
 
 std::unique_ptr<FastOps> make_fast_ops(std::shared_ptr<FftPlan> plan) {
   const int nx = plan->nx;
-  if (!(nx == 64 || nx == 128 || nx == 256) || !axis_ok(plan->ny) || !axis_ok(plan->nz)) {
+  if (!nx_ok(nx) || !axis_ok(plan->ny) || !axis_ok(plan->nz)) {
     set_last_error("slab-decomposed engine: dims %dx%dx%d are not supported by the power-of-two fast path",
                    plan->nz, plan->ny, plan->nx);
     return nullptr;
@@ -419,7 +424,7 @@ std::unique_ptr<FastOps> make_fast_ops(std::shared_ptr<FftPlan> plan) {
 
 std::unique_ptr<ConvEngine> make_fused_engine(std::shared_ptr<FftPlan> plan) {
   const int nx = plan->nx;
-  if (!(nx == 64 || nx == 128 || nx == 256)) return nullptr;
+  if (!nx_ok(nx)) return nullptr;
   if (!axis_ok(plan->ny) || !axis_ok(plan->nz)) return nullptr;
   const size_t rows = size_t(plan->nz) * plan->ny;
   if (rows % 128 != 0) return nullptr;

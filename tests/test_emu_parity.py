@@ -109,6 +109,7 @@ def LF(L):
 @pytest.mark.parametrize("dims,kdims", [
     ((16, 16, 64), (5, 5, 5)), ((32, 64, 128), (7, 4, 3)), ((64, 16, 256), (3, 3, 9)), ((16, 128, 64), (5, 5, 5)),
     ((256, 16, 64), (5, 5, 5)), ((16, 512, 64), (3, 9, 3)), ((512, 16, 64), (9, 3, 3)), ((16, 16, 64), (16, 16, 64)),
+    ((16, 16, 512), (3, 3, 11)), ((16, 1024, 64), (3, 9, 3)), ((1024, 16, 64), (9, 3, 3)),
 ])
 def test_fused_conv_random(LF, dims, kdims):
     pc.case_conv_random_vs_oracle(LF, dims, kdims)

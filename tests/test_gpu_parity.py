@@ -69,7 +69,7 @@ def test_conv_identity_asymmetric_image(LS):
 @pytest.mark.parametrize("dims,kdims", [
     ((64, 64, 64), (15, 15, 15)), ((128, 64, 64), (21, 21, 21)), ((128, 128, 64), (31, 31, 31)),
     ((64, 64, 64), (63, 63, 63)), ((12, 10, 14), (4, 3, 2)), ((8, 8, 8), (8, 8, 8)), ((50, 36, 30), (7, 9, 5)),
-    ((256, 128, 128), (41, 41, 41)),
+    ((256, 128, 128), (41, 41, 41)), ((64, 128, 512), (9, 5, 21)), ((64, 1024, 64), (3, 31, 3)), ((1024, 64, 64), (31, 3, 3)),
 ])
 def test_conv_random_vs_oracle(LS, dims, kdims):
     pc.case_conv_random_vs_oracle(LS, dims, kdims)

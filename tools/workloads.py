@@ -1,0 +1,200 @@
+"""Secondary workloads of bench.py (BASELINE.json configs 2, 4 and 5).  The default bench.py run is
+config 3; these print the same kind of JSON line for the other measurement rows of SURVEY.md §8d."""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+
+SWEEP_SHAPES = [(64, 64, 64), (128, 64, 64), (128, 128, 64), (128, 128, 128), (256, 128, 128), (256, 256, 128),
+                (256, 256, 256), (512, 256, 256), (512, 512, 256), (512, 512, 512)]  # ref: python/generate_dims.py:4-48
+SWEEP_KERNELS = [15, 21, 31, 41, 63]                                                  # 21 = reference default
+
+
+def conv_bytes(dims):
+    """Device-resident convolution with a precomputed K^: image S->C, (C + K^ C)->C, C->S = 2S + 5C.
+    (SURVEY.md §8d's B_conv = 2S + 6C additionally counts building K^ once per call; that part is in e2e_ms.)"""
+    nz, ny, nx = dims
+    S = 4 * nz * ny * nx
+    C = 8 * nz * ny * (nx // 2 + 1)
+    return 2 * S + 5 * C
+
+
+def conv_sweep(args, lib, torch, peak, peak_src, device=0):
+    """Config 2: single-view FFT convolution, device-resident (CUDA events) and through
+    inplace_gpu_convolution with host pointers; cuFFT (torch.fft) pipeline timed beside it."""
+    from libmultiviewnative_b200.synthetic import gaussian_psf
+    from oracle import mvn_oracle as orc  # checker only: correctness of every shape, outside the timed regions
+
+    rows = []
+    rng = np.random.default_rng(11)
+    shapes = SWEEP_SHAPES if not args.dims else [tuple(int(x) for x in args.dims.split(","))]
+    for dims in shapes:
+        img = (rng.random(dims, dtype=np.float32) + 1.0).astype(np.float32)
+        timg = torch.from_numpy(img).pin_memory()
+        for ks in SWEEP_KERNELS:
+            if ks > min(dims):
+                continue
+            k = gaussian_psf(ks, (ks / 8.0, ks / 10.0, ks / 12.0))
+            with lib.plan(dims, 1, device) as p:
+                p.set_view(0, img, img, k, k)
+                p.set_psi(img)
+                info = p.info()
+                p.convolve(0, 1, 1)                      # warm-up (reference: 1 warm-up, 10 timed repeats)
+                ms = p.convolve(0, 1, 10) / 10.0
+                strategy = info.strategy
+            # end to end through the reference entry point, host pointers (pinned)
+            work = timg.numpy()
+            out = work.copy()
+            lib.inplace_gpu_convolution(out, k, device)   # warm-up + result for the check
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                lib.inplace_gpu_convolution(work, k, device)
+            e2e_ms = (time.perf_counter() - t0) / reps * 1e3
+            np.copyto(work, img)
+            # cuFFT comparator: rfftn -> multiply -> irfftn with a precomputed kernel spectrum
+            x = torch.from_numpy(img).to("cuda:%d" % device)
+            kh = torch.fft.rfftn(torch.from_numpy(orc.wrap_kernel(k, dims)).to(x.device))
+            torch.fft.irfftn(torch.fft.rfftn(x) * kh, s=dims)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                y = torch.fft.irfftn(torch.fft.rfftn(x) * kh, s=dims)
+            e1.record()
+            torch.cuda.synchronize()
+            cufft_ms = e0.elapsed_time(e1) / 10.0
+            err = None
+            if np.prod(dims) <= 256 ** 3 and ks == 21:
+                exp = orc.inplace_cpu_convolution(img, k)
+                err = float(np.linalg.norm(out - exp) / np.linalg.norm(exp))
+                assert err < 1e-5, (dims, ks, err)
+            del x, kh, y
+            nb = conv_bytes(dims)
+            rows.append({"dims_zyx": list(dims), "kernel": ks, "strategy": int(strategy), "ms": ms, "GBps": nb / (ms * 1e-3) / 1e9,
+                         "frac_of_peak": nb / (ms * 1e-3) / 1e9 / peak, "e2e_ms": e2e_ms, "cufft_pipeline_ms": cufft_ms,
+                         "speedup_vs_cufft": cufft_ms / ms, "rel_l2_vs_oracle": err})
+    big = max(rows, key=lambda r: (np.prod(r["dims_zyx"]), -abs(r["kernel"] - 21)))
+    return {
+        "metric": "fft_conv_GBps", "value": big["GBps"], "unit": "GB/s", "n_gpus": 1, "steps": 10, "warmup": 1,
+        "ms_per_step": big["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "config 2: single-view 3-D FFT convolution sweep, bytes = 2S + 5C per device-resident convolution",
+                   "headline_row": {"dims_zyx": big["dims_zyx"], "kernel": big["kernel"]},
+                   "peak": peak, "peak_source": peak_src},
+        "sweep": rows,
+    }
+
+
+def blocks(args, lib, torch, dist, rank, world, device, fast_views, barrier, max_over_ranks):
+    """Config 4: independent 256^3 blocks (6 views, 41^3 PSFs, 50 iterations) sharded b -> GPU b mod G,
+    every block through inplace_gpu_deconvolve with host buffers (H2D/D2H inside the timed region)."""
+    from libmultiviewnative_b200.blocks import shard
+
+    dims = tuple(int(x) for x in args.dims.split(",")) if args.dims else (256, 256, 256)
+    n_blocks = args.blocks
+    workers = max(1, (os.cpu_count() or 1) // max(1, world))
+    distinct = [fast_views(dims, args.views, args.kernel, 20240607 + 17 * i, workers) for i in range(4)]
+
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+    keep = []
+    for d in distinct:
+        for key in ("views", "weights"):
+            for i, a in enumerate(d[key]):
+                tt, d[key][i] = pin(a)
+                keep.append(tt)
+    tt, psi = pin(distinct[0]["psi0"].copy())
+    keep.append(tt)
+    mine = shard(n_blocks, rank, world)
+
+    def run_block(b):
+        d = distinct[b % len(distinct)]
+        np.copyto(psi, d["psi0"])
+        t0 = time.perf_counter()
+        lib.inplace_gpu_deconvolve(psi, d["views"], d["kernels1"], d["kernels2"], d["weights"], args.iterations, 0.006,
+                                   1e-4, device)
+        return time.perf_counter() - t0
+
+    run_block(mine[0] if mine else 0)  # warm-up
+    barrier()
+    t_wall = time.perf_counter()
+    busy = sum(run_block(b) for b in mine)
+    barrier()
+    wall = max_over_ranks(time.perf_counter() - t_wall)
+    busy = max_over_ranks(busy)
+    nvox = float(np.prod(dims))
+    units = nvox * args.views * args.iterations * n_blocks
+    return {
+        "metric": "rl_deconv_gvoxel_view_iter_per_s", "value": units / busy / 1e9, "unit": "Gvoxel*view*iter/s",
+        "n_gpus": world, "steps": n_blocks, "warmup": 1, "ms_per_step": busy / max(1, len(mine)) * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config 4: %d independent %dx%dx%d blocks, %d views, %d^3 PSFs, %d iterations, block b on GPU b mod G, "
+                               "no collective; every block through inplace_gpu_deconvolve with pinned host buffers" % (
+                                   n_blocks, dims[0], dims[1], dims[2], args.views, args.kernel, args.iterations),
+                   "blocks_per_rank": len(mine), "wall_s_incl_host_psi_reset": wall},
+        "e2e": {"value": units / busy / 1e9, "unit": "Gvoxel*view*iter/s",
+                "h2d_bytes_per_step": int((2 * args.views + 1) * nvox * 4), "d2h_bytes_per_step": int(nvox * 4)},
+    }
+
+
+def volume(args, lib, torch, dist, rank, world, device, barrier, max_over_ranks, peak, peak_src):
+    """Config 5: ONE volume over G GPUs: slab-decomposed FFT, exchanges fused into the transform kernels
+    as stores into peer memory over NVLink.  Strong scaling; G = 1 runs the ordinary plan."""
+    from libmultiviewnative_b200.slabs import ProcessSlabPlan
+    from libmultiviewnative_b200.synthetic import gaussian_psf
+
+    dims = tuple(int(x) for x in args.dims.split(",")) if args.dims else (512, 512, 256)
+    nvox = float(np.prod(dims))
+    iters = args.iterations
+    rng = np.random.default_rng(5 + rank)
+    nz_l = dims[0] // world
+    slab = (nz_l, dims[1], dims[2])
+    # timing is data independent: one random slab serves as every view, constant weights
+    img = (rng.random(slab, dtype=np.float32) + 1.0).astype(np.float32)
+    wts = np.full(slab, 1.0 / args.views, dtype=np.float32)
+    k = gaussian_psf(args.kernel, (4.0, 1.5, 1.5))
+    k2 = np.ascontiguousarray(k[::-1, ::-1, ::-1])
+    exch = 0
+    if world == 1:
+        plan = lib.plan(dims, args.views, device)
+        for v in range(args.views):
+            plan.set_view(v, img, wts, k, k2)
+        plan.set_psi(img)
+        run = lambda n: plan.iterate(n, 0.006, 1e-4)
+    else:
+        plan = ProcessSlabPlan(lib, dims, args.views, dist, device)
+        for v in range(args.views):
+            plan.set_view(v, img, wts, k, k2)
+        plan.set_psi_slab(img)
+        exch = int(plan.info().exchange_bytes_per_view_iteration)
+        run = lambda n: plan.iterate(n, 0.006, 1e-4)
+    for _ in range(args.warmup):
+        run(iters)
+    barrier()
+    ms = 0.0
+    for _ in range(args.steps):
+        ms += run(iters)
+    barrier()
+    ms = max_over_ranks(ms)
+    units = nvox * args.views * iters * args.steps
+    S = 4 * nvox
+    C = 8 * dims[0] * dims[1] * (dims[2] // 2 + 1)
+    alg = 7 * S + 10 * C
+    gbps = alg * args.views * iters * args.steps / (ms * 1e-3) / 1e9
+    plan.close()
+    return {
+        "metric": "rl_deconv_gvoxel_view_iter_per_s", "value": units / (ms * 1e-3) / 1e9, "unit": "Gvoxel*view*iter/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config 5: ONE %dx%dx%d volume, %d views, %d^3 PSFs, %d iterations, slabs of nz/G planes, "
+                               "pencils of ny/G rows, exchanges = P2P stores from the y / z transform kernels" % (
+                                   dims[0], dims[1], dims[2], args.views, args.kernel, iters),
+                   "exchange_bytes_per_view_iteration_all_ranks": exch},
+        "roofline": {"bound": "hbm", "achieved": gbps, "peak": peak * world, "unit": "GB/s", "frac": gbps / (peak * world),
+                     "peak_source": peak_src + " x n_gpus", "alg_bytes_per_view_iteration": alg,
+                     "nvlink_GBps_per_gpu_out": (exch / world) * args.views * iters * args.steps / (ms * 1e-3) / 1e9 if world > 1 else 0.0},
+    }
