@@ -3,6 +3,7 @@
 #include "engine.cuh"
 #include "fft_generic.cuh"
 
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 
@@ -326,13 +327,21 @@ int Deconv::init(const int* d, int nviews, int dev, int strategy) {
     set_last_error("invalid number of views %d", nviews);
     return -1;
   }
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (trace_enabled())
+      trace("  init %-18s +%.2f ms", what,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+  };
   device = resolve_device(dev);
   if (device < 0) return -1;
   LMVN_CUDA_TRY(cudaSetDevice(device));
   dims[0] = d[0]; dims[1] = d[1]; dims[2] = d[2];
   num_views = nviews;
+  lap("device");
   auto fp = get_fft_plan(device, d[0], d[1], d[2]);
   if (!fp) return -1;
+  lap("fft plan");
   if (strategy == 0) strategy = default_strategy();
   if (strategy == 0 || strategy == 2) {
     engine = make_fused_engine(fp);
@@ -342,6 +351,7 @@ int Deconv::init(const int* d, int nviews, int dev, int strategy) {
     }
   }
   if (!engine) engine = make_generic_engine(fp);
+  lap("engine");
 
   const size_t S = align_up(fp->voxels() * sizeof(float), 256);
   const size_t K = align_up(engine->khat_elems() * sizeof(cplx), 256);
@@ -362,6 +372,7 @@ int Deconv::init(const int* d, int nviews, int dev, int strategy) {
     LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&arena), arena_bytes));
     arena_capacity = arena_bytes;
   }
+  lap("arena");
   unsigned char* p = arena;
   auto take = [&](size_t bytes) { unsigned char* r = p; p += bytes; return r; };
   psi = reinterpret_cast<float*>(take(S));
@@ -379,6 +390,7 @@ int Deconv::init(const int* d, int nviews, int dev, int strategy) {
   LMVN_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   LMVN_CUDA_TRY(cudaEventCreate(&ev0));
   LMVN_CUDA_TRY(cudaEventCreate(&ev1));
+  lap("stream+events");
   trace("deconv handle dev=%d dims=%dx%dx%d views=%d strategy=%d arena=%.1f MiB", device, d[0], d[1],
         d[2], nviews, engine->strategy(), arena_bytes / 1048576.0);
   return 0;

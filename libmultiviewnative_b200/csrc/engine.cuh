@@ -33,6 +33,9 @@ struct FftPlan {
   cplx* d_tw[3] = {nullptr, nullptr, nullptr};
   int lines[3] = {1, 1, 1};    // lines per CTA in the generic passes
   size_t smem[3] = {0, 0, 0};  // dynamic shared memory of the generic passes
+  // device tables of the fast path, built once per (device, dims) and shared by every engine on the plan
+  std::shared_ptr<void> fast_tables;
+  std::mutex fast_mu;
   size_t voxels() const { return size_t(nz) * ny * nx; }
   size_t spec_elems() const { return size_t(nz) * ny * nxc; }
   ~FftPlan();

@@ -23,7 +23,28 @@ namespace {
 
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
+// twiddle tables + device facts, cached on the FftPlan (process-wide store): creating an engine for a
+// shape that has been seen before makes no CUDA allocation and no synchronous copy
+struct FastTables {
+  int device = 0;
+  int num_sms = 148;
+  cplx* tw_m = nullptr;
+  cplx* tw_nx = nullptr;
+  cplx* tw_y[2] = {nullptr, nullptr};
+  cplx* tw_z[2] = {nullptr, nullptr};
+  ~FastTables() {
+    cudaSetDevice(device);
+    if (tw_m) cudaFree(tw_m);
+    if (tw_nx) cudaFree(tw_nx);
+    for (int i = 0; i < 2; ++i) {
+      if (tw_y[i]) cudaFree(tw_y[i]);
+      if (tw_z[i]) cudaFree(tw_z[i]);
+    }
+  }
+};
+
 struct FastEngine : ConvEngine, FastOps {
+  std::shared_ptr<FastTables> tables;
   int M = 0, nxc = 0, nxp = 0;
   int num_sms = 148;
   int rows_ctas_per_sm = 8;
@@ -42,13 +63,7 @@ struct FastEngine : ConvEngine, FastOps {
   cplx* d_tw_z[2] = {nullptr, nullptr};
 
   ~FastEngine() override {
-    if (d_tw_m) cudaFree(d_tw_m);
-    if (d_tw_nx) cudaFree(d_tw_nx);
     if (d_xy_sync) cudaFree(d_xy_sync);
-    for (int i = 0; i < 2; ++i) {
-      if (d_tw_y[i]) cudaFree(d_tw_y[i]);
-      if (d_tw_z[i]) cudaFree(d_tw_z[i]);
-    }
   }
   int strategy() const override { return 2; }
   size_t khat_elems() const override { return size_t(plan->nz) * plan->ny * nxp; }
@@ -76,17 +91,29 @@ struct FastEngine : ConvEngine, FastOps {
       if (const char* e = getenv("LMVN_NXP_ALIGN")) align = std::max(1, atoi(e));
       nxp = (nxc + align - 1) / align * align;
     }
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, plan->device) == cudaSuccess && prop.multiProcessorCount > 0)
-      num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("LMVN_PREFETCH")) y_fwd_prefetch = std::max(0, atoi(e));
     if (const char* e = getenv("LMVN_PREFETCH_KHAT")) khat_prefetch = atoi(e);
     if (const char* e = getenv("LMVN_PREFETCH_ROWS")) rows_prefetch = atoi(e);
     if (const char* e = getenv("LMVN_ROWS_CTAS")) rows_ctas_per_sm = std::max(1, atoi(e));
-    LMVN_TRY(upload_table(&d_tw_m, M, M));
-    LMVN_TRY(upload_table(&d_tw_nx, plan->nx, M + 1));
-    LMVN_TRY(upload_stage_tables(d_tw_y, plan->ny));
-    LMVN_TRY(upload_stage_tables(d_tw_z, plan->nz));
+    {
+      std::lock_guard<std::mutex> lk(plan->fast_mu);
+      if (!plan->fast_tables) {
+        std::shared_ptr<FastTables> t(new FastTables());
+        t->device = plan->device;
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, plan->device) == cudaSuccess && sms > 0)
+          t->num_sms = sms;
+        LMVN_TRY(upload_table(&t->tw_m, M, M));
+        LMVN_TRY(upload_table(&t->tw_nx, plan->nx, M + 1));
+        LMVN_TRY(upload_stage_tables(t->tw_y, plan->ny));
+        LMVN_TRY(upload_stage_tables(t->tw_z, plan->nz));
+        plan->fast_tables = t;
+      }
+      tables = std::static_pointer_cast<FastTables>(plan->fast_tables);
+    }
+    num_sms = tables->num_sms;
+    d_tw_m = tables->tw_m; d_tw_nx = tables->tw_nx;
+    for (int i = 0; i < 2; ++i) { d_tw_y[i] = tables->tw_y[i]; d_tw_z[i] = tables->tw_z[i]; }
     LMVN_TRY(init_xy());
     return 0;
   }

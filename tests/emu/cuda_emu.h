@@ -199,6 +199,8 @@ static inline cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = *t = size_
 template <typename F>
 static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
 enum { cudaErrorPeerAccessAlreadyEnabled = 704 };
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 4; return 0; }
 static inline cudaError_t cudaIpcCloseMemHandle(void*) { return 0; }
 static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return 0; }
 
