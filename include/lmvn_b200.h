@@ -138,6 +138,16 @@ LMVN_EXPORT int lmvn_dist_iterate(lmvn_dist* plan, int iterations, double lambda
                                   float* device_ms);
 LMVN_EXPORT int lmvn_dist_synchronize(lmvn_dist* plan);
 
+/* Comparator path: the same exchanges staged through local buffers and moved by the CALLER with a library
+ * all-to-all (NCCL).  set_staged(1): phase 0 / 1 scatter into STAGE_SEND as G contiguous blocks
+ * [dest][nz/G][ny/G][pitch]; the caller all-to-alls them into PENCIL_WORK (forward) or into STAGE_RECV and
+ * then interleaves the sources into SLAB_WORK ([nz/G][src][ny/G][pitch]) (backward).  set_stream makes the
+ * plan issue its kernels on the caller's stream so that both sides are stream ordered. */
+enum lmvn_dist_buffer_id { LMVN_DIST_SLAB_WORK = 0, LMVN_DIST_PENCIL_WORK = 1, LMVN_DIST_STAGE_SEND = 2, LMVN_DIST_STAGE_RECV = 3 };
+LMVN_EXPORT int lmvn_dist_set_stream(lmvn_dist* plan, void* cuda_stream);
+LMVN_EXPORT int lmvn_dist_set_staged(lmvn_dist* plan, int on);
+LMVN_EXPORT int lmvn_dist_buffer(lmvn_dist* plan, int which, void** device_ptr, unsigned long long* bytes);
+
 /* r2c / c2r of a host volume through the generic passes, natural layout:
  * spectrum = nz*ny*(nx/2+1) interleaved (re,im) pairs.  c2r is unnormalised. */
 LMVN_EXPORT int lmvn_debug_rfftn(const float* in, const int* dims_zyx, float* spectrum, int device);

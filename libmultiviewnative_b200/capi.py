@@ -75,6 +75,7 @@ EXTENSION_SYMBOLS = [
     "lmvn_dist_create", "lmvn_dist_destroy", "lmvn_dist_get_info", "lmvn_dist_export_handle", "lmvn_dist_connect_ipc",
     "lmvn_dist_connect_local", "lmvn_dist_set_view_slab", "lmvn_dist_set_psi_slab", "lmvn_dist_get_psi_slab",
     "lmvn_dist_psf_phase", "lmvn_dist_conv_phase", "lmvn_dist_barrier", "lmvn_dist_iterate", "lmvn_dist_synchronize",
+    "lmvn_dist_set_stream", "lmvn_dist_set_staged", "lmvn_dist_buffer",
 ]
 
 STRATEGY_AUTO, STRATEGY_GENERIC, STRATEGY_FUSED = 0, 1, 2
@@ -163,6 +164,9 @@ class Library:
         L.lmvn_dist_barrier.argtypes = [C.c_void_p]
         L.lmvn_dist_iterate.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_float, c_float_p]
         L.lmvn_dist_synchronize.argtypes = [C.c_void_p]
+        L.lmvn_dist_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.lmvn_dist_set_staged.argtypes = [C.c_void_p, C.c_int]
+        L.lmvn_dist_buffer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_ulonglong)]
         L.lmvn_debug_rfftn.argtypes = [c_float_p, c_int_p, c_float_p, C.c_int]
         L.lmvn_debug_irfftn.argtypes = [c_float_p, c_int_p, c_float_p, C.c_int]
 

@@ -102,6 +102,11 @@ struct DistDeconv {
   unsigned epoch = 0;
   unsigned** d_peer_flags = nullptr;  // device array of kMaxRanks pointers
   unsigned* d_err = nullptr;
+  // comparator: exchanges staged through local buffers and moved by the caller (NCCL all-to-all)
+  bool staged = false;
+  bool own_stream = true;
+  cplx* stage_send = nullptr;
+  cplx* stage_recv = nullptr;
 
   size_t slab_real() const { return size_t(nz_l) * ny * nx; }
   size_t slab_spec() const { return size_t(nz_l) * ny * nxp; }
@@ -117,7 +122,9 @@ struct DistDeconv {
       if (peer_ipc[r] && peer[r]) cudaIpcCloseMemHandle(peer[r]);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
-    if (stream) cudaStreamDestroy(stream);
+    if (stream && own_stream) cudaStreamDestroy(stream);
+    if (stage_send) cudaFree(stage_send);
+    if (stage_recv) cudaFree(stage_recv);
     if (d_peer_flags) cudaFree(d_peer_flags);
     if (d_err) cudaFree(d_err);
     if (arena) cudaFree(arena);
@@ -211,11 +218,16 @@ struct DistDeconv {
     g.mode = mode;
     if (mode == fast::SM_FWD_SCATTER) {
       // row y' of local plane z_l -> rank y'/ny_l, pencil [z = rank*nz_l + z_l][y' % ny_l][kx]
-      for (int r = 0; r < world; ++r) g.sc.base[r] = pencil_work(r);
       g.sc.shift = ilog2(ny_l);
       g.sc.row_stride = nxp;
       g.sc.tile_stride = (long long)ny_l * nxp;
-      g.sc.offset = (long long)rank * nz_l * ny_l * nxp;
+      if (!staged) {
+        for (int r = 0; r < world; ++r) g.sc.base[r] = pencil_work(r);
+        g.sc.offset = (long long)rank * nz_l * ny_l * nxp;
+      } else {  // send block of destination r: [z_l][y'_l][kx]; the all-to-all puts it at [src = rank] over there
+        for (int r = 0; r < world; ++r) g.sc.base[r] = stage_send + size_t(r) * nz_l * ny_l * nxp;
+        g.sc.offset = 0;
+      }
     }
     return g;
   }
@@ -228,11 +240,17 @@ struct DistDeconv {
     g.scale = scale;
     if (mode == fast::SM_FWD_MUL_INV_SCATTER) {
       // plane z of local row y'_l -> rank z/nz_l, slab [z % nz_l][y' = rank*ny_l + y'_l][kx]
-      for (int r = 0; r < world; ++r) g.sc.base[r] = slab_work(r);
       g.sc.shift = ilog2(nz_l);
-      g.sc.row_stride = (long long)ny * nxp;
       g.sc.tile_stride = nxp;
-      g.sc.offset = (long long)rank * ny_l * nxp;
+      if (!staged) {
+        for (int r = 0; r < world; ++r) g.sc.base[r] = slab_work(r);
+        g.sc.row_stride = (long long)ny * nxp;
+        g.sc.offset = (long long)rank * ny_l * nxp;
+      } else {  // send block of destination r: [z_l][y'_l][kx]; the receiver still has to interleave the sources
+        for (int r = 0; r < world; ++r) g.sc.base[r] = stage_send + size_t(r) * nz_l * ny_l * nxp;
+        g.sc.row_stride = (long long)ny_l * nxp;
+        g.sc.offset = 0;
+      }
     }
     return g;
   }
@@ -509,6 +527,47 @@ extern "C" int lmvn_dist_barrier(lmvn_dist* h) {
 extern "C" int lmvn_dist_iterate(lmvn_dist* h, int iterations, double lambda, float min_value, float* device_ms) {
   LMVN_DIST_GUARD(h);
   return h->d.iterate(iterations, lambda, min_value, device_ms);
+}
+
+extern "C" int lmvn_dist_set_stream(lmvn_dist* h, void* cuda_stream) {
+  LMVN_DIST_GUARD(h);
+  DistDeconv& d = h->d;
+  LMVN_CUDA_TRY(cudaSetDevice(d.device));
+  LMVN_CUDA_TRY(cudaStreamSynchronize(d.stream));
+  if (d.own_stream) LMVN_CUDA_TRY(cudaStreamDestroy(d.stream));
+  d.stream = static_cast<cudaStream_t>(cuda_stream);
+  d.own_stream = false;
+  return 0;
+}
+
+extern "C" int lmvn_dist_set_staged(lmvn_dist* h, int on) {
+  LMVN_DIST_GUARD(h);
+  DistDeconv& d = h->d;
+  LMVN_CUDA_TRY(cudaSetDevice(d.device));
+  if (on && !d.stage_send) {
+    const size_t bytes = std::max(d.slab_spec(), d.pencil_spec()) * sizeof(cplx);
+    LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d.stage_send), bytes));
+    LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d.stage_recv), bytes));
+  }
+  d.staged = on != 0;
+  return 0;
+}
+
+extern "C" int lmvn_dist_buffer(lmvn_dist* h, int which, void** ptr, unsigned long long* bytes) {
+  LMVN_DIST_GUARD(h);
+  DistDeconv& d = h->d;
+  if (!ptr || !bytes) { set_last_error("null output"); return -1; }
+  switch (which) {
+    case LMVN_DIST_SLAB_WORK: *ptr = d.slab_work(d.rank); *bytes = d.slab_spec() * sizeof(cplx); return 0;
+    case LMVN_DIST_PENCIL_WORK: *ptr = d.pencil_work(d.rank); *bytes = d.pencil_spec() * sizeof(cplx); return 0;
+    case LMVN_DIST_STAGE_SEND:
+    case LMVN_DIST_STAGE_RECV:
+      if (!d.stage_send) { set_last_error("staged exchange has not been enabled"); return -1; }
+      *ptr = which == LMVN_DIST_STAGE_SEND ? d.stage_send : d.stage_recv;
+      *bytes = std::max(d.slab_spec(), d.pencil_spec()) * sizeof(cplx);
+      return 0;
+    default: set_last_error("unknown buffer %d", which); return -1;
+  }
 }
 
 extern "C" int lmvn_dist_synchronize(lmvn_dist* h) {

@@ -201,3 +201,54 @@ class ProcessSlabPlan(SlabPlan):
             self.barrier()
             self.psf_phase(v, which, 1)
         self.synchronize()
+
+
+    # ---- comparator: the same exchanges through NCCL all_to_all_single ------------------------------
+    def _tensor(self, which: int, torch):
+        ptr, nbytes = C.c_void_p(), C.c_ulonglong()
+        self.L._check(self.L.lib.lmvn_dist_buffer(self.handle, which, C.byref(ptr), C.byref(nbytes)), "lmvn_dist_buffer")
+
+        class _Raw:  # device memory owned by the plan, exposed through the CUDA array interface
+            __cuda_array_interface__ = {"shape": (int(nbytes.value) // 4,), "typestr": "<f4", "data": (int(ptr.value), False),
+                                        "version": 3}
+        return torch.as_tensor(_Raw(), device="cuda")
+
+    def enable_nccl_comparator(self):
+        import torch
+
+        torch.cuda.synchronize()
+        self.synchronize()
+        self.L._check(self.L.lib.lmvn_dist_set_stream(self.handle, C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                      "lmvn_dist_set_stream")
+        self.L._check(self.L.lib.lmvn_dist_set_staged(self.handle, 1), "lmvn_dist_set_staged")
+        info = self.info()
+        g, nzl, nyl, p2 = self.world, info.planes_per_rank, info.rows_per_rank, 2 * info.spectrum_pitch
+        n = g * nzl * nyl * p2  # floats of one local spectrum
+        self._t = {
+            "slab": self._tensor(0, torch)[:n].view(nzl, g, nyl, p2),
+            "pencil": self._tensor(1, torch)[:n],
+            "send": self._tensor(2, torch)[:n],
+            "recv": self._tensor(3, torch)[:n],
+        }
+
+    def iterate_nccl(self, iterations: int, lam: float = 0.0, min_value: float = 1e-4) -> float:
+        """Same loop, exchanges = local scatter + torch.distributed.all_to_all_single (NCCL) + one interleaving
+        copy on the way back.  Returns the CUDA-event time in ms."""
+        import torch
+
+        t, g = self._t, self.world
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.dist.barrier()
+        e0.record()
+        for _ in range(int(iterations)):
+            for v in range(self.num_views):
+                for which in (1, 2):
+                    self.conv_phase(v, which, 0, lam, min_value)
+                    self.dist.all_to_all_single(t["pencil"], t["send"])
+                    self.conv_phase(v, which, 1, lam, min_value)
+                    self.dist.all_to_all_single(t["recv"], t["send"])
+                    t["slab"].copy_(t["recv"].view(g, t["slab"].shape[0], t["slab"].shape[2], t["slab"].shape[3]).permute(1, 0, 2, 3))
+                    self.conv_phase(v, which, 2, lam, min_value)
+        e1.record()
+        torch.cuda.synchronize()
+        return float(e0.elapsed_time(e1))
