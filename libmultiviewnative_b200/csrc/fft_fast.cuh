@@ -750,8 +750,14 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
   __syncwarp();
 }
 
+#ifndef LMVN_ROWS_FWD_BLOCKS
+#define LMVN_ROWS_FWD_BLOCKS 2
+#endif
+#ifndef LMVN_ROWS_INVQ_BLOCKS
+#define LMVN_ROWS_INVQ_BLOCKS 2
+#endif
 template <int M, bool WRAPPED>
-static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_fwd2(RowArgs A) {
+static __global__ void __launch_bounds__(kRowThreads, LMVN_ROWS_FWD_BLOCKS) k_rows_fwd2(RowArgs A) {
   typedef Row2Cfg<M> CF;
   LMVN_DYN_SMEM(cplx, sm);
   const int lane = threadIdx.x % 16;
@@ -769,7 +775,7 @@ static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_fwd2(RowArgs A) 
 }
 
 template <int M, int EPI>
-static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_inv2(RowArgs A) {
+static __global__ void __launch_bounds__(kRowThreads, EPI == gen::EPI_UPDATE ? 2 : LMVN_ROWS_INVQ_BLOCKS) k_rows_inv2(RowArgs A) {
   typedef Row2Cfg<M> CF;
   LMVN_DYN_SMEM(cplx, sm);
   __shared__ cplx s_tw[RowTwShared<M>::ENTRIES * 16];
