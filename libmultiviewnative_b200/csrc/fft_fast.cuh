@@ -239,8 +239,17 @@ template <> struct Radix<16> { static const int S = 2, R1 = 4, R2 = 4, R3 = 1; }
 
 // tile width in kx columns: N x COLS x 8 bytes of shared memory; 1024 rows take half lines (64 KB tiles)
 template <int N> struct Cols { static const int V = (N >= 1024) ? 8 : ((N >= 256) ? 16 : (N >= 128 ? 32 : 64)); };
+#ifdef LMVN_STRIDED_HALF
+template <> struct Cols<512> { static const int V = 8; };
+#endif
 
 static const int kStridedThreads = 256;
+// threads per CTA of a strided pass; LMVN_STRIDED_HALF (A/B knob): 512-point passes on half-line tiles
+// (8 columns, 32 KB) with 128 threads, four CTAs per SM instead of two
+template <int N> struct Threads { static const int V = kStridedThreads; };
+#ifdef LMVN_STRIDED_HALF
+template <> struct Threads<512> { static const int V = 128; };
+#endif
 #ifndef LMVN_ZMUL_BLOCKS
 #define LMVN_ZMUL_BLOCKS 2
 #endif
@@ -268,7 +277,7 @@ __device__ __forceinline__ void strided_stage(cplx* __restrict__ sm, cplx* __res
                                               const cplx* __restrict__ tws, float scale,
                                               const Scatter* sc = nullptr, long long sc_tile = 0) {
   constexpr int M = L / R;
-  constexpr int RG = kStridedThreads / COLS;   // row groups per block
+  constexpr int RG = Threads<N>::V / COLS;   // row groups per block
   constexpr int PER_THREAD = (N / R) / RG;
   static_assert(PER_THREAD >= 1, "tile too small for the block");
   const int rg = threadIdx.x / COLS;
@@ -335,7 +344,7 @@ __device__ __forceinline__ void strided_stage(cplx* __restrict__ sm, cplx* __res
 // the middle so that their latency overlaps the barrier wait and the shared-memory reads.
 template <int N, int R, int COLS>
 struct Middle {
-  static const int RG = kStridedThreads / COLS;
+  static const int RG = Threads<N>::V / COLS;
   static const int PT = (N / R) / RG;  // butterflies per thread: 1 or 2 in every plan that is used
   struct K { cplx k[PT][R]; };
   static __device__ __forceinline__ void load(K& o, const cplx* __restrict__ gk, int rs) {
@@ -429,7 +438,7 @@ __device__ __forceinline__ void strided_tile(const StridedArgs& A, cplx* sm, cpl
 }
 
 template <int N, int MODE>
-static __global__ void __launch_bounds__(kStridedThreads, StridedBlocks<N, MODE>::V)
+static __global__ void __launch_bounds__(Threads<N>::V, StridedBlocks<N, MODE>::V * (kStridedThreads / Threads<N>::V))
     k_strided(StridedArgs A) {
   constexpr int COLS = Cols<N>::V;
   LMVN_DYN_SMEM(cplx, smem);  // [N][COLS]
@@ -452,7 +461,7 @@ static __global__ void __launch_bounds__(kStridedThreads, StridedBlocks<N, MODE>
     // K^ is first needed two stages from now: start its trip from HBM to L2 right away
     constexpr int LINES = (COLS + 15) / 16;
     const long long tb = (long long)blockIdx.y * A.tile_stride + blockIdx.x * COLS;
-    for (int i = threadIdx.x; i < N * LINES; i += kStridedThreads)
+    for (int i = threadIdx.x; i < N * LINES; i += Threads<N>::V)
       prefetch_l2(A.khat + tb + (long long)(i / LINES) * A.row_stride + (i % LINES) * 16);
   }
   if (A.prefetch > 0) {
@@ -461,7 +470,7 @@ static __global__ void __launch_bounds__(kStridedThreads, StridedBlocks<N, MODE>
     if (id < (long long)gridDim.x * gridDim.y && !(A.nyq_gather && id % gridDim.x == gridDim.x - 1)) {
       const long long fb = (id / gridDim.x) * A.tile_stride + (id % gridDim.x) * COLS;
       constexpr int LINES = (COLS + 15) / 16;  // 128-byte lines per tile row
-      for (int i = threadIdx.x; i < N * LINES; i += kStridedThreads) {
+      for (int i = threadIdx.x; i < N * LINES; i += Threads<N>::V) {
         const long long off = fb + (long long)(i / LINES) * A.row_stride + (i % LINES) * 16;
         prefetch_l2(A.data + off);
       }
@@ -497,6 +506,7 @@ struct RowArgs {
   const cplx* tw_nx;     // w_nx^k, k = 0..M
   int prefetch;          // pull the next loop iteration's rows into L2 one iteration ahead
   int z0, nz_wrap;       // wrapped source on a slab of planes: global index of plane 0, global nz
+  const cplx* tw_h;      // nx = 1024 only: w_{M/2} table (M/2 entries) of the two half-length sub-transforms
 };
 
 // real-transform split for one (k, M-k) pair:  X[k] = E + w^k O,  X[M-k] = conj(E - w^k O)
@@ -807,6 +817,261 @@ static __global__ void __launch_bounds__(kRowThreads, EPI == gen::EPI_UPDATE ? 2
 }
 
 // ------------------------------------------------------------------------------
+// x passes for nx = 1024 (M = 512 complex samples per row).  One more radix-2 level
+// around the M = 256 scheme, decimation in time: a lane loads float4 = one even and one
+// odd complex sample (16 lanes x 16 B = two full lines), runs the two 256-point
+// sub-transforms E, O exactly like the M = 256 kernel (radix 16, exchange, radix 16,
+// exchange to natural order) and fuses the last butterfly Z[k] = E[k] + w_512^k O[k],
+// Z[k+256] = E[k] - w_512^k O[k] into the real-transform split: the pair (k, 512-k)
+// needs Z[k] and Z[256 + (256-k)] = E[256-k] + conj(w_512^k) O[256-k].  The inverse is
+// the mirror; E'[k], O'[k] for k = lane + 16 i are exactly the inputs of the lane's
+// first inverse radix-16, so the un-combine costs no extra exchange.
+// ------------------------------------------------------------------------------
+struct RowWide {
+  static const int H = 256, M = 512, NX = 1024;
+  static const int RS = 272;                 // 17 * 16: pitch of one half-length slab
+  static const int SLAB = 2 * RS;            // E and O (>= 512: also holds Z in natural order)
+  static const int GROUPS = kRowThreads / 16;
+  static const int ROWS = GROUPS;            // one row per 16-lane group and iteration
+  static const int SMEM = GROUPS * SLAB * int(sizeof(cplx));
+};
+
+__device__ __forceinline__ float4 ld_stream4(const float4* p) {
+#ifdef LMVN_EMU
+  return *p;
+#else
+  return __ldcg(p);
+#endif
+}
+__device__ __forceinline__ void st_stream4(float4* p, float4 v) {
+#ifdef LMVN_EMU
+  *p = v;
+#else
+  __stcg(p, v);
+#endif
+}
+
+template <bool WRAPPED>
+__device__ __forceinline__ void rows_fwd_wide_group(const RowArgs& A, cplx* slab, long long row, int lane) {
+  constexpr int H = RowWide::H, M = RowWide::M, nx = RowWide::NX, RS = RowWide::RS;
+  cplx* se = slab;
+  cplx* so = slab + RS;
+  cplx ve[16], vo[16];
+  if (!WRAPPED) {
+    const float4* in = reinterpret_cast<const float4*>(A.src.data + row * nx);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const float4 f = ld_stream4(in + lane + 16 * r);
+      ve[r] = cmake(f.x, f.y);
+      vo[r] = cmake(f.z, f.w);
+    }
+  } else {
+    const int z = int(row / A.ny) + A.z0, y = int(row % A.ny);
+    const int sz = gen::wrap_src_index(z, A.nz_wrap, A.src.kz);
+    const int sy = gen::wrap_src_index(y, A.ny, A.src.ky);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      float f[4] = {0.f, 0.f, 0.f, 0.f};
+      if (sz >= 0 && sy >= 0) {
+        const float* kr = A.src.data + (size_t(sz) * A.src.ky + sy) * A.src.kx;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int sx = gen::wrap_src_index(4 * (lane + 16 * r) + c, nx, A.src.kx);
+          if (sx >= 0) f[c] = kr[sx];
+        }
+      }
+      ve[r] = cmake(f[0], f[1]);
+      vo[r] = cmake(f[2], f[3]);
+    }
+  }
+  Bfly<16, false>::run(ve);
+  Bfly<16, false>::run(vo);
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    cplx a = ve[q], b = vo[q];
+    if (q > 0) {
+      const cplx w = __ldg(A.tw_h + lane * q);
+      a = cmul(a, w);
+      b = cmul(b, w);
+    }
+    se[q * 17 + lane] = a;
+    so[q * 17 + lane] = b;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    ve[j] = se[lane * 17 + j];
+    vo[j] = so[lane * 17 + j];
+  }
+  Bfly<16, false>::run(ve);
+  Bfly<16, false>::run(vo);
+  __syncwarp();
+#pragma unroll
+  for (int q2 = 0; q2 < 16; ++q2) {  // E[k], O[k], k = lane + 16 q2, natural order
+    se[lane + 16 * q2] = ve[q2];
+    so[lane + 16 * q2] = vo[q2];
+  }
+  __syncwarp();
+  cplx* orow = A.spec + row * A.nxp;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int k = lane + 16 * i;
+    if (k == 0) {
+      const cplx e0 = se[0], o0 = so[0];
+      const cplx z0 = cadd(e0, o0), zh = csub(e0, o0);  // Z[0], Z[256]
+      st_stream(orow, cmake(z0.x + z0.y, 0.f));
+      st_stream(orow + M, cmake(z0.x - z0.y, 0.f));
+      st_stream(orow + H, cconj(zh));
+    } else {
+      const cplx w5 = __ldg(A.tw_m + k);  // w_512^k
+      const cplx zk = cadd(se[k], cmul(so[k], w5));
+      const cplx zm = cadd(se[H - k], cmulc(so[H - k], w5));  // Z[512-k]
+      cplx xk, xm;
+      r2c_pair(zk, zm, __ldg(A.tw_nx + k), xk, xm);
+      st_stream(orow + k, xk);
+      st_stream(orow + (M - k), xm);
+    }
+  }
+  __syncwarp();
+}
+
+template <int EPI>
+__device__ __forceinline__ void rows_inv_wide_group(const RowArgs& A, cplx* slab, long long row, int lane) {
+  constexpr int H = RowWide::H, M = RowWide::M, nx = RowWide::NX, RS = RowWide::RS;
+  const cplx* irow = A.spec + row * A.nxp;
+  // ---- loads + inverse split: Z in natural order ----
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int k = lane + 16 * i;
+    const cplx xk = ld_stream(irow + k);
+    const cplx xm = ld_stream(irow + (M - k));  // k = 0 reads X[512]
+    if (k == 0) {
+      const cplx xh = ld_stream(irow + H);
+      slab[0] = cmake(xk.x + xm.x, xk.x - xm.x);  // imaginary parts ignored (c2r)
+      slab[H] = cmake(2.f * xh.x, -2.f * xh.y);
+    } else {
+      cplx zk, zm;
+      c2r_pair(xk, xm, __ldg(A.tw_nx + k), zk, zm);
+      slab[k] = zk;
+      slab[M - k] = zm;
+    }
+  }
+  __syncwarp();
+  // ---- un-combine: E'[k] = Z[k] + Z[k+256], O'[k] = (Z[k] - Z[k+256]) conj(w_512^k), k = lane + 16 i ----
+  cplx ve[16], vo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int k = lane + 16 * i;
+    const cplx a = slab[k], b = slab[k + H];
+    ve[i] = cadd(a, b);
+    const cplx d = csub(a, b);
+    vo[i] = (k == 0) ? d : cmulc(d, __ldg(A.tw_m + k));
+  }
+  // these are the inputs Z[q_blk + 16 q2] of the lane's first inverse radix-16 (q_blk = lane)
+  Bfly<16, true>::run(ve);
+  Bfly<16, true>::run(vo);
+  __syncwarp();
+  cplx* se = slab;
+  cplx* so = slab + RS;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    se[lane * 17 + j] = ve[j];
+    so[lane * 17 + j] = vo[j];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    cplx a = se[q * 17 + lane], b = so[q * 17 + lane];
+    if (q > 0) {
+      const cplx w = __ldg(A.tw_h + lane * q);
+      a = cmulc(a, w);
+      b = cmulc(b, w);
+    }
+    ve[q] = a;
+    vo[q] = b;
+  }
+  Bfly<16, true>::run(ve);
+  Bfly<16, true>::run(vo);
+  // ve[r], vo[r] = complex samples 2m, 2m+1 with m = lane + 16 r = real samples 4m .. 4m+3
+  float* obase = (EPI == gen::EPI_UPDATE) ? A.ep.psi : A.out;
+  float4* orow = reinterpret_cast<float4*>(obase + row * nx);
+  const float4* pa = reinterpret_cast<const float4*>((EPI == gen::EPI_QUOTIENT ? A.ep.view : A.ep.psi) + row * nx);
+  const float4* pb = reinterpret_cast<const float4*>(A.ep.weights + row * nx);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {  // operands eight float4 at a time (register budget)
+    float4 oa[8], ob[8];
+    if (EPI != gen::EPI_STORE) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) oa[r] = ld_stream4(pa + lane + 16 * (8 * h + r));
+    }
+    if (EPI == gen::EPI_UPDATE) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) ob[r] = ld_stream4(pb + lane + 16 * (8 * h + r));
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int rr = 8 * h + r;
+      float4 val = make_float4(ve[rr].x * A.ep.scale, ve[rr].y * A.ep.scale, vo[rr].x * A.ep.scale, vo[rr].y * A.ep.scale);
+      if (EPI == gen::EPI_QUOTIENT) {
+        val.x = quotient(oa[r].x, val.x); val.y = quotient(oa[r].y, val.y);
+        val.z = quotient(oa[r].z, val.z); val.w = quotient(oa[r].w, val.w);
+      } else if (EPI == gen::EPI_UPDATE) {
+        val.x = rl_update(oa[r].x, val.x, ob[r].x, A.ep.up); val.y = rl_update(oa[r].y, val.y, ob[r].y, A.ep.up);
+        val.z = rl_update(oa[r].z, val.z, ob[r].z, A.ep.up); val.w = rl_update(oa[r].w, val.w, ob[r].w, A.ep.up);
+      }
+      st_stream4(orow + lane + 16 * rr, val);
+    }
+  }
+  __syncwarp();
+}
+
+template <bool WRAPPED>
+static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_fwd_wide(RowArgs A) {
+  LMVN_DYN_SMEM(cplx, sm);
+  const int lane = threadIdx.x % 16;
+  const int group = threadIdx.x / 16;
+  cplx* slab = sm + group * RowWide::SLAB;
+  const long long rows = (long long)A.nz * A.ny;
+  const long long stride = (long long)gridDim.x * RowWide::ROWS;
+  for (long long row = (long long)blockIdx.x * RowWide::ROWS + group; row < rows; row += stride) {
+    if (!WRAPPED && A.prefetch && row + stride < rows) {  // next iteration's row: 4 KB = 32 lines
+      const char* nxt = reinterpret_cast<const char*>(A.src.data + (row + stride) * RowWide::NX);
+      prefetch_l2(nxt + lane * 128);
+      prefetch_l2(nxt + 2048 + lane * 128);
+    }
+    rows_fwd_wide_group<WRAPPED>(A, slab, row, lane);
+  }
+}
+
+template <int EPI>
+static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_inv_wide(RowArgs A) {
+  LMVN_DYN_SMEM(cplx, sm);
+  const int lane = threadIdx.x % 16;
+  const int group = threadIdx.x / 16;
+  cplx* slab = sm + group * RowWide::SLAB;
+  const long long rows = (long long)A.nz * A.ny;
+  const long long stride = (long long)gridDim.x * RowWide::ROWS;
+  for (long long row = (long long)blockIdx.x * RowWide::ROWS + group; row < rows; row += stride) {
+    if (A.prefetch && row + stride < rows) {
+      const long long nr = row + stride;
+      const char* sp = reinterpret_cast<const char*>(A.spec + nr * A.nxp);
+      for (int b = lane * 128; b < A.nxp * int(sizeof(cplx)); b += 16 * 128) prefetch_l2(sp + b);
+      if (EPI != gen::EPI_STORE) {
+        const char* oa = reinterpret_cast<const char*>((EPI == gen::EPI_QUOTIENT ? A.ep.view : A.ep.psi) + nr * RowWide::NX);
+        prefetch_l2(oa + lane * 128);
+        prefetch_l2(oa + 2048 + lane * 128);
+      }
+      if (EPI == gen::EPI_UPDATE) {
+        const char* ob = reinterpret_cast<const char*>(A.ep.weights + nr * RowWide::NX);
+        prefetch_l2(ob + lane * 128);
+        prefetch_l2(ob + 2048 + lane * 128);
+      }
+    }
+    rows_inv_wide_group<EPI>(A, slab, row, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------
 // x and y passes in ONE persistent launch, plane by plane, so that the x<->y
 // intermediate of a plane lives in the 126 MB L2 and never makes an HBM round trip
 // (HBM traffic of the launch: S + C instead of S + 3C).
@@ -868,7 +1133,7 @@ static __global__ void __launch_bounds__(kRowThreads, 2) k_xy(XYArgs A) {
   typedef Row2Cfg<M> CF;
   constexpr int COLS = Cols<NY>::V;
   constexpr int MODE = INVERSE ? SM_INV : SM_FWD;
-  static_assert(kStridedThreads == kRowThreads, "one block shape for both item kinds");
+  static_assert(Threads<NY>::V == kRowThreads, "one block shape for both item kinds");
   LMVN_DYN_SMEM(cplx, sm);  // max(row slabs, [NY][COLS] tile)
   __shared__ unsigned s_ticket;
   __shared__ cplx s_tw[RowTwShared<M>::ENTRIES * 16];

@@ -30,10 +30,12 @@ struct FastTables {
   int num_sms = 148;
   cplx* tw_m = nullptr;
   cplx* tw_nx = nullptr;
+  cplx* tw_h = nullptr;  // nx = 1024: w_{M/2}
   cplx* tw_y[2] = {nullptr, nullptr};
   cplx* tw_z[2] = {nullptr, nullptr};
   ~FastTables() {
     cudaSetDevice(device);
+    if (tw_h) cudaFree(tw_h);
     if (tw_m) cudaFree(tw_m);
     if (tw_nx) cudaFree(tw_nx);
     for (int i = 0; i < 2; ++i) {
@@ -60,6 +62,7 @@ struct FastEngine : ConvEngine, FastOps {
   static const int kSyncRing = 4;
   cplx* d_tw_m = nullptr;
   cplx* d_tw_nx = nullptr;
+  cplx* d_tw_h = nullptr;
   cplx* d_tw_y[2] = {nullptr, nullptr};  // per-stage tables of the y / z passes
   cplx* d_tw_z[2] = {nullptr, nullptr};
 
@@ -107,6 +110,7 @@ struct FastEngine : ConvEngine, FastOps {
           t->num_sms = sms;
         LMVN_TRY(upload_table(&t->tw_m, M, M));
         LMVN_TRY(upload_table(&t->tw_nx, plan->nx, M + 1));
+        if (M == 512) LMVN_TRY(upload_table(&t->tw_h, M / 2, M / 2));
         LMVN_TRY(upload_stage_tables(t->tw_y, plan->ny));
         LMVN_TRY(upload_stage_tables(t->tw_z, plan->nz));
         plan->fast_tables = t;
@@ -114,7 +118,7 @@ struct FastEngine : ConvEngine, FastOps {
       tables = std::static_pointer_cast<FastTables>(plan->fast_tables);
     }
     num_sms = tables->num_sms;
-    d_tw_m = tables->tw_m; d_tw_nx = tables->tw_nx;
+    d_tw_m = tables->tw_m; d_tw_nx = tables->tw_nx; d_tw_h = tables->tw_h;
     for (int i = 0; i < 2; ++i) { d_tw_y[i] = tables->tw_y[i]; d_tw_z[i] = tables->tw_z[i]; }
     LMVN_TRY(init_xy());
     return 0;
@@ -221,6 +225,40 @@ struct FastEngine : ConvEngine, FastOps {
     }
     return 0;
   }
+  // nx = 1024
+  int launch_rows_fwd_wide(const fast::RowArgs& a, bool wrapped, cudaStream_t s) {
+    const size_t rows = size_t(a.nz) * plan->ny;
+    const dim3 grid(unsigned(std::min<size_t>(ceil_div(rows, fast::RowWide::ROWS), size_t(num_sms) * rows_ctas_per_sm)));
+    const size_t smem = fast::RowWide::SMEM;
+    auto kw = fast::k_rows_fwd_wide<true>;
+    auto kp = fast::k_rows_fwd_wide<false>;
+    LMVN_CUDA_TRY(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    LMVN_CUDA_TRY(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    if (wrapped) {
+      LMVN_LAUNCH(kw, grid, dim3(fast::kRowThreads), smem, s, a);
+    } else {
+      LMVN_LAUNCH(kp, grid, dim3(fast::kRowThreads), smem, s, a);
+    }
+    return 0;
+  }
+  int launch_rows_inv_wide(const fast::RowArgs& a, cudaStream_t s) {
+    const size_t rows = size_t(a.nz) * plan->ny;
+    const dim3 grid(unsigned(std::min<size_t>(ceil_div(rows, fast::RowWide::ROWS), size_t(num_sms) * rows_ctas_per_sm)));
+    const size_t smem = fast::RowWide::SMEM;
+    auto k0 = fast::k_rows_inv_wide<gen::EPI_STORE>;
+    auto k1 = fast::k_rows_inv_wide<gen::EPI_QUOTIENT>;
+    auto k2 = fast::k_rows_inv_wide<gen::EPI_UPDATE>;
+    LMVN_CUDA_TRY(cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    LMVN_CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    LMVN_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    switch (a.ep.mode) {
+      case gen::EPI_QUOTIENT: LMVN_LAUNCH(k1, grid, dim3(fast::kRowThreads), smem, s, a); break;
+      case gen::EPI_UPDATE: LMVN_LAUNCH(k2, grid, dim3(fast::kRowThreads), smem, s, a); break;
+      default: LMVN_LAUNCH(k0, grid, dim3(fast::kRowThreads), smem, s, a); break;
+    }
+    return 0;
+  }
+
   template <int MM>
   int launch_rows_inv2(const fast::RowArgs& a, cudaStream_t s) {
     typedef fast::Row2Cfg<MM> CF;
@@ -253,12 +291,14 @@ struct FastEngine : ConvEngine, FastOps {
     a.tw_m = d_tw_m; a.tw_nx = d_tw_nx;
     a.prefetch = rows_prefetch;
     a.z0 = wrap_z0; a.nz_wrap = wrap_nz > 0 ? wrap_nz : plan->nz;
+    a.tw_h = d_tw_h;
     const bool w = src.wrapped != 0;
     switch (M) {
       case 32: LMVN_TRY(launch_rows_fwd2<32>(a, w, s)); break;
       case 64: LMVN_TRY(launch_rows_fwd2<64>(a, w, s)); break;
       case 128: LMVN_TRY(launch_rows_fwd2<128>(a, w, s)); break;
       case 256: LMVN_TRY(launch_rows_fwd2<256>(a, w, s)); break;
+      case 512: LMVN_TRY(launch_rows_fwd_wide(a, w, s)); break;
       default: set_last_error("fused path: unsupported nx"); return -1;
     }
     LMVN_CUDA_TRY(cudaGetLastError());
@@ -281,11 +321,13 @@ struct FastEngine : ConvEngine, FastOps {
     a.nz = nzs; a.ny = plan->ny; a.nxp = nxp;
     a.tw_m = d_tw_m; a.tw_nx = d_tw_nx;
     a.prefetch = rows_prefetch;
+    a.tw_h = d_tw_h;
     switch (M) {
       case 32: LMVN_TRY(launch_rows_inv2<32>(a, s)); break;
       case 64: LMVN_TRY(launch_rows_inv2<64>(a, s)); break;
       case 128: LMVN_TRY(launch_rows_inv2<128>(a, s)); break;
       case 256: LMVN_TRY(launch_rows_inv2<256>(a, s)); break;
+      case 512: LMVN_TRY(launch_rows_inv_wide(a, s)); break;
       default: set_last_error("fused path: unsupported nx"); return -1;
     }
     LMVN_CUDA_TRY(cudaGetLastError());
@@ -303,7 +345,7 @@ struct FastEngine : ConvEngine, FastOps {
     if (smem > 48 * 1024) {  // per device, cheap: set every time
       LMVN_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     }
-    LMVN_LAUNCH(kfn, grid, dim3(fast::kStridedThreads), smem, s, a);
+    LMVN_LAUNCH(kfn, grid, dim3(fast::Threads<N>::V), smem, s, a);
     return 0;
   }
   template <int N>
@@ -435,7 +477,7 @@ struct FastEngine : ConvEngine, FastOps {
 };
 
 bool axis_ok(int n) { return n == 16 || n == 32 || n == 64 || n == 128 || n == 256 || n == 512 || n == 1024; }
-bool nx_ok(int nx) { return nx == 64 || nx == 128 || nx == 256 || nx == 512; }
+bool nx_ok(int nx) { return nx == 64 || nx == 128 || nx == 256 || nx == 512 || nx == 1024; }
 
 }  // namespace
 

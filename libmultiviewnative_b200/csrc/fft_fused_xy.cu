@@ -51,13 +51,18 @@ struct XY {
 
 }  // namespace
 
+#ifdef LMVN_STRIDED_HALF
+#define LMVN_XY_512(MM, EXPR)
+#else
+#define LMVN_XY_512(MM, EXPR) case 512: { typedef XY<MM, 512> K; EXPR; } break;
+#endif
 #define LMVN_XY_DISPATCH(EXPR)                                     \
   switch (M) {                                                     \
     case 32:                                                       \
       switch (ny) {                                                \
         case 128: { typedef XY<32, 128> K; EXPR; } break;          \
         case 256: { typedef XY<32, 256> K; EXPR; } break;          \
-        case 512: { typedef XY<32, 512> K; EXPR; } break;          \
+        LMVN_XY_512(32, EXPR)                                          \
         default: break;                                            \
       }                                                            \
       break;                                                       \
@@ -65,7 +70,7 @@ struct XY {
       switch (ny) {                                                \
         case 128: { typedef XY<64, 128> K; EXPR; } break;          \
         case 256: { typedef XY<64, 256> K; EXPR; } break;          \
-        case 512: { typedef XY<64, 512> K; EXPR; } break;          \
+        LMVN_XY_512(64, EXPR)                                          \
         default: break;                                            \
       }                                                            \
       break;                                                       \
@@ -73,7 +78,7 @@ struct XY {
       switch (ny) {                                                \
         case 128: { typedef XY<128, 128> K; EXPR; } break;         \
         case 256: { typedef XY<128, 256> K; EXPR; } break;         \
-        case 512: { typedef XY<128, 512> K; EXPR; } break;         \
+        LMVN_XY_512(128, EXPR)                                         \
         default: break;                                            \
       }                                                            \
       break;                                                       \

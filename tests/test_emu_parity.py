@@ -109,7 +109,7 @@ def LF(L):
 @pytest.mark.parametrize("dims,kdims", [
     ((16, 16, 64), (5, 5, 5)), ((32, 64, 128), (7, 4, 3)), ((64, 16, 256), (3, 3, 9)), ((16, 128, 64), (5, 5, 5)),
     ((256, 16, 64), (5, 5, 5)), ((16, 512, 64), (3, 9, 3)), ((512, 16, 64), (9, 3, 3)), ((16, 16, 64), (16, 16, 64)),
-    ((16, 16, 512), (3, 3, 11)), ((16, 1024, 64), (3, 9, 3)), ((1024, 16, 64), (9, 3, 3)),
+    ((16, 16, 512), (3, 3, 11)), ((16, 1024, 64), (3, 9, 3)), ((1024, 16, 64), (9, 3, 3)), ((16, 16, 1024), (3, 5, 13)),
 ])
 def test_fused_conv_random(LF, dims, kdims):
     pc.case_conv_random_vs_oracle(LF, dims, kdims)
@@ -132,6 +132,10 @@ def test_fused_strategy_is_selected_and_rejected(L, LF):
 @pytest.mark.parametrize("lam", [0.0, 0.006])
 def test_fused_deconvolve_vs_oracle(LF, lam):
     pc.case_deconvolve_vs_oracle(LF, (16, 32, 64), 3, 7, lam, iters_list=(1, 3), n_sources=10)
+
+
+def test_fused_deconvolve_nx1024(LF):
+    pc.case_deconvolve_vs_oracle(LF, (16, 16, 1024), 2, 5, 0.006, iters_list=(1,), n_sources=6)
 
 
 def test_fused_deconvolve_nx128(LF):

@@ -70,6 +70,7 @@ def test_conv_identity_asymmetric_image(LS):
     ((64, 64, 64), (15, 15, 15)), ((128, 64, 64), (21, 21, 21)), ((128, 128, 64), (31, 31, 31)),
     ((64, 64, 64), (63, 63, 63)), ((12, 10, 14), (4, 3, 2)), ((8, 8, 8), (8, 8, 8)), ((50, 36, 30), (7, 9, 5)),
     ((256, 128, 128), (41, 41, 41)), ((64, 128, 512), (9, 5, 21)), ((64, 1024, 64), (3, 31, 3)), ((1024, 64, 64), (31, 3, 3)),
+    ((32, 64, 1024), (5, 9, 41)),
 ])
 def test_conv_random_vs_oracle(LS, dims, kdims):
     pc.case_conv_random_vs_oracle(LS, dims, kdims)
@@ -100,6 +101,10 @@ def test_config1_deconvolve_vs_oracle(LS, lam):
 
 def test_deconvolve_non_power_of_two(L):
     pc.case_deconvolve_vs_oracle(L, (50, 36, 30), 2, 9, 0.006, iters_list=(1, 10), n_sources=20)
+
+
+def test_deconvolve_nx1024(L):
+    pc.case_deconvolve_vs_oracle(L, (32, 32, 1024), 2, 21, 0.006, iters_list=(1, 10), n_sources=50)
 
 
 def test_deconvolve_config4_block_shape(LS):
