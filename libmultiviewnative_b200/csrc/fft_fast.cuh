@@ -997,20 +997,21 @@ __device__ __forceinline__ void rows_inv_wide_group(const RowArgs& A, cplx* slab
   float4* orow = reinterpret_cast<float4*>(obase + row * nx);
   const float4* pa = reinterpret_cast<const float4*>((EPI == gen::EPI_QUOTIENT ? A.ep.view : A.ep.psi) + row * nx);
   const float4* pb = reinterpret_cast<const float4*>(A.ep.weights + row * nx);
+  constexpr int CH = (EPI == gen::EPI_UPDATE) ? 4 : 8;  // operands CH float4 at a time (register budget)
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {  // operands eight float4 at a time (register budget)
-    float4 oa[8], ob[8];
+  for (int h = 0; h < 16 / CH; ++h) {
+    float4 oa[CH], ob[CH];
     if (EPI != gen::EPI_STORE) {
 #pragma unroll
-      for (int r = 0; r < 8; ++r) oa[r] = ld_stream4(pa + lane + 16 * (8 * h + r));
+      for (int r = 0; r < CH; ++r) oa[r] = ld_stream4(pa + lane + 16 * (CH * h + r));
     }
     if (EPI == gen::EPI_UPDATE) {
 #pragma unroll
-      for (int r = 0; r < 8; ++r) ob[r] = ld_stream4(pb + lane + 16 * (8 * h + r));
+      for (int r = 0; r < CH; ++r) ob[r] = ld_stream4(pb + lane + 16 * (CH * h + r));
     }
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int rr = 8 * h + r;
+    for (int r = 0; r < CH; ++r) {
+      const int rr = CH * h + r;
       float4 val = make_float4(ve[rr].x * A.ep.scale, ve[rr].y * A.ep.scale, vo[rr].x * A.ep.scale, vo[rr].y * A.ep.scale);
       if (EPI == gen::EPI_QUOTIENT) {
         val.x = quotient(oa[r].x, val.x); val.y = quotient(oa[r].y, val.y);
