@@ -57,6 +57,15 @@ LMVN_EXPORT int lmvn_set_default_strategy(int strategy);
 LMVN_EXPORT void lmvn_release_cached_memory(void);
 
 LMVN_EXPORT int lmvn_plan_create(lmvn_plan** out, const int* dims_zyx, int num_views, int device);
+/* zero_padd mode of the reference's GPU path (ref: inc/padd_utils.h:102-249, src/gpu_deconvolve_methods.cuh:366-449):
+ * the plan works on image + kernel - 1 extents (rounded up to a fast-path extent when that is cheap), the caller's
+ * stacks keep the image extents and sit at offset (kernel - 1) / 2; uploads zero-fill, get_psi crops.  Linear instead of
+ * circular convolution at the image borders.  lmvn_set_padding / env LMVN_PAD=zero switch the one-shot entry points
+ * (inplace_gpu_deconvolve, inplace_gpu_convolution) to it; the default is the CPU path's circular geometry. */
+enum lmvn_padding { LMVN_PAD_NONE = 0, LMVN_PAD_ZERO = 1 };
+LMVN_EXPORT int lmvn_set_padding(int mode);
+LMVN_EXPORT int lmvn_plan_create_zero_padded(lmvn_plan** out, const int* image_dims_zyx, const int* max_kernel_dims_zyx,
+                                             int num_views, int device);
 LMVN_EXPORT void lmvn_plan_destroy(lmvn_plan* plan);
 LMVN_EXPORT int lmvn_plan_get_info(const lmvn_plan* plan, lmvn_plan_info* info);
 

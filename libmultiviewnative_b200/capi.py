@@ -69,7 +69,7 @@ REFERENCE_SYMBOLS = [
 ]
 EXTENSION_SYMBOLS = [
     "lmvn_last_error", "lmvn_clear_error", "lmvn_version", "lmvn_set_default_strategy", "lmvn_release_cached_memory",
-    "lmvn_plan_create",
+    "lmvn_plan_create", "lmvn_set_padding", "lmvn_plan_create_zero_padded",
     "lmvn_plan_destroy", "lmvn_plan_get_info", "lmvn_plan_set_view", "lmvn_plan_set_psi", "lmvn_plan_get_psi",
     "lmvn_plan_iterate", "lmvn_plan_convolve", "lmvn_plan_profile", "lmvn_plan_synchronize", "lmvn_debug_rfftn", "lmvn_debug_irfftn",
     "lmvn_dist_create", "lmvn_dist_destroy", "lmvn_dist_get_info", "lmvn_dist_export_handle", "lmvn_dist_connect_ipc",
@@ -138,6 +138,7 @@ class Library:
         L.getNameDeviceCUDA.restype = None
         L.getMemDeviceCUDA.restype = C.c_longlong
         L.lmvn_plan_create.argtypes = [C.POINTER(C.c_void_p), c_int_p, C.c_int, C.c_int]
+        L.lmvn_plan_create_zero_padded.argtypes = [C.POINTER(C.c_void_p), c_int_p, c_int_p, C.c_int, C.c_int]
         L.lmvn_plan_destroy.argtypes = [C.c_void_p]
         L.lmvn_plan_destroy.restype = None
         L.lmvn_plan_get_info.argtypes = [C.c_void_p, C.POINTER(PlanInfo)]
@@ -169,6 +170,10 @@ class Library:
         L.lmvn_dist_buffer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_ulonglong)]
         L.lmvn_debug_rfftn.argtypes = [c_float_p, c_int_p, c_float_p, C.c_int]
         L.lmvn_debug_irfftn.argtypes = [c_float_p, c_int_p, c_float_p, C.c_int]
+
+    def set_padding(self, mode: int):
+        """0: circular at the image extents (the CPU path, default); 1: zero_padd (the reference's GPU geometry)."""
+        self._check(self.lib.lmvn_set_padding(int(mode)), "lmvn_set_padding")
 
     def release_cached_memory(self):
         self.lib.lmvn_release_cached_memory()

@@ -62,6 +62,60 @@ extern "C" int lmvn_plan_create(lmvn_plan** out, const int* dims_zyx, int num_vi
   *out = p;
   return 0;
 }
+namespace {
+// smallest extent >= n that the power-of-two fast path takes on this axis (0: none)
+int fast_extent(int n, bool x_axis) {
+  for (int e = x_axis ? 64 : 16; e <= 1024; e *= 2)
+    if (e >= n) return e;
+  return 0;
+}
+int pad_mode_from_env() {
+  const char* e = getenv("LMVN_PAD");
+  return (e && (e[0] == 'z' || e[0] == 'Z')) ? LMVN_PAD_ZERO : LMVN_PAD_NONE;
+}
+int g_pad_mode = -1;
+}  // namespace
+
+extern "C" int lmvn_set_padding(int mode) {
+  if (mode != LMVN_PAD_NONE && mode != LMVN_PAD_ZERO) {
+    set_last_error("unknown padding mode %d", mode);
+    return -1;
+  }
+  g_pad_mode = mode;
+  return 0;
+}
+static int current_pad_mode() { return g_pad_mode >= 0 ? g_pad_mode : pad_mode_from_env(); }
+
+extern "C" int lmvn_plan_create_zero_padded(lmvn_plan** out, const int* image_dims, const int* max_kernel_dims,
+                                            int num_views, int device) {
+  if (!out || !image_dims || !max_kernel_dims) {
+    set_last_error("null argument");
+    return -1;
+  }
+  *out = nullptr;
+  int padded[3], off[3], fast[3];
+  bool all_fast = true;
+  for (int a = 0; a < 3; ++a) {
+    if (image_dims[a] <= 0 || max_kernel_dims[a] <= 0) { set_last_error("invalid extents"); return -1; }
+    padded[a] = image_dims[a] + max_kernel_dims[a] - 1;  // ref: inc/padd_utils.h:133-134
+    off[a] = (max_kernel_dims[a] - 1) / 2;               // ref: inc/padd_utils.h:136-137
+    fast[a] = fast_extent(padded[a], a == 2);
+    all_fast = all_fast && fast[a] > 0;
+  }
+  // any extent >= image + kernel - 1 gives the same voxels inside the image; prefer one the fast path takes
+  // unless that more than doubles the volume
+  if (all_fast && double(fast[0]) * fast[1] * fast[2] <= 2.0 * double(padded[0]) * padded[1] * padded[2])
+    for (int a = 0; a < 3; ++a) padded[a] = fast[a];
+  lmvn_plan* p = new (std::nothrow) lmvn_plan();
+  if (!p) { set_last_error("out of host memory"); return -1; }
+  if (p->d.init(padded, num_views, device, 0) != 0 || p->d.set_logical(image_dims, off) != 0) {
+    delete p;
+    return -1;
+  }
+  *out = p;
+  return 0;
+}
+
 extern "C" void lmvn_plan_destroy(lmvn_plan* plan) { delete plan; }
 
 extern "C" int lmvn_plan_get_info(const lmvn_plan* plan, lmvn_plan_info* info) {
@@ -164,7 +218,18 @@ int gpu_deconvolve_impl(float* psi, const workspace& in, int device) {
   }
   if (in.num_iterations_ <= 0) return 0;  // psi unchanged (ref: tests/test_gpu_deconvolve_impl.cu:333-377)
   PlanGuard g;
-  LMVN_TRY(lmvn_plan_create(&g.p, dims, in.num_views_, device));
+  if (current_pad_mode() == LMVN_PAD_ZERO) {
+    // the reference's GPU geometry: extents = image + largest kernel - 1 (ref: src/gpu_deconvolve_methods.cuh:366-379)
+    int kmax[3] = {1, 1, 1};
+    for (int v = 0; v < in.num_views_; ++v)
+      for (int a = 0; a < 3; ++a) {
+        if (in.data_[v].kernel1_dims_) kmax[a] = std::max(kmax[a], in.data_[v].kernel1_dims_[a]);
+        if (in.data_[v].kernel2_dims_) kmax[a] = std::max(kmax[a], in.data_[v].kernel2_dims_[a]);
+      }
+    LMVN_TRY(lmvn_plan_create_zero_padded(&g.p, dims, kmax, in.num_views_, device));
+  } else {
+    LMVN_TRY(lmvn_plan_create(&g.p, dims, in.num_views_, device));
+  }
   for (int v = 0; v < in.num_views_; ++v) {
     const view_data& vd = in.data_[v];
     LMVN_TRY(g.p->d.set_view(v, vd.image_, vd.weights_, vd.kernel1_, vd.kernel1_dims_, vd.kernel2_, vd.kernel2_dims_));
@@ -182,7 +247,11 @@ int gpu_convolution_impl(float* im, const int* imDim, const float* kernel, const
     return -1;
   }
   PlanGuard g;
-  LMVN_TRY(lmvn_plan_create(&g.p, imDim, 1, device));
+  if (current_pad_mode() == LMVN_PAD_ZERO) {
+    LMVN_TRY(lmvn_plan_create_zero_padded(&g.p, imDim, kernelDim, 1, device));
+  } else {
+    LMVN_TRY(lmvn_plan_create(&g.p, imDim, 1, device));
+  }
   Deconv& d = g.p->d;
   // a one-view handle: only kernel1's spectrum is used, the image doubles as the
   // view/weights upload (never read by convolve_psi)

@@ -412,6 +412,52 @@ static int check_kernel_dims(const int* kd, const int* dims, const char* what) {
   return 0;
 }
 
+int Deconv::set_logical(const int* image_dims, const int* off) {
+  for (int a = 0; a < 3; ++a) {
+    if (image_dims[a] <= 0 || off[a] < 0 || image_dims[a] + off[a] > dims[a]) {
+      set_last_error("zero-padded plan: image extent %d at offset %d does not fit the padded extent %d (axis %d)",
+                     image_dims[a], off[a], dims[a], a);
+      return -1;
+    }
+    logical[a] = image_dims[a];
+    offset[a] = off[a];
+  }
+  padded = (logical[0] != dims[0] || logical[1] != dims[1] || logical[2] != dims[2]);
+  return 0;
+}
+
+// host stack (logical extents) -> device volume (plan extents), zero filled around it
+int Deconv::upload_stack(float* dst, const float* src_h) {
+  const size_t n = engine->plan->voxels();
+  if (!padded) {
+    LMVN_CUDA_TRY(cudaMemcpyAsync(dst, src_h, n * sizeof(float), cudaMemcpyHostToDevice, stream));
+    return 0;
+  }
+  LMVN_CUDA_TRY(cudaMemsetAsync(dst, 0, n * sizeof(float), stream));
+  // one 2-D copy per plane: rows of logical[2] floats into rows of dims[2] floats
+  for (int z = 0; z < logical[0]; ++z) {
+    float* d = dst + (size_t(z + offset[0]) * dims[1] + offset[1]) * dims[2] + offset[2];
+    const float* s = src_h + size_t(z) * logical[1] * logical[2];
+    LMVN_CUDA_TRY(cudaMemcpy2DAsync(d, size_t(dims[2]) * sizeof(float), s, size_t(logical[2]) * sizeof(float),
+                                    size_t(logical[2]) * sizeof(float), size_t(logical[1]), cudaMemcpyHostToDevice, stream));
+  }
+  return 0;
+}
+
+int Deconv::download_stack(float* dst_h, const float* src) {
+  if (!padded) {
+    LMVN_CUDA_TRY(cudaMemcpyAsync(dst_h, src, engine->plan->voxels() * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    return 0;
+  }
+  for (int z = 0; z < logical[0]; ++z) {
+    const float* s = src + (size_t(z + offset[0]) * dims[1] + offset[1]) * dims[2] + offset[2];
+    float* d = dst_h + size_t(z) * logical[1] * logical[2];
+    LMVN_CUDA_TRY(cudaMemcpy2DAsync(d, size_t(logical[2]) * sizeof(float), s, size_t(dims[2]) * sizeof(float),
+                                    size_t(logical[2]) * sizeof(float), size_t(logical[1]), cudaMemcpyDeviceToHost, stream));
+  }
+  return 0;
+}
+
 int Deconv::set_view(int v, const float* image_h, const float* weights_h, const float* k1, const int* k1d,
                      const float* k2, const int* k2d) {
   if (v < 0 || v >= num_views) {
@@ -425,9 +471,8 @@ int Deconv::set_view(int v, const float* image_h, const float* weights_h, const 
   LMVN_TRY(check_kernel_dims(k1d, dims, "kernel1"));
   LMVN_TRY(check_kernel_dims(k2d, dims, "kernel2"));
   LMVN_CUDA_TRY(cudaSetDevice(device));
-  const size_t S = engine->plan->voxels() * sizeof(float);
-  LMVN_CUDA_TRY(cudaMemcpyAsync(image[v], image_h, S, cudaMemcpyHostToDevice, stream));
-  LMVN_CUDA_TRY(cudaMemcpyAsync(weights[v], weights_h, S, cudaMemcpyHostToDevice, stream));
+  LMVN_TRY(upload_stack(image[v], image_h));
+  LMVN_TRY(upload_stack(weights[v], weights_h));
   const float* ks[2] = {k1, k2};
   const int* kds[2] = {k1d, k2d};
   cplx* dst[2] = {khat1[v], khat2[v]};
@@ -452,7 +497,7 @@ int Deconv::set_psi(const float* psi_h) {
     return -1;
   }
   LMVN_CUDA_TRY(cudaSetDevice(device));
-  LMVN_CUDA_TRY(cudaMemcpyAsync(psi, psi_h, engine->plan->voxels() * sizeof(float), cudaMemcpyHostToDevice, stream));
+  LMVN_TRY(upload_stack(psi, psi_h));
   psi_set = true;
   return 0;
 }
@@ -463,7 +508,7 @@ int Deconv::get_psi(float* psi_h) {
     return -1;
   }
   LMVN_CUDA_TRY(cudaSetDevice(device));
-  LMVN_CUDA_TRY(cudaMemcpyAsync(psi_h, psi, engine->plan->voxels() * sizeof(float), cudaMemcpyDeviceToHost, stream));
+  LMVN_TRY(download_stack(psi_h, psi));
   LMVN_CUDA_TRY(cudaStreamSynchronize(stream));
   return 0;
 }

@@ -124,6 +124,16 @@ struct Deconv {
   std::vector<char> view_set;
   bool psi_set = false;
 
+  // zero_padd mode (ref: inc/padd_utils.h:102-249, src/gpu_deconvolve_methods.cuh:366-449): the plan works on
+  // `dims` = image + kernel - 1 (rounded up to a fast-path extent), the caller's stacks have `logical` extents
+  // and sit at `offset` = (kernel - 1) / 2 inside it; uploads zero-fill, downloads crop.
+  bool padded = false;
+  int logical[3] = {0, 0, 0};
+  int offset[3] = {0, 0, 0};
+  int set_logical(const int* image_dims, const int* off);
+  int upload_stack(float* dst, const float* src_h);
+  int download_stack(float* dst_h, const float* src);
+
   ~Deconv();
   int init(const int* dims_zyx, int nviews, int dev, int strategy);
   int set_view(int v, const float* image_h, const float* weights_h, const float* k1, const int* k1d,

@@ -215,3 +215,56 @@ def case_legacy_iterate(L):
     im = inp.copy()
     L.convolution3DfftCUDAInPlace(im, k1)
     assert rel_l2(im, orc.inplace_cpu_convolution(inp, k1)) <= 1e-5
+
+
+# ---- zero_padd mode (ref: inc/padd_utils.h:102-249; the reference's GPU geometry) ----------------
+def _zero_pad(a, kmax):
+    ext = [a.shape[i] + kmax[i] - 1 for i in range(3)]
+    off = [(kmax[i] - 1) // 2 for i in range(3)]
+    out = np.zeros(ext, dtype=F32)
+    out[off[0]:off[0] + a.shape[0], off[1]:off[1] + a.shape[1], off[2]:off[2] + a.shape[2]] = a
+    return out, off
+
+
+def _crop(a, off, shape):
+    return np.ascontiguousarray(a[off[0]:off[0] + shape[0], off[1]:off[1] + shape[1], off[2]:off[2] + shape[2]])
+
+
+def case_zero_padd_convolution(L, dims, kdims):
+    """zero mode == circular convolution of the explicitly zero-padded image (image + kernel - 1, offset
+    (kernel - 1) / 2), cropped: no wrap-around inside the image."""
+    rng = np.random.default_rng(21)
+    img = (rng.random(dims, dtype=F32) + 1).astype(F32)
+    k = rng.random(kdims, dtype=F32)
+    k /= k.sum()
+    padded, off = _zero_pad(img, kdims)
+    exp = _crop(orc.inplace_cpu_convolution(padded, k), off, dims)
+    L.set_padding(1)
+    try:
+        got = img.copy()
+        L.inplace_gpu_convolution(got, k)
+    finally:
+        L.set_padding(0)
+    assert rel_l2(got, exp) < 1e-5
+    circ = img.copy()
+    L.inplace_gpu_convolution(circ, k)
+    assert rel_l2(circ, exp) > 1e-3  # the circular default differs at the borders
+
+
+def case_zero_padd_deconvolve(L, dims, ksize, lam=0.006, iters=2):
+    d = make_views(dims, num_views=2, kernel_size=ksize, n_sources=8, workers=1)
+    kmax = [max(k.shape[a] for k in d["kernels1"] + d["kernels2"]) for a in range(3)]
+    pv, pw = [], []
+    for v, w in zip(d["views"], d["weights"]):
+        a, off = _zero_pad(v, kmax)
+        pv.append(a)
+        pw.append(_zero_pad(w, kmax)[0])
+    ppsi, off = _zero_pad(d["psi0"], kmax)
+    exp = _crop(orc.inplace_cpu_deconvolve(ppsi, pv, d["kernels1"], d["kernels2"], pw, iters, lam, 1e-4), off, dims)
+    L.set_padding(1)
+    try:
+        got = d["psi0"].copy()
+        L.inplace_gpu_deconvolve(got, d["views"], d["kernels1"], d["kernels2"], d["weights"], iters, lam, 1e-4)
+    finally:
+        L.set_padding(0)
+    assert max_rel(got, exp) < PER_VOXEL_TOL_1_ITER

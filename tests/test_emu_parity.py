@@ -48,6 +48,15 @@ def test_conv_rejects_oversized_kernel(L):
     pc.case_conv_rejects_oversized_kernel(L)
 
 
+@pytest.mark.parametrize("dims,kdims", [((12, 10, 14), (4, 3, 2)), ((20, 24, 50), (5, 7, 9))])
+def test_zero_padd_convolution(L, dims, kdims):
+    pc.case_zero_padd_convolution(L, dims, kdims)
+
+
+def test_zero_padd_deconvolve(L):
+    pc.case_zero_padd_deconvolve(L, (10, 12, 14), 5)
+
+
 def test_pointwise(L):
     pc.case_pointwise(L)
 

@@ -80,6 +80,15 @@ def test_conv_rejects_oversized_kernel(L):
     pc.case_conv_rejects_oversized_kernel(L)
 
 
+@pytest.mark.parametrize("dims,kdims", [((12, 10, 14), (4, 3, 2)), ((100, 120, 200), (21, 21, 21)), ((50, 36, 30), (7, 9, 5))])
+def test_zero_padd_convolution(L, dims, kdims):
+    pc.case_zero_padd_convolution(L, dims, kdims)
+
+
+def test_zero_padd_deconvolve(L):
+    pc.case_zero_padd_deconvolve(L, (100, 100, 100), 21)
+
+
 def test_pointwise(L):
     pc.case_pointwise(L)
 
