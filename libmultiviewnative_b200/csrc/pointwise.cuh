@@ -20,25 +20,48 @@ __device__ __forceinline__ float quotient(float view, float blurred) {
   return __fmul_rn(view, __frcp_rn(blurred));
 }
 
+// Branch-free building blocks.  The update runs once per voxel inside the last transform pass; with the
+// IEEE-rounded division / square root (range checks + slow paths: FCHK, BSSY/BSYNC, ~120 instructions per
+// voxel) that pass was bound by instruction issue, not by memory.  MUFU approximations followed by one
+// Newton step stay within ~1 ulp, which is 3 orders of magnitude inside the parity tolerance.
+__device__ __forceinline__ float rcp_nr(float d) {  // 1/d, d finite and not tiny
+#ifdef LMVN_EMU
+  return 1.0f / d;
+#else
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return __fmaf_rn(__fmaf_rn(-d, r, 1.0f), r, r);
+#endif
+}
+__device__ __forceinline__ float sqrt_nr(float x) {  // sqrt(x), x >= 1 (or NaN/Inf, which propagate as NaN)
+#ifdef LMVN_EMU
+  return std::sqrt(x);
+#else
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  const float s = __fmul_rn(x, r);
+  return __fmaf_rn(__fmul_rn(__fmaf_rn(-s, s, x), 0.5f), r, s);
+#endif
+}
+
 // Tikhonov step in the cancellation-free form
 //   (1/l)(sqrt(1+2 l v) - 1) == 2 v / (1 + sqrt(1 + 2 l v)),
 // which float32 evaluates to ~1e-7 of the reference's double evaluation (the
 // textbook form loses up to 6.6e-3 relative for small v in float32).
 __device__ __forceinline__ float tikhonov(float v, const UpdateParams& p) {
-  float s = __fsqrt_rn(__fmaf_rn(p.two_lambda, v, 1.0f));
-  return __fdiv_rn(__fmul_rn(p.coef, v), __fadd_rn(1.0f, s));
+  const float s = sqrt_nr(__fmaf_rn(p.two_lambda, v, 1.0f));
+  return __fmul_rn(__fmul_rn(p.coef, v), rcp_nr(__fadd_rn(1.0f, s)));
 }
 
 __device__ __forceinline__ float rl_update(float psi, float integral, float weight,
                                            const UpdateParams& p) {
   const float last = psi;
   float v = __fmul_rn(last, integral);
-  if (v > 0.f) {
-    if (p.regularized) v = tikhonov(v, p);
-  } else {
-    v = p.min_value;  // also catches NaN
-  }
-  float next = (isnan(v) || isinf(v)) ? p.min_value : fmaxf(v, p.min_value);
+  // selects instead of branches: !(v > 0) also catches NaN (ref: inc/cpu_kernels.h:36-38, 66-79)
+  const float t = p.regularized ? tikhonov(v, p) : v;
+  v = (v > 0.f) ? t : p.min_value;
+  // NaN or Inf -> minValue, else max(v, minValue) (ref: inc/cpu_kernels.h:40-47)
+  const float next = (fabsf(v) <= 3.402823466e+38f) ? fmaxf(v, p.min_value) : p.min_value;
   // two roundings like the CPU code, no FMA contraction
   return __fadd_rn(__fmul_rn(weight, __fadd_rn(next, -last)), last);
 }
