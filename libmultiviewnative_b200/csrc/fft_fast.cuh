@@ -293,12 +293,15 @@ __device__ __forceinline__ void strided_stage(cplx* __restrict__ sm, cplx* __res
 #pragma unroll
       for (int r = 0; r < R; ++r) v[r] = p[r * M * COLS];
     } else {
-      unsigned off = unsigned(row0 * rs);
-      const unsigned step = unsigned(M * rs);
+      // one 64-bit pointer bumped by a uniform 64-bit step: two integer instructions per access
+      // (index arithmetic in 32 bits costs five: zero extension, carry chain, scaled address)
+      const cplx* gp = g + (long long)row0 * rs;
+      const int step = M * rs;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        v[r] = ld_stream(g + off);
-        off += step;
+        v[r] = ld_stream(gp);
+        gp += step;
+        LMVN_KEEP_PTR(gp);
       }
     }
     cplx t[R];  // fetched before the butterfly so that their latency hides behind it
@@ -328,12 +331,13 @@ __device__ __forceinline__ void strided_stage(cplx* __restrict__ sm, cplx* __res
         st_stream(sc->base[row >> sc->shift] + sc_tile + (long long)(row & mask) * sc->row_stride, v[q]);
       }
     } else {
-      unsigned off = unsigned(row0 * rs);
-      const unsigned step = unsigned(M * rs);
+      cplx* gp = g + (long long)row0 * rs;
+      const int step = M * rs;
 #pragma unroll
       for (int q = 0; q < R; ++q) {
-        st_stream(g + off, DST == W_GLOBAL_SCALED ? cscale(v[q], scale) : v[q]);
-        off += step;
+        st_stream(gp, DST == W_GLOBAL_SCALED ? cscale(v[q], scale) : v[q]);
+        gp += step;
+        LMVN_KEEP_PTR(gp);
       }
     }
   }
@@ -351,11 +355,12 @@ struct Middle {
     const int rg = threadIdx.x / COLS;
 #pragma unroll
     for (int i = 0; i < PT; ++i) {
-      unsigned off = unsigned((rg + i * RG) * R * rs);
+      const cplx* gp = gk + (long long)((rg + i * RG) * R) * rs;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        o.k[i][r] = ld_stream(gk + off);
-        off += unsigned(rs);
+        o.k[i][r] = ld_stream(gp);
+        gp += rs;
+        LMVN_KEEP_PTR(gp);
       }
     }
   }

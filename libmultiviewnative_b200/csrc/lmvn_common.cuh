@@ -73,6 +73,15 @@ __device__ __forceinline__ void st_stream(cplx* p, cplx v) {
 #endif
 }
 
+// Makes the value of a bumped pointer opaque to the optimiser.  Without it nvcc re-derives every address of
+// an unrolled access sequence from the base (five integer instructions per access: zero extension, carry
+// chain, scaled 64-bit add); with it the bump stays ONE IMAD.WIDE per access.
+#if defined(LMVN_EMU) || !defined(__CUDA_ARCH__)
+#define LMVN_KEEP_PTR(p) ((void)0)
+#else
+#define LMVN_KEEP_PTR(p) asm volatile("" : "+l"(p))
+#endif
+
 // L2 prefetch of the 128-byte line holding p (no register, no scoreboard entry)
 __device__ __forceinline__ void prefetch_l2(const void* p) {
 #ifndef LMVN_EMU

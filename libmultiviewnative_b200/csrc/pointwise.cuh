@@ -14,10 +14,19 @@
 
 namespace lmvn {
 
-// view / blurred.  __frcp_rn is the correctly rounded float reciprocal, i.e.
-// float(1.0 / double(x)) up to (rare) double rounding; no fast-math.
+// view / blurred: view * (1 / blurred) like the reference (ref: inc/cpu_kernels.h:19-26, which rounds a
+// double reciprocal to float).
 __device__ __forceinline__ float quotient(float view, float blurred) {
+#ifdef LMVN_EMU
   return __fmul_rn(view, __frcp_rn(blurred));
+#else
+  // MUFU reciprocal + one Newton step (<= 1 ulp), no range-check branches; where the refinement is not
+  // finite (blurred = 0, Inf, NaN or denormal) the raw approximation carries the IEEE special value
+  float r0;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(blurred));
+  const float r = __fmaf_rn(__fmaf_rn(-blurred, r0, 1.0f), r0, r0);
+  return __fmul_rn(view, (fabsf(r) <= 3.402823466e+38f) ? r : r0);
+#endif
 }
 
 // Branch-free building blocks.  The update runs once per voxel inside the last transform pass; with the
