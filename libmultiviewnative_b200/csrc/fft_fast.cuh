@@ -211,11 +211,6 @@ struct StridedArgs {
   int prefetch;           // > 0: every CTA first pulls the tile of block (id + prefetch) into L2
   int prefetch_khat;      // SM_FWD_MUL_INV: pull the CTA's own K^ tile into L2 at kernel entry
   Scatter sc;             // SM_*_SCATTER
-  // The half spectrum has nx/2 + 1 columns: a multiple of the tile width plus the Nyquist column.  Instead
-  // of one nearly empty tile per slow index, the CTAs of the last tile column each take the Nyquist column
-  // of COLS consecutive slow indices (1/129 of the data, gathered with 8-byte accesses).
-  int nyq_gather;
-  unsigned slow;          // number of slow indices (== gridDim.y)
 };
 
 // number of stages and the radix of stage s for N = R1*R2*R3
@@ -450,16 +445,6 @@ static __global__ void __launch_bounds__(Threads<N>::V, StridedBlocks<N, MODE>::
   const int c = threadIdx.x % COLS;
   const int col = blockIdx.x * COLS + c;
   constexpr bool ZMUL = (MODE == SM_FWD_MUL_INV || MODE == SM_FWD_MUL_INV_SCATTER);
-  if (A.nyq_gather && blockIdx.x == gridDim.x - 1) {
-    if (blockIdx.y * COLS >= A.slow) return;  // the whole CTA: fewer Nyquist tiles than slow indices
-    const unsigned s = blockIdx.y * COLS + c;  // this thread's column = Nyquist column of slow index s
-    const int ncol = A.ncols - 1;
-    const long long nb = (long long)s * A.tile_stride + ncol;
-    const long long nsc = A.sc.offset + (long long)s * A.sc.tile_stride + ncol;
-    strided_tile<N, MODE, (ZMUL ? LMVN_ZMUL_UNROLL : LMVN_Y_UNROLL)>(A, smem + c, A.data + nb, A.khat + nb,
-                                                                      s < A.slow, nsc);
-    return;
-  }
   const long long base = (long long)blockIdx.y * A.tile_stride + col;
   constexpr int U = ZMUL ? LMVN_ZMUL_UNROLL : LMVN_Y_UNROLL;
   if (ZMUL && A.prefetch_khat) {
@@ -472,7 +457,7 @@ static __global__ void __launch_bounds__(Threads<N>::V, StridedBlocks<N, MODE>::
   if (A.prefetch > 0) {
     // the block that will take this CTA's slot next: its loads then hit L2 instead of waiting for HBM
     const long long id = (long long)blockIdx.y * gridDim.x + blockIdx.x + A.prefetch;
-    if (id < (long long)gridDim.x * gridDim.y && !(A.nyq_gather && id % gridDim.x == gridDim.x - 1)) {
+    if (id < (long long)gridDim.x * gridDim.y) {
       const long long fb = (id / gridDim.x) * A.tile_stride + (id % gridDim.x) * COLS;
       constexpr int LINES = (COLS + 15) / 16;  // 128-byte lines per tile row
       for (int i = threadIdx.x; i < N * LINES; i += Threads<N>::V) {

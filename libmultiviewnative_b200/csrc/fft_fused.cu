@@ -53,7 +53,6 @@ struct FastEngine : ConvEngine, FastOps {
   int y_fwd_prefetch = 148;  // blocks of look-ahead of the L2 prefetch in the forward y pass
   int khat_prefetch = 0;  // measured: hurts the z pass (plane-strided lines), kept as a knob
   int rows_prefetch = 1;
-  int nyq_gather = 0;  // measured slower on B200 (scattered 8-byte accesses form a tail); knob kept for A/B runs
   // fused x/y launches (fft_fused_xy.cu): ring of sync blocks, each cleared by the launch before it
   bool xy_ok = false;
   int xy_grid = 0, xy_lag = 0, xy_sync_words = 0;
@@ -98,7 +97,6 @@ struct FastEngine : ConvEngine, FastOps {
     if (const char* e = getenv("LMVN_PREFETCH")) y_fwd_prefetch = std::max(0, atoi(e));
     if (const char* e = getenv("LMVN_PREFETCH_KHAT")) khat_prefetch = atoi(e);
     if (const char* e = getenv("LMVN_PREFETCH_ROWS")) rows_prefetch = atoi(e);
-    if (const char* e = getenv("LMVN_NYQ_GATHER")) nyq_gather = atoi(e);
     if (const char* e = getenv("LMVN_ROWS_CTAS")) rows_ctas_per_sm = std::max(1, atoi(e));
     {
       std::lock_guard<std::mutex> lk(plan->fast_mu);
@@ -403,8 +401,6 @@ struct FastEngine : ConvEngine, FastOps {
 #define LMVN_STRIDED_CASE(NN)                                                                   \
   case NN: {                                                                                    \
     const dim3 grid(unsigned(ceil_div(size_t(nxc), size_t(fast::Cols<NN>::V))), slow);          \
-    a.nyq_gather = (nyq_gather && nxc % fast::Cols<NN>::V == 1) ? 1 : 0;                       \
-    a.slow = slow;                                                                              \
     rc = launch_strided_mode<NN>(a, mode, grid, s);                                             \
   } break;
     switch (g.n) {
