@@ -499,10 +499,26 @@ struct RowArgs {
   const cplx* tw_h;      // nx = 1024 only: w_{M/2} table (M/2 entries) of the two half-length sub-transforms
 };
 
+// a + conj(b) and a - conj(b): one packed FFMA2 each on sm_100
+__device__ __forceinline__ cplx cadd_conj(cplx a, cplx b) {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+  return __ffma2_rn(b, make_float2(1.f, -1.f), a);
+#else
+  return make_float2(a.x + b.x, a.y - b.y);
+#endif
+}
+__device__ __forceinline__ cplx csub_conj(cplx a, cplx b) {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+  return __ffma2_rn(b, make_float2(-1.f, 1.f), a);
+#else
+  return make_float2(a.x - b.x, a.y + b.y);
+#endif
+}
+
 // real-transform split for one (k, M-k) pair:  X[k] = E + w^k O,  X[M-k] = conj(E - w^k O)
 __device__ __forceinline__ void r2c_pair(cplx zk, cplx zm, cplx w, cplx& xk, cplx& xm) {
-  const cplx e = cmake(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));   // (Zk + conj Zm)/2
-  const cplx d = cmake(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));   // (Zk - conj Zm)/2
+  const cplx e = cscale(cadd_conj(zk, zm), 0.5f);   // (Zk + conj Zm)/2
+  const cplx d = cscale(csub_conj(zk, zm), 0.5f);   // (Zk - conj Zm)/2
   const cplx o = cmake(d.y, -d.x);                                    // d / i
   const cplx wo = cmul(w, o);
   xk = cadd(e, wo);
@@ -511,8 +527,8 @@ __device__ __forceinline__ void r2c_pair(cplx zk, cplx zm, cplx w, cplx& xk, cpl
 // inverse split (doubled, so that the result is the UNNORMALISED c2r):
 //   Z[k] = E' + i O',  Z[M-k] = conj(E') + i conj(O'),  E' = X[k] + conj X[M-k],  O' = (X[k] - conj X[M-k]) conj(w^k)
 __device__ __forceinline__ void c2r_pair(cplx xk, cplx xm, cplx w, cplx& zk, cplx& zm) {
-  const cplx e = cmake(xk.x + xm.x, xk.y - xm.y);
-  const cplx d = cmake(xk.x - xm.x, xk.y + xm.y);
+  const cplx e = cadd_conj(xk, xm);
+  const cplx d = csub_conj(xk, xm);
   const cplx o = cmulc(d, w);
   zk = cmake(e.x - o.y, e.y + o.x);
   zm = cmake(e.x + o.y, -e.y + o.x);
@@ -736,7 +752,7 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
     float2* orow = reinterpret_cast<float2*>(obase + (row0 + a) * nx);
 #pragma unroll
     for (int r = 0; r < R1; ++r) {
-      float2 val = make_float2(v[a * R1 + r].x * A.ep.scale, v[a * R1 + r].y * A.ep.scale);
+      float2 val = v[a * R1 + r];  // 1/N lives in K^: no scale here (the host rejects ep.scale != 1)
       if (mode == gen::EPI_QUOTIENT) {
         val.x = quotient(oa[a * R1 + r].x, val.x);
         val.y = quotient(oa[a * R1 + r].y, val.y);
@@ -1002,7 +1018,7 @@ __device__ __forceinline__ void rows_inv_wide_group(const RowArgs& A, cplx* slab
 #pragma unroll
     for (int r = 0; r < CH; ++r) {
       const int rr = CH * h + r;
-      float4 val = make_float4(ve[rr].x * A.ep.scale, ve[rr].y * A.ep.scale, vo[rr].x * A.ep.scale, vo[rr].y * A.ep.scale);
+      float4 val = make_float4(ve[rr].x, ve[rr].y, vo[rr].x, vo[rr].y);  // 1/N lives in K^: no scale here
       if (EPI == gen::EPI_QUOTIENT) {
         val.x = quotient(oa[r].x, val.x); val.y = quotient(oa[r].y, val.y);
         val.z = quotient(oa[r].z, val.z); val.w = quotient(oa[r].w, val.w);

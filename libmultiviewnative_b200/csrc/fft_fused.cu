@@ -310,6 +310,10 @@ struct FastEngine : ConvEngine, FastOps {
     std::memset(&a, 0, sizeof(a));
     const size_t voff = size_t(z0) * plan->ny * plan->nx;
     gen::Epilogue ep = ep_in;
+    if (ep.scale != 1.f) {
+      set_last_error("fast path: the 1/N scale lives in the PSF spectra, epilogue scale must be 1");
+      return -1;
+    }
     if (ep.view) ep.view += voff;
     if (ep.psi) ep.psi += voff;
     if (ep.weights) ep.weights += voff;

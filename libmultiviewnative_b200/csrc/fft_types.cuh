@@ -22,8 +22,9 @@ static inline UpdateParams make_update_params(double lambda, float min_value) {
     p.two_lambda = float(2.0 * lambda);
     p.coef = float(2.0 * lambda * double(lambda_inv));
   } else {
+    // plain RL through the same arithmetic: 2 v / (1 + sqrt(1 + 0 v)) == v (see rl_update)
     p.two_lambda = 0.f;
-    p.coef = 0.f;
+    p.coef = 2.f;
   }
   return p;
 }

@@ -20,36 +20,34 @@ __device__ __forceinline__ float quotient(float view, float blurred) {
 #ifdef LMVN_EMU
   return __fmul_rn(view, __frcp_rn(blurred));
 #else
-  // MUFU reciprocal + one Newton step (<= 1 ulp), no range-check branches; where the refinement is not
-  // finite (blurred = 0, Inf, NaN or denormal) the raw approximation carries the IEEE special value
-  float r0;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(blurred));
-  const float r = __fmaf_rn(__fmaf_rn(-blurred, r0, 1.0f), r0, r0);
-  return __fmul_rn(view, (fabsf(r) <= 3.402823466e+38f) ? r : r0);
+  // MUFU reciprocal (<= 1 ulp, IEEE special values for 0 / Inf / NaN): two instructions per voxel instead of
+  // the range-checked IEEE sequence with its slow-path branch
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(blurred));
+  return __fmul_rn(view, r);
 #endif
 }
 
-// Branch-free building blocks.  The update runs once per voxel inside the last transform pass; with the
-// IEEE-rounded division / square root (range checks + slow paths: FCHK, BSSY/BSYNC, ~120 instructions per
-// voxel) that pass was bound by instruction issue, not by memory.  MUFU approximations followed by one
-// Newton step stay within ~1 ulp, which is 3 orders of magnitude inside the parity tolerance.
-__device__ __forceinline__ float rcp_nr(float d) {  // 1/d, d finite and not tiny
+// Building blocks of the update.  It runs once per voxel inside the last transform pass; with IEEE-rounded
+// division and square root (range checks, slow paths: FCHK, BSSY/BSYNC, ~120 instructions per voxel) that
+// pass was bound by instruction issue, not by memory.  The MUFU approximations are within 1-2 ulp, three
+// orders of magnitude inside the parity tolerance (measured: tests/test_gpu_parity.py prints ~1e-6).
+__device__ __forceinline__ float rcp_fast(float d) {
 #ifdef LMVN_EMU
   return 1.0f / d;
 #else
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
-  return __fmaf_rn(__fmaf_rn(-d, r, 1.0f), r, r);
+  return r;
 #endif
 }
-__device__ __forceinline__ float sqrt_nr(float x) {  // sqrt(x), x >= 1 (or NaN/Inf, which propagate as NaN)
+__device__ __forceinline__ float sqrt_fast(float x) {
 #ifdef LMVN_EMU
   return std::sqrt(x);
 #else
   float r;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  const float s = __fmul_rn(x, r);
-  return __fmaf_rn(__fmul_rn(__fmaf_rn(-s, s, x), 0.5f), r, s);
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 #endif
 }
 
@@ -58,8 +56,8 @@ __device__ __forceinline__ float sqrt_nr(float x) {  // sqrt(x), x >= 1 (or NaN/
 // which float32 evaluates to ~1e-7 of the reference's double evaluation (the
 // textbook form loses up to 6.6e-3 relative for small v in float32).
 __device__ __forceinline__ float tikhonov(float v, const UpdateParams& p) {
-  const float s = sqrt_nr(__fmaf_rn(p.two_lambda, v, 1.0f));
-  return __fmul_rn(__fmul_rn(p.coef, v), rcp_nr(__fadd_rn(1.0f, s)));
+  const float s = sqrt_fast(__fmaf_rn(p.two_lambda, v, 1.0f));
+  return __fmul_rn(__fmul_rn(p.coef, v), rcp_fast(__fadd_rn(1.0f, s)));
 }
 
 __device__ __forceinline__ float rl_update(float psi, float integral, float weight,
@@ -67,7 +65,9 @@ __device__ __forceinline__ float rl_update(float psi, float integral, float weig
   const float last = psi;
   float v = __fmul_rn(last, integral);
   // selects instead of branches: !(v > 0) also catches NaN (ref: inc/cpu_kernels.h:36-38, 66-79)
-  const float t = p.regularized ? tikhonov(v, p) : v;
+  // plain RL (lambda <= 0) runs the same formula with two_lambda = 0, coef = 2: 2 v / (1 + sqrt(1)) == v
+  // exactly (sqrt(1) and 1/2 are exact in the MUFU approximations), so there is no per-voxel mode branch
+  const float t = tikhonov(v, p);
   v = (v > 0.f) ? t : p.min_value;
   // NaN or Inf -> minValue, else max(v, minValue) (ref: inc/cpu_kernels.h:40-47)
   const float next = (fabsf(v) <= 3.402823466e+38f) ? fmaxf(v, p.min_value) : p.min_value;
