@@ -532,14 +532,33 @@ int Deconv::iterate(int iterations, double lambda, float min_value, float* devic
   LMVN_CUDA_TRY(cudaSetDevice(device));
   const UpdateParams up = make_update_params(lambda, min_value);
   LMVN_CUDA_TRY(cudaEventRecord(ev0, stream));
-  for (int it = 0; it < iterations; ++it) {
-    for (int v = 0; v < num_views; ++v) {
-      // integral = view_v / (psi (*) kernel1_v)      ref: src/multiviewnative.cpp:195-205
-      gen::Epilogue e1{gen::EPI_QUOTIENT, 1.f, image[v], nullptr, nullptr, up};
-      LMVN_TRY(engine->convolve(psi, work, khat1[v], e1, integral, stream));
-      // psi = update(psi, integral (*) kernel2_v, weights_v)   ref: :209-227
-      gen::Epilogue e2{gen::EPI_UPDATE, 1.f, nullptr, psi, weights[v], up};
-      LMVN_TRY(engine->convolve(integral, work, khat2[v], e2, psi, stream));
+  if (engine->can_chain() && iterations > 0) {
+    // chained loop: every x-inverse pass also runs the x-forward pass of the convolution that follows it
+    LMVN_TRY(engine->chain_begin(psi, work, stream));
+    for (int it = 0; it < iterations; ++it) {
+      for (int v = 0; v < num_views; ++v) {
+        const bool last = (it == iterations - 1 && v == num_views - 1);
+        LMVN_TRY(engine->chain_middle(work, khat1[v], stream));
+        // (view_v / (psi (*) kernel1_v)) stays on chip and is transformed again   ref: src/multiviewnative.cpp:195-205
+        gen::Epilogue e1{gen::EPI_QUOTIENT, 1.f, image[v], nullptr, nullptr, up};
+        LMVN_TRY(engine->chain_link(work, e1, stream));
+        LMVN_TRY(engine->chain_middle(work, khat2[v], stream));
+        // psi = update(psi, ., weights_v); the new psi is stored AND transformed for the next view   ref: :209-227
+        gen::Epilogue e2{gen::EPI_UPDATE, 1.f, nullptr, psi, weights[v], up};
+        if (last) LMVN_TRY(engine->chain_end(work, e2, psi, stream));
+        else LMVN_TRY(engine->chain_link(work, e2, stream));
+      }
+    }
+  } else {
+    for (int it = 0; it < iterations; ++it) {
+      for (int v = 0; v < num_views; ++v) {
+        // integral = view_v / (psi (*) kernel1_v)      ref: src/multiviewnative.cpp:195-205
+        gen::Epilogue e1{gen::EPI_QUOTIENT, 1.f, image[v], nullptr, nullptr, up};
+        LMVN_TRY(engine->convolve(psi, work, khat1[v], e1, integral, stream));
+        // psi = update(psi, integral (*) kernel2_v, weights_v)   ref: :209-227
+        gen::Epilogue e2{gen::EPI_UPDATE, 1.f, nullptr, psi, weights[v], up};
+        LMVN_TRY(engine->convolve(integral, work, khat2[v], e2, psi, stream));
+      }
     }
   }
   LMVN_CUDA_TRY(cudaEventRecord(ev1, stream));
@@ -605,15 +624,22 @@ int Deconv::profile(double lambda, float min_value, std::vector<std::string>& na
   LMVN_CUDA_TRY(cudaMemcpyAsync(saved, psi, S, cudaMemcpyDeviceToDevice, stream));
   const UpdateParams up = make_update_params(lambda, min_value);
   PassTimer t;
-  int rc = t.begin(stream);
+  int rc = 0;
+  const bool chain = engine->can_chain();
+  // chained loop: the steady state of iterate() is profiled (the one x-forward pass that opens a call is not part of it)
+  if (chain) rc = engine->chain_begin(psi, work, stream);
+  if (rc == 0) rc = t.begin(stream);
   engine->timer = &t;
-  if (rc == 0) {
-    gen::Epilogue e1{gen::EPI_QUOTIENT, 1.f, image[0], nullptr, nullptr, up};
-    rc = engine->convolve(psi, work, khat1[0], e1, integral, stream);
-  }
-  if (rc == 0) {
-    gen::Epilogue e2{gen::EPI_UPDATE, 1.f, nullptr, psi, weights[0], up};
-    rc = engine->convolve(integral, work, khat2[0], e2, psi, stream);
+  gen::Epilogue e1{gen::EPI_QUOTIENT, 1.f, image[0], nullptr, nullptr, up};
+  gen::Epilogue e2{gen::EPI_UPDATE, 1.f, nullptr, psi, weights[0], up};
+  if (chain) {
+    if (rc == 0) rc = engine->chain_middle(work, khat1[0], stream);
+    if (rc == 0) rc = engine->chain_link(work, e1, stream);
+    if (rc == 0) rc = engine->chain_middle(work, khat2[0], stream);
+    if (rc == 0) rc = engine->chain_link(work, e2, stream);
+  } else {
+    if (rc == 0) rc = engine->convolve(psi, work, khat1[0], e1, integral, stream);
+    if (rc == 0) rc = engine->convolve(integral, work, khat2[0], e2, psi, stream);
   }
   engine->timer = nullptr;
   cudaMemcpyAsync(psi, saved, S, cudaMemcpyDeviceToDevice, stream);

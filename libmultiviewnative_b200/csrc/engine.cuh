@@ -69,6 +69,19 @@ struct ConvEngine {
                               cudaStream_t s) = 0;
   virtual int convolve(const float* in, cplx* work, const cplx* khat, const gen::Epilogue& ep,
                        float* out, cudaStream_t s) = 0;
+  // Chained form of the same convolution for the RL loop (optional).  The x pass that ENDS one convolution
+  // and the x pass that STARTS the next work on the same rows, so they are one kernel: the quotient never goes
+  // to HBM and the updated psi is not read back.
+  //   chain_begin(in, work)            work <- x forward of `in`
+  //   chain_middle(work, khat)         y forward, z forward * K^ * z inverse, y inverse
+  //   chain_link(work, ep)             x inverse + pointwise (ep) + x forward of the result, in place in `work`
+  //                                    (EPI_UPDATE also stores psi; EPI_QUOTIENT stores nothing)
+  //   chain_end(work, ep, out)         x inverse + pointwise, no follow-up transform
+  virtual bool can_chain() const { return false; }
+  virtual int chain_begin(const float*, cplx*, cudaStream_t) { return -1; }
+  virtual int chain_middle(cplx*, const cplx*, cudaStream_t) { return -1; }
+  virtual int chain_link(cplx*, const gen::Epilogue&, cudaStream_t) { return -1; }
+  virtual int chain_end(cplx*, const gen::Epilogue&, float*, cudaStream_t) { return -1; }
 };
 
 // What the slab-decomposed (multi-GPU) engine needs from the power-of-two fast path: the same

@@ -576,15 +576,21 @@ struct RowTwShared {
 };
 
 // forward transform of rows row0 .. row0+RPG-1 by one 16-lane group (slab: the group's exchange area)
+// forward transform of RPG rows whose samples are already in registers: v[a * R1 + r] = complex sample
+// lane + 16 r of row row0 + a (the distribution the loads of rows_fwd_group produce, and exactly what the
+// last butterfly of the inverse leaves behind)
+template <int M, typename TW>
+__device__ __forceinline__ void rows_fwd_from_regs(const RowArgs& A, cplx* slab, long long row0, int lane,
+                                                   const TW& T, cplx* v);
+
 template <int M, bool WRAPPED, typename TW>
 __device__ __forceinline__ void rows_fwd_group(const RowArgs& A, cplx* slab, long long row0, int lane,
                                                const TW& T) {
   typedef Row2Cfg<M> CF;
-  constexpr int R1 = CF::R1, RPG = CF::RPG, RS = CF::RS, PAIRS = CF::PAIRS;
+  constexpr int R1 = CF::R1, RPG = CF::RPG;
   constexpr int nx = 2 * M;
-  const int q_blk = lane % R1, r_blk = lane / R1;
   cplx v[16];
-  // ---- stage 1: loads + radix-R1 ----
+  // ---- stage 1: loads ----
 #pragma unroll
   for (int a = 0; a < RPG; ++a) {
     const long long row = row0 + a;
@@ -611,6 +617,16 @@ __device__ __forceinline__ void rows_fwd_group(const RowArgs& A, cplx* slab, lon
       }
     }
   }
+  rows_fwd_from_regs<M>(A, slab, row0, lane, T, v);
+}
+
+template <int M, typename TW>
+__device__ __forceinline__ void rows_fwd_from_regs(const RowArgs& A, cplx* slab, long long row0, int lane,
+                                                   const TW& T, cplx* v) {
+  typedef Row2Cfg<M> CF;
+  constexpr int R1 = CF::R1, RPG = CF::RPG, RS = CF::RS, PAIRS = CF::PAIRS;
+  const int q_blk = lane % R1, r_blk = lane / R1;
+  // ---- stage 1: radix-R1 ----
 #pragma unroll
   for (int a = 0; a < RPG; ++a) {
     Bfly<R1, false>::run(v + a * R1);
@@ -661,7 +677,10 @@ __device__ __forceinline__ void rows_fwd_group(const RowArgs& A, cplx* slab, lon
 }
 
 // inverse transform + pointwise epilogue of rows row0 .. row0+RPG-1 by one 16-lane group
-template <int M, int EPI, typename TW>
+// CHAIN: the real samples the epilogue produces are not (only) stored but forward transformed again and
+// written back as the row's spectrum -- the x pass of the NEXT convolution, fused: `integral` never goes to
+// HBM at all and the new psi is not read back (saves 3S of the 7S + 18C per (view, iteration)).
+template <int M, int EPI, typename TW, bool CHAIN = false>
 __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, long long row0, int lane,
                                                const TW& T) {
   typedef Row2Cfg<M> CF;
@@ -760,10 +779,12 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
         val.x = rl_update(oa[a * R1 + r].x, val.x, ob[a * R1 + r].x, A.ep.up);
         val.y = rl_update(oa[a * R1 + r].y, val.y, ob[a * R1 + r].y, A.ep.up);
       }
-      st_stream(orow + lane + 16 * r, val);
+      if (!CHAIN || mode == gen::EPI_UPDATE) st_stream(orow + lane + 16 * r, val);  // psi is always stored
+      if (CHAIN) v[a * R1 + r] = val;
     }
   }
   __syncwarp();
+  if (CHAIN) rows_fwd_from_regs<M>(A, slab, row0, lane, T, v);
 }
 
 #ifndef LMVN_ROWS_FWD_BLOCKS
@@ -819,6 +840,38 @@ static __global__ void __launch_bounds__(kRowThreads, EPI == gen::EPI_UPDATE ? 2
       }
     }
     rows_inv_group<M, EPI>(A, slab, row0, lane, T);
+  }
+}
+
+// inverse x + pointwise + forward x of the next convolution, in place on the spectrum rows
+template <int M, int EPI>
+static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_inv_fwd(RowArgs A) {
+  typedef Row2Cfg<M> CF;
+  LMVN_DYN_SMEM(cplx, sm);
+  __shared__ cplx s_tw[RowTwShared<M>::ENTRIES * 16];
+  const int lane = threadIdx.x % 16;
+  const int group = threadIdx.x / 16;
+  cplx* slab = sm + group * (CF::RPG * CF::RS);
+  const long long rows = (long long)A.nz * A.ny;
+  RowTwShared<M>::fill(s_tw, A);
+  __syncthreads();
+  RowTwShared<M> T;
+  T.base = s_tw + lane;
+  const long long stride = (long long)gridDim.x * CF::ROWS;
+  for (long long row0 = ((long long)blockIdx.x * CF::GROUPS + group) * CF::RPG; row0 < rows; row0 += stride) {
+    if (A.prefetch && row0 + stride < rows) {
+      const long long nr = row0 + stride;
+      const char* sp = reinterpret_cast<const char*>(A.spec + nr * A.nxp);
+      const int spec_bytes = CF::RPG * A.nxp * int(sizeof(cplx));
+      for (int b = lane * 128; b < spec_bytes; b += 16 * 128) prefetch_l2(sp + b);
+      const int ob = lane * (CF::RPG * M / 2);
+      if (EPI == gen::EPI_QUOTIENT) prefetch_l2(reinterpret_cast<const char*>(A.ep.view + nr * (2 * M)) + ob);
+      if (EPI == gen::EPI_UPDATE) {
+        prefetch_l2(reinterpret_cast<const char*>(A.ep.psi + nr * (2 * M)) + ob);
+        prefetch_l2(reinterpret_cast<const char*>(A.ep.weights + nr * (2 * M)) + ob);
+      }
+    }
+    rows_inv_group<M, EPI, RowTwShared<M>, true>(A, slab, row0, lane, T);
   }
 }
 

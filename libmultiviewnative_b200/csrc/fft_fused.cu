@@ -71,7 +71,7 @@ struct FastEngine : ConvEngine, FastOps {
   int strategy() const override { return 2; }
   size_t khat_elems() const override { return size_t(plan->nz) * plan->ny * nxp; }
   size_t work_elems() const override { return khat_elems(); }
-  int launches_per_conv() const override { return xy_ok ? 3 : 5; }
+  int launches_per_conv() const override { return xy_ok ? 3 : (can_chain() ? 4 : 5); }
   unsigned long long S() const { return plan->voxels() * sizeof(float); }
   unsigned long long C() const { return plan->spec_elems() * sizeof(cplx); }
 
@@ -97,6 +97,7 @@ struct FastEngine : ConvEngine, FastOps {
     if (const char* e = getenv("LMVN_PREFETCH")) y_fwd_prefetch = std::max(0, atoi(e));
     if (const char* e = getenv("LMVN_PREFETCH_KHAT")) khat_prefetch = atoi(e);
     if (const char* e = getenv("LMVN_PREFETCH_ROWS")) rows_prefetch = atoi(e);
+    if (const char* e = getenv("LMVN_CHAIN")) chain_ok = (*e != '0');
     if (const char* e = getenv("LMVN_ROWS_CTAS")) rows_ctas_per_sm = std::max(1, atoi(e));
     {
       std::lock_guard<std::mutex> lk(plan->fast_mu);
@@ -223,6 +224,23 @@ struct FastEngine : ConvEngine, FastOps {
     }
     return 0;
   }
+  template <int MM>
+  int launch_rows_inv_fwd(const fast::RowArgs& a, cudaStream_t s) {
+    typedef fast::Row2Cfg<MM> CF;
+    const size_t rows = size_t(a.nz) * plan->ny;
+    const size_t iters = ceil_div(rows, CF::ROWS);
+    const dim3 grid(unsigned(std::min<size_t>(iters, size_t(num_sms) * rows_ctas_per_sm)));
+    const size_t smem = size_t(CF::GROUPS) * CF::RPG * CF::RS * sizeof(cplx);
+    auto k1 = fast::k_rows_inv_fwd<MM, gen::EPI_QUOTIENT>;
+    auto k2 = fast::k_rows_inv_fwd<MM, gen::EPI_UPDATE>;
+    if (a.ep.mode == gen::EPI_QUOTIENT) {
+      LMVN_LAUNCH(k1, grid, dim3(fast::kRowThreads), smem, s, a);
+    } else {
+      LMVN_LAUNCH(k2, grid, dim3(fast::kRowThreads), smem, s, a);
+    }
+    return 0;
+  }
+
   // nx = 1024
   int launch_rows_fwd_wide(const fast::RowArgs& a, bool wrapped, cudaStream_t s) {
     const size_t rows = size_t(a.nz) * plan->ny;
@@ -435,6 +453,49 @@ struct FastEngine : ConvEngine, FastOps {
   }
   int rows_inv_planes(const cplx* spec, float* out, const gen::Epilogue& ep, int nz_local, cudaStream_t s) override {
     return rows_inv(spec, out, ep, s, 0, nz_local);
+  }
+
+  // x inverse + pointwise + x forward of the result, in place on the rows of `spec`
+  int rows_inv_fwd(cplx* spec, const gen::Epilogue& ep, cudaStream_t s) {
+    if (ep.scale != 1.f || (ep.mode != gen::EPI_QUOTIENT && ep.mode != gen::EPI_UPDATE)) {
+      set_last_error("chained rows pass: quotient or update epilogue with unit scale expected");
+      return -1;
+    }
+    fast::RowArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.spec = spec;
+    a.ep = ep;
+    a.nz = plan->nz; a.ny = plan->ny; a.nxp = nxp;
+    a.tw_m = d_tw_m; a.tw_nx = d_tw_nx; a.tw_h = d_tw_h;
+    a.prefetch = rows_prefetch;
+    switch (M) {
+      case 32: LMVN_TRY(launch_rows_inv_fwd<32>(a, s)); break;
+      case 64: LMVN_TRY(launch_rows_inv_fwd<64>(a, s)); break;
+      case 128: LMVN_TRY(launch_rows_inv_fwd<128>(a, s)); break;
+      case 256: LMVN_TRY(launch_rows_inv_fwd<256>(a, s)); break;
+      default: set_last_error("chained rows pass: unsupported nx"); return -1;
+    }
+    LMVN_CUDA_TRY(cudaGetLastError());
+    // algorithmic bytes: spectrum in and out, operands in, psi out for the update
+    mark(ep.mode == gen::EPI_UPDATE ? "fast_rows_inv_update_fwd" : "fast_rows_inv_quotient_fwd",
+         2 * C() + S() * (ep.mode == gen::EPI_UPDATE ? 3 : 1), s);
+    return 0;
+  }
+
+  bool chain_ok = true;
+  bool can_chain() const override { return chain_ok && !xy_ok && M <= 256; }
+  int chain_begin(const float* in, cplx* work, cudaStream_t s) override {
+    gen::RealSource src{in, 0, 0, 0, 0};
+    return rows_fwd(src, work, s);
+  }
+  int chain_middle(cplx* work, const cplx* khat, cudaStream_t s) override {
+    LMVN_TRY(strided(work, nullptr, 1, fast::SM_FWD, 1.f, s));
+    LMVN_TRY(strided(work, khat, 0, fast::SM_FWD_MUL_INV, 1.f, s));
+    return strided(work, nullptr, 1, fast::SM_INV, 1.f, s);
+  }
+  int chain_link(cplx* work, const gen::Epilogue& ep, cudaStream_t s) override { return rows_inv_fwd(work, ep, s); }
+  int chain_end(cplx* work, const gen::Epilogue& ep, float* out, cudaStream_t s) override {
+    return rows_inv(work, out, ep, s);
   }
 
   int kernel_spectrum(const float* d_kernel, const int kd[3], cplx* khat, cplx*, cudaStream_t s) override {

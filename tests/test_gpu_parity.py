@@ -213,9 +213,11 @@ def test_xy_kernel_deconvolve_config1(LXY):
 
 # ---- one volume over several ranks (slab-decomposed plans), all ranks on this GPU ------------
 @pytest.mark.parametrize("dims,world", [((64, 64, 64), 2), ((128, 128, 128), 4), ((256, 256, 256), 8)])
-def test_slab_group_equals_single_plan(L, dims, world):
+def test_slab_group_equals_single_plan(L, dims, world, monkeypatch):
     """parity of the multi-GPU code path against the single-GPU path (256^3 case
-    included).  Same butterflies on the same data => bit-identical."""
+    included).  Same butterflies on the same data; the single-GPU loop runs the chained x passes (another
+    compilation of the same source, so FMA contraction may differ in the last bit): identical to a few ulp,
+    and bit-identical to the unchained single-GPU loop."""
     from libmultiviewnative_b200.slabs import LocalSlabGroup
     from libmultiviewnative_b200.synthetic import make_views
 
@@ -229,7 +231,11 @@ def test_slab_group_equals_single_plan(L, dims, world):
         got = g.get_psi()
     single = d["psi0"].copy()
     L.inplace_gpu_deconvolve(single, d["views"], d["kernels1"], d["kernels2"], d["weights"], iters, lam, 1e-4)
-    np.testing.assert_array_equal(got, single)
+    assert pc.max_rel(got, single) < 5e-6
+    monkeypatch.setenv("LMVN_CHAIN", "0")  # read when a plan is created
+    unchained = d["psi0"].copy()
+    L.inplace_gpu_deconvolve(unchained, d["views"], d["kernels1"], d["kernels2"], d["weights"], iters, lam, 1e-4)
+    np.testing.assert_array_equal(got, unchained)
 
 
 def test_slab_group_vs_oracle(L):
@@ -264,5 +270,5 @@ def test_slab_plans_two_processes_two_gpus(L):
            "--master-port", "29533", os.path.join(root, "tools", "slab_mp_check.py"), "128,128,128", "2", "2"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
-    assert "identical=True" in res.stdout
+    assert "slab_mp_check dims=" in res.stdout  # rank 0 asserts the comparison itself (exit code above)
     assert "identical to the P2P-fused path on every rank = True" in res.stdout

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Multi-process check of the slab-decomposed plans (run under torchrun, one rank per GPU):
 every rank deconvolves its slab with P2P-fused exchanges; rank 0 gathers psi and compares it
-with the single-GPU plan bit for bit, then prints timings.
+with the single-GPU plan (identical up to the FMA contraction of the chained x passes: a few ulp),
+then prints timings.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29511 tools/slab_mp_check.py 256,256,256 2 5
@@ -73,7 +74,7 @@ def main():
               "= %.1f Gvox/s | single GPU %.3f ms = %.1f Gvox/s | speed-up %.2fx" % (
                   dims, world, nv, same, rel, ms, world, t.item() / (10 * nv), nvox * 10 * nv / (t.item() * 1e-3) / 1e9,
                   t1 / (10 * nv), nvox * 10 * nv / (t1 * 1e-3) / 1e9, t1 / t.item()), flush=True)
-        assert same or rel < 1e-5
+        assert same or rel < 5e-6  # the single-GPU loop chains its x passes: same source, other FMA contraction
     dist.barrier()
     plan.close()
     dist.destroy_process_group()
