@@ -911,6 +911,10 @@ __device__ __forceinline__ void st_stream4(float4* p, float4 v) {
 }
 
 template <bool WRAPPED>
+__device__ __forceinline__ void rows_fwd_wide_from_regs(const RowArgs& A, cplx* slab, long long row, int lane, cplx* ve,
+                                                        cplx* vo);
+
+template <bool WRAPPED>
 __device__ __forceinline__ void rows_fwd_wide_group(const RowArgs& A, cplx* slab, long long row, int lane) {
   constexpr int H = RowWide::H, M = RowWide::M, nx = RowWide::NX, RS = RowWide::RS;
   cplx* se = slab;
@@ -943,6 +947,16 @@ __device__ __forceinline__ void rows_fwd_wide_group(const RowArgs& A, cplx* slab
       vo[r] = cmake(f[2], f[3]);
     }
   }
+  rows_fwd_wide_from_regs<WRAPPED>(A, slab, row, lane, ve, vo);
+}
+
+// ve[r], vo[r] = complex samples 2m, 2m+1 with m = lane + 16 r
+template <bool WRAPPED>
+__device__ __forceinline__ void rows_fwd_wide_from_regs(const RowArgs& A, cplx* slab, long long row, int lane, cplx* ve,
+                                                        cplx* vo) {
+  constexpr int H = RowWide::H, M = RowWide::M, RS = RowWide::RS;
+  cplx* se = slab;
+  cplx* so = slab + RS;
   Bfly<16, false>::run(ve);
   Bfly<16, false>::run(vo);
 #pragma unroll
@@ -994,7 +1008,7 @@ __device__ __forceinline__ void rows_fwd_wide_group(const RowArgs& A, cplx* slab
   __syncwarp();
 }
 
-template <int EPI>
+template <int EPI, bool CHAIN = false>
 __device__ __forceinline__ void rows_inv_wide_group(const RowArgs& A, cplx* slab, long long row, int lane) {
   constexpr int H = RowWide::H, M = RowWide::M, nx = RowWide::NX, RS = RowWide::RS;
   const cplx* irow = A.spec + row * A.nxp;
@@ -1056,7 +1070,8 @@ __device__ __forceinline__ void rows_inv_wide_group(const RowArgs& A, cplx* slab
   float4* orow = reinterpret_cast<float4*>(obase + row * nx);
   const float4* pa = reinterpret_cast<const float4*>((EPI == gen::EPI_QUOTIENT ? A.ep.view : A.ep.psi) + row * nx);
   const float4* pb = reinterpret_cast<const float4*>(A.ep.weights + row * nx);
-  constexpr int CH = (EPI == gen::EPI_UPDATE) ? 4 : 8;  // operands CH float4 at a time (register budget)
+  // operands CH float4 at a time (register budget; the chained form keeps all 32 results live)
+  constexpr int CH = CHAIN ? (EPI == gen::EPI_UPDATE ? 2 : 4) : (EPI == gen::EPI_UPDATE ? 4 : 8);
 #pragma unroll
   for (int h = 0; h < 16 / CH; ++h) {
     float4 oa[CH], ob[CH];
@@ -1079,8 +1094,20 @@ __device__ __forceinline__ void rows_inv_wide_group(const RowArgs& A, cplx* slab
         val.x = rl_update(oa[r].x, val.x, ob[r].x, A.ep.up); val.y = rl_update(oa[r].y, val.y, ob[r].y, A.ep.up);
         val.z = rl_update(oa[r].z, val.z, ob[r].z, A.ep.up); val.w = rl_update(oa[r].w, val.w, ob[r].w, A.ep.up);
       }
-      st_stream4(orow + lane + 16 * rr, val);
+      if (!CHAIN || EPI == gen::EPI_UPDATE) st_stream4(orow + lane + 16 * rr, val);
+      if (CHAIN) {
+        ve[rr] = cmake(val.x, val.y);
+        vo[rr] = cmake(val.z, val.w);
+      }
     }
+#if !defined(LMVN_EMU) && defined(__CUDA_ARCH__)
+    if (CHAIN) asm volatile("" ::: "memory");  // keep the operand loads of the next chunk from being hoisted (spills)
+#endif
+  }
+  if (CHAIN) {
+    __syncwarp();
+    rows_fwd_wide_from_regs<false>(A, slab, row, lane, ve, vo);
+    return;
   }
   __syncwarp();
 }
@@ -1128,6 +1155,32 @@ static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_inv_wide(RowArgs
       }
     }
     rows_inv_wide_group<EPI>(A, slab, row, lane);
+  }
+}
+
+template <int EPI>
+static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_inv_fwd_wide(RowArgs A) {
+  LMVN_DYN_SMEM(cplx, sm);
+  const int lane = threadIdx.x % 16;
+  const int group = threadIdx.x / 16;
+  cplx* slab = sm + group * RowWide::SLAB;
+  const long long rows = (long long)A.nz * A.ny;
+  const long long stride = (long long)gridDim.x * RowWide::ROWS;
+  for (long long row = (long long)blockIdx.x * RowWide::ROWS + group; row < rows; row += stride) {
+    if (A.prefetch && row + stride < rows) {
+      const long long nr = row + stride;
+      const char* sp = reinterpret_cast<const char*>(A.spec + nr * A.nxp);
+      for (int b = lane * 128; b < A.nxp * int(sizeof(cplx)); b += 16 * 128) prefetch_l2(sp + b);
+      const char* oa = reinterpret_cast<const char*>((EPI == gen::EPI_QUOTIENT ? A.ep.view : A.ep.psi) + nr * RowWide::NX);
+      prefetch_l2(oa + lane * 128);
+      prefetch_l2(oa + 2048 + lane * 128);
+      if (EPI == gen::EPI_UPDATE) {
+        const char* ob = reinterpret_cast<const char*>(A.ep.weights + nr * RowWide::NX);
+        prefetch_l2(ob + lane * 128);
+        prefetch_l2(ob + 2048 + lane * 128);
+      }
+    }
+    rows_inv_wide_group<EPI, true>(A, slab, row, lane);
   }
 }
 
