@@ -344,15 +344,36 @@ struct DistDeconv {
     const UpdateParams up = make_update_params(lambda, min_value);
     LMVN_TRY(barrier());  // nobody starts scattering before every peer is ready
     LMVN_CUDA_TRY(cudaEventRecord(ev0, stream));
-    for (int it = 0; it < iterations; ++it)
-      for (int v = 0; v < num_views; ++v)
-        for (int which = 1; which <= 2; ++which) {
-          LMVN_TRY(conv_phase(v, which, 0, up));
-          LMVN_TRY(barrier());
-          LMVN_TRY(conv_phase(v, which, 1, up));
-          LMVN_TRY(barrier());
-          LMVN_TRY(conv_phase(v, which, 2, up));
-        }
+    if (ops->can_chain_rows() && !staged && iterations > 0) {
+      // chained loop (see Deconv::iterate): the x-inverse pass also runs the x-forward pass of the next
+      // convolution, in place on the slab's spectrum rows
+      gen::RealSource src{psi, 0, 0, 0, 0};
+      LMVN_TRY(ops->rows_fwd_planes(src, slab_work(rank), nz_l, rank * nz_l, nz, stream));
+      for (int it = 0; it < iterations; ++it)
+        for (int v = 0; v < num_views; ++v)
+          for (int which = 1; which <= 2; ++which) {
+            const bool last = (it == iterations - 1 && v == num_views - 1 && which == 2);
+            LMVN_TRY(ops->strided_geom(y_geom(fast::SM_FWD_SCATTER), stream));
+            LMVN_TRY(barrier());
+            LMVN_TRY(conv_phase(v, which, 1, up));
+            LMVN_TRY(barrier());
+            LMVN_TRY(ops->strided_geom(y_geom(fast::SM_INV), stream));
+            gen::Epilogue e = (which == 1) ? gen::Epilogue{gen::EPI_QUOTIENT, 1.f, image[v], nullptr, nullptr, up}
+                                           : gen::Epilogue{gen::EPI_UPDATE, 1.f, nullptr, psi, weights[v], up};
+            if (last) LMVN_TRY(ops->rows_inv_planes(slab_work(rank), psi, e, nz_l, stream));
+            else LMVN_TRY(ops->rows_inv_fwd_planes(slab_work(rank), e, nz_l, stream));
+          }
+    } else {
+      for (int it = 0; it < iterations; ++it)
+        for (int v = 0; v < num_views; ++v)
+          for (int which = 1; which <= 2; ++which) {
+            LMVN_TRY(conv_phase(v, which, 0, up));
+            LMVN_TRY(barrier());
+            LMVN_TRY(conv_phase(v, which, 1, up));
+            LMVN_TRY(barrier());
+            LMVN_TRY(conv_phase(v, which, 2, up));
+          }
+    }
     LMVN_CUDA_TRY(cudaEventRecord(ev1, stream));
     LMVN_TRY(check_device_error());
     if (device_ms) LMVN_CUDA_TRY(cudaEventElapsedTime(device_ms, ev0, ev1));

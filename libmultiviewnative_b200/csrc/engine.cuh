@@ -106,6 +106,9 @@ struct FastOps {
                               cudaStream_t s) = 0;
   virtual int rows_inv_planes(const cplx* spec, float* out, const gen::Epilogue& ep, int nz_local, cudaStream_t s) = 0;
   virtual int strided_geom(const StridedGeom& g, cudaStream_t s) = 0;
+  // chained x passes (x inverse + pointwise + x forward in place on nz_local planes of `spec`); false: not available
+  virtual bool can_chain_rows() const = 0;
+  virtual int rows_inv_fwd_planes(cplx* spec, const gen::Epilogue& ep, int nz_local, cudaStream_t s) = 0;
 };
 // nullptr (last error set) when the global shape is not eligible for the fast path
 std::unique_ptr<FastOps> make_fast_ops(std::shared_ptr<FftPlan> plan_global);

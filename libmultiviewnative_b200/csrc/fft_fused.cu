@@ -457,9 +457,13 @@ struct FastEngine : ConvEngine, FastOps {
   int rows_inv_planes(const cplx* spec, float* out, const gen::Epilogue& ep, int nz_local, cudaStream_t s) override {
     return rows_inv(spec, out, ep, s, 0, nz_local);
   }
+  bool can_chain_rows() const override { return chain_ok && (M <= 256 || chain_wide); }
+  int rows_inv_fwd_planes(cplx* spec, const gen::Epilogue& ep, int nz_local, cudaStream_t s) override {
+    return rows_inv_fwd(spec, ep, s, nz_local);
+  }
 
   // x inverse + pointwise + x forward of the result, in place on the rows of `spec`
-  int rows_inv_fwd(cplx* spec, const gen::Epilogue& ep, cudaStream_t s) {
+  int rows_inv_fwd(cplx* spec, const gen::Epilogue& ep, cudaStream_t s, int nzs = -1) {
     if (ep.scale != 1.f || (ep.mode != gen::EPI_QUOTIENT && ep.mode != gen::EPI_UPDATE)) {
       set_last_error("chained rows pass: quotient or update epilogue with unit scale expected");
       return -1;
@@ -468,7 +472,7 @@ struct FastEngine : ConvEngine, FastOps {
     std::memset(&a, 0, sizeof(a));
     a.spec = spec;
     a.ep = ep;
-    a.nz = plan->nz; a.ny = plan->ny; a.nxp = nxp;
+    a.nz = nzs >= 0 ? nzs : plan->nz; a.ny = plan->ny; a.nxp = nxp;
     a.tw_m = d_tw_m; a.tw_nx = d_tw_nx; a.tw_h = d_tw_h;
     a.prefetch = rows_prefetch;
     switch (M) {
