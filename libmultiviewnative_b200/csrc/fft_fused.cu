@@ -1,13 +1,17 @@
 // fft_fused.cu -- host side of the power-of-two fast path (kernels: fft_fast.cuh).
 //
-// Strategy LMVN_STRATEGY_FUSED: five launches per convolution, every pointwise step
-// of the RL iteration fused into a transform pass:
-//   rows_fwd            S -> C     real rows (or wrapped PSF) -> half spectrum along x
-//   strided y forward   C -> C
-//   strided z fwd*K^*inv C,K -> C  last forward stage, spectrum product and first inverse
-//                                  stage share registers
-//   strided y inverse   C -> C
-//   rows_inv            C(+S..) -> S   inverse along x + quotient / RL update
+// Strategy LMVN_STRATEGY_FUSED.  One convolution = five passes, every pointwise step fused into a pass edge:
+//   rows_fwd             S -> C          real rows (or wrapped PSF) -> half spectrum along x
+//   strided y forward    C -> C
+//   strided z fwd*K^*inv C, K^ -> C      last forward stage, spectrum product and first inverse stage share registers
+//   strided y inverse    C -> C
+//   rows_inv             C (+S..) -> S   inverse along x + quotient / RL update
+// Inside the RL loop (ConvEngine::chain_*) rows_inv of one convolution and rows_fwd of the next are ONE kernel
+// (rows_inv_fwd), four launches per convolution.  Runtime knobs (environment, read when an engine is created) are
+// A/B switches of measured design decisions, see DESIGN.md section 3.1:
+//   LMVN_CHAIN=0           unchained loop              LMVN_XY_FUSED=1      persistent L2-resident x/y kernel
+//   LMVN_PREFETCH=<blocks> y-forward look-ahead (148)  LMVN_PREFETCH_ROWS=0 no next-iteration row prefetch
+//   LMVN_NXP_ALIGN=<n>     spectrum pitch alignment (8 complex elements)
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -540,23 +544,11 @@ struct FastEngine : ConvEngine, FastOps {
       LMVN_TRY(xy(nullptr, work, out, &ep, s));
       return 0;
     }
-    static int slabs = -1;
-    if (slabs < 0) {
-      const char* e = getenv("LMVN_SLABS");
-      slabs = e ? atoi(e) : 1;
-      if (slabs < 1) slabs = 1;
-    }
-    const int ns = (plan->nz % slabs == 0) ? slabs : 1;
-    const int nzs = plan->nz / ns;
-    for (int i = 0; i < ns; ++i) {
-      LMVN_TRY(rows_fwd(src, work, s, i * nzs, nzs));
-      LMVN_TRY(strided(work, nullptr, 1, fast::SM_FWD, 1.f, s, i * nzs, nzs));
-    }
+    LMVN_TRY(rows_fwd(src, work, s));
+    LMVN_TRY(strided(work, nullptr, 1, fast::SM_FWD, 1.f, s));
     LMVN_TRY(strided(work, khat, 0, fast::SM_FWD_MUL_INV, 1.f, s));
-    for (int i = 0; i < ns; ++i) {
-      LMVN_TRY(strided(work, nullptr, 1, fast::SM_INV, 1.f, s, i * nzs, nzs));
-      LMVN_TRY(rows_inv(work, out, ep, s, i * nzs, nzs));
-    }
+    LMVN_TRY(strided(work, nullptr, 1, fast::SM_INV, 1.f, s));
+    LMVN_TRY(rows_inv(work, out, ep, s));
     return 0;
   }
 };
