@@ -35,6 +35,14 @@
 #include "fft_fast.cuh"
 #include "lmvn_b200.h"
 
+#ifdef LMVN_EMU
+// host emulation (tests): the peer-visible exchange region is POSIX shared memory, so that the multi-process
+// path (handle exchange, peer stores, phases) runs under a gloo group on the CPU
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+#endif
+
 namespace lmvn {
 
 namespace {
@@ -107,6 +115,28 @@ struct DistDeconv {
   bool own_stream = true;
   cplx* stage_send = nullptr;
   cplx* stage_recv = nullptr;
+#ifdef LMVN_EMU
+  char shm_name[64] = {0};
+  int alloc_exchange() {
+    static int counter = 0;
+    std::snprintf(shm_name, sizeof(shm_name), "/lmvn_emu_%d_%d_%d", int(getpid()), rank, counter++);
+    const int fd = shm_open(shm_name, O_CREAT | O_RDWR, 0600);
+    if (fd < 0 || ftruncate(fd, off_t(xchg_bytes)) != 0) { set_last_error("emu: shm_open failed"); return -1; }
+    void* p = mmap(nullptr, xchg_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) { set_last_error("emu: mmap failed"); return -1; }
+    xchg = static_cast<unsigned char*>(p);
+    return 0;
+  }
+  void free_exchange() {
+    for (int r = 0; r < kMaxRanks; ++r)
+      if (peer_ipc[r] && peer[r]) munmap(peer[r], xchg_bytes);
+    if (xchg) {
+      munmap(xchg, xchg_bytes);
+      shm_unlink(shm_name);
+    }
+  }
+#endif
 
   size_t slab_real() const { return size_t(nz_l) * ny * nx; }
   size_t slab_spec() const { return size_t(nz_l) * ny * nxp; }
@@ -118,8 +148,13 @@ struct DistDeconv {
   ~DistDeconv() {
     if (arena || xchg || stream) cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
+#ifdef LMVN_EMU
+    free_exchange();
+    xchg = nullptr;
+#else
     for (int r = 0; r < kMaxRanks; ++r)
       if (peer_ipc[r] && peer[r]) cudaIpcCloseMemHandle(peer[r]);
+#endif
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream && own_stream) cudaStreamDestroy(stream);
@@ -128,7 +163,9 @@ struct DistDeconv {
     if (d_peer_flags) cudaFree(d_peer_flags);
     if (d_err) cudaFree(d_err);
     if (arena) cudaFree(arena);
+#ifndef LMVN_EMU
     if (xchg) cudaFree(xchg);
+#endif
   }
 
   int init(const int* d, int nviews, int rank_, int world_, int dev) {
@@ -173,7 +210,11 @@ struct DistDeconv {
       return -1;
     }
     LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&arena), arena_bytes));
+#ifdef LMVN_EMU
+    LMVN_TRY(alloc_exchange());
+#else
     LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&xchg), xchg_bytes));
+#endif
     LMVN_CUDA_TRY(cudaMemset(xchg + flags_off, 0, 256));
     LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_peer_flags), sizeof(unsigned*) * kMaxRanks));
     LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_err), sizeof(unsigned)));
@@ -432,9 +473,9 @@ extern "C" int lmvn_dist_get_info(const lmvn_dist* h, lmvn_dist_info* info) {
 extern "C" int lmvn_dist_export_handle(lmvn_dist* h, void* handle64) {
   LMVN_DIST_GUARD(h);
 #ifdef LMVN_EMU
-  (void)handle64;
-  set_last_error("no IPC in the emulated build");
-  return -1;
+  std::memset(handle64, 0, 64);
+  std::memcpy(handle64, h->d.shm_name, std::strlen(h->d.shm_name));
+  return 0;
 #else
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   LMVN_CUDA_TRY(cudaSetDevice(h->d.device));
@@ -448,9 +489,21 @@ extern "C" int lmvn_dist_export_handle(lmvn_dist* h, void* handle64) {
 extern "C" int lmvn_dist_connect_ipc(lmvn_dist* h, int peer_rank, const void* handle64) {
   LMVN_DIST_GUARD(h);
 #ifdef LMVN_EMU
-  (void)peer_rank; (void)handle64;
-  set_last_error("no IPC in the emulated build");
-  return -1;
+  {
+    DistDeconv& d = h->d;
+    if (peer_rank < 0 || peer_rank >= d.world || peer_rank == d.rank) { set_last_error("bad peer rank %d", peer_rank); return -1; }
+    char name[65] = {0};
+    std::memcpy(name, handle64, 64);
+    const int fd = shm_open(name, O_RDWR, 0600);
+    if (fd < 0) { set_last_error("emu: cannot open the exchange region of rank %d", peer_rank); return -1; }
+    void* p = mmap(nullptr, d.xchg_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) { set_last_error("emu: mmap of the peer region failed"); return -1; }
+    d.peer[peer_rank] = static_cast<unsigned char*>(p);
+    d.peer_ipc[peer_rank] = true;
+    d.multi_process = true;
+    return 0;
+  }
 #else
   DistDeconv& d = h->d;
   if (peer_rank < 0 || peer_rank >= d.world || peer_rank == d.rank) { set_last_error("bad peer rank %d", peer_rank); return -1; }

@@ -203,6 +203,33 @@ class ProcessSlabPlan(SlabPlan):
         self.synchronize()
 
 
+    def _host_barrier(self):
+        self.synchronize()
+        self.dist.barrier()
+
+    def set_view_host_barriers(self, v: int, image_slab, weights_slab, kernel1, kernel2):
+        """set_view with host-side barriers between the phases (any backend; used by the CPU tests)."""
+        self.set_view_slab(v, image_slab, weights_slab)
+        for which, k in ((1, kernel1), (2, kernel2)):
+            self._host_barrier()
+            self.psf_phase(v, which, 0, np.ascontiguousarray(k, dtype=np.float32))
+            self._host_barrier()
+            self.psf_phase(v, which, 1)
+        self._host_barrier()
+
+    def iterate_host_barriers(self, iterations: int, lam: float = 0.0, min_value: float = 1e-4):
+        """The phase sequence of lmvn_dist_iterate with torch.distributed barriers instead of the device-side
+        flag barrier: slower, but independent of peer-visible flags (and what the gloo tests on the CPU drive)."""
+        self._host_barrier()
+        for _ in range(int(iterations)):
+            for v in range(self.num_views):
+                for which in (1, 2):
+                    self.conv_phase(v, which, 0, lam, min_value)
+                    self._host_barrier()
+                    self.conv_phase(v, which, 1, lam, min_value)
+                    self._host_barrier()
+                    self.conv_phase(v, which, 2, lam, min_value)
+
     # ---- comparator: the same exchanges through NCCL all_to_all_single ------------------------------
     def _tensor(self, which: int, torch):
         ptr, nbytes = C.c_void_p(), C.c_ulonglong()
