@@ -54,6 +54,7 @@ struct FastEngine : ConvEngine, FastOps {
   int M = 0, nxc = 0, nxp = 0;
   int num_sms = 148;
   int rows_ctas_per_sm = 8;
+  int update_ctas_per_sm = 64;
   int y_fwd_prefetch = 148;  // blocks of look-ahead of the L2 prefetch in the forward y pass
   int khat_prefetch = 0;  // measured: hurts the z pass (plane-strided lines), kept as a knob
   int rows_prefetch = 1;
@@ -105,7 +106,7 @@ struct FastEngine : ConvEngine, FastOps {
     if (const char* e = getenv("LMVN_PREFETCH_ROWS")) rows_prefetch = atoi(e);
     if (const char* e = getenv("LMVN_CHAIN")) chain_ok = (*e != '0');
     if (const char* e = getenv("LMVN_CHAIN_WIDE")) chain_wide = (*e != '0');
-    if (const char* e = getenv("LMVN_ROWS_CTAS")) rows_ctas_per_sm = std::max(1, atoi(e));
+    if (const char* e = getenv("LMVN_ROWS_CTAS")) rows_ctas_per_sm = update_ctas_per_sm = std::max(1, atoi(e));
     {
       std::lock_guard<std::mutex> lk(plan->fast_mu);
       if (!plan->fast_tables) {
@@ -236,7 +237,10 @@ struct FastEngine : ConvEngine, FastOps {
     typedef fast::Row2Cfg<MM> CF;
     const size_t rows = size_t(a.nz) * plan->ny;
     const size_t iters = ceil_div(rows, CF::ROWS);
-    const dim3 grid(unsigned(std::min<size_t>(iters, size_t(num_sms) * rows_ctas_per_sm)));
+    // measured: the update link (four streams per row) runs best with one loop iteration per CTA, i.e. left to the
+    // hardware CTA scheduler (0.268 -> 0.242 ms on config 3); the quotient link with a persistent loop of ~7 iterations
+    const int per_sm = (a.ep.mode == gen::EPI_UPDATE) ? update_ctas_per_sm : rows_ctas_per_sm;
+    const dim3 grid(unsigned(std::min<size_t>(iters, size_t(num_sms) * per_sm)));
     const size_t smem = size_t(CF::GROUPS) * CF::RPG * CF::RS * sizeof(cplx);
     auto k1 = fast::k_rows_inv_fwd<MM, gen::EPI_QUOTIENT>;
     auto k2 = fast::k_rows_inv_fwd<MM, gen::EPI_UPDATE>;
