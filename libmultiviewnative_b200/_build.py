@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libmultiviewnative.so")
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
 EMU_PATH = os.path.join(EMU_DIR, "_lmvn_emu.so")
 
-CUDA_SOURCES = ["api.cu", "engine.cu", "fft_fused.cu", "fft_fused_xy.cu", "dist.cu"]
+CUDA_SOURCES = ["api.cu", "engine.cu", "fft_fused.cu", "dist.cu"]
 HOST_SOURCES = ["cpu_path.cpp"]
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

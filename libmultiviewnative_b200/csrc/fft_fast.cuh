@@ -1184,162 +1184,5 @@ static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_inv_fwd_wide(Row
   }
 }
 
-// ------------------------------------------------------------------------------
-// x and y passes in ONE persistent launch, plane by plane, so that the x<->y
-// intermediate of a plane lives in the 126 MB L2 and never makes an HBM round trip
-// (HBM traffic of the launch: S + C instead of S + 3C).
-//
-// Work items are handed out by a global ticket counter in plane order:
-//   forward   step s:  row items of plane s (x transform, ROWS rows each), then the
-//                      y tiles of plane s - lag;
-//   inverse   step s:  y tiles of plane s, then the row items of plane s - lag.
-// A consumer item waits for its plane's completion counter.  An item only depends on
-// items with SMALLER tickets, and a ticket is only ever held by a running CTA, so the
-// waits cannot deadlock whatever the residency; `lag` is sized so that the producers of
-// a plane have normally finished by the time its consumers are handed out.
-// The sync block (ticket, error flag, per-plane counters) is zeroed by the PREVIOUS
-// launch of the ring (engine side), so no memset sits between launches.
-// ------------------------------------------------------------------------------
-struct XYArgs {
-  RowArgs rows;
-  StridedArgs y;          // data = spectrum base, row_stride = nxp, tile_stride = ny * nxp
-  unsigned* sync;         // this launch: [0] ticket, [1] error flag, [4 + p] plane counters
-  unsigned* sync_next;    // next launch's block, cleared here
-  int sync_words;
-  int lag;                // planes between producer and consumer hand-out
-};
-
-__device__ __forceinline__ void plane_signal(unsigned* counter) {
-  __threadfence();
-  atomicAdd(counter, 1u);
-}
-__device__ __forceinline__ void plane_wait(unsigned* counter, unsigned target, unsigned* err) {
-#ifdef LMVN_EMU
-  if (*counter < target) { std::fprintf(stderr, "emu: plane_wait would block\n"); std::abort(); }
-  (void)err;
-#else
-  unsigned v;
-  unsigned spins = 0;
-  for (;;) {
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-    if (v >= target) break;
-    __nanosleep(64);
-    if (++spins > (1u << 24)) {  // ~seconds: a lost producer must not hang the device
-      *err = 1u;
-      break;
-    }
-  }
-#endif
-}
-
-// decoded work item of the x/y kernel
-struct XYItem {
-  int plane;      // < 0: nothing to do (padding ticket at either end of the schedule)
-  int idx;        // row item or y tile within the plane
-  bool first;     // producer group of its step
-  bool is_rows;
-};
-
-template <int M, int NY, bool INVERSE, int EPI>
-static __global__ void __launch_bounds__(kRowThreads, 2) k_xy(XYArgs A) {
-  constexpr bool WRAPPED = false;
-  typedef Row2Cfg<M> CF;
-  constexpr int COLS = Cols<NY>::V;
-  constexpr int MODE = INVERSE ? SM_INV : SM_FWD;
-  static_assert(Threads<NY>::V == kRowThreads, "one block shape for both item kinds");
-  LMVN_DYN_SMEM(cplx, sm);  // max(row slabs, [NY][COLS] tile)
-  __shared__ unsigned s_ticket;
-  __shared__ cplx s_tw[RowTwShared<M>::ENTRIES * 16];
-  RowTwShared<M>::fill(s_tw, A.rows);
-  const int lane = threadIdx.x % 16;
-  const int group = threadIdx.x / 16;
-  cplx* slab = sm + group * (CF::RPG * CF::RS);
-  const int c = threadIdx.x % COLS;
-  const int nz = A.rows.nz, ny = A.rows.ny;
-  const int n_r = ny / CF::ROWS;
-  const int n_y = (A.y.ncols + COLS - 1) / COLS;
-  const int per_step = n_r + n_y;
-  const unsigned total = unsigned(nz + A.lag) * unsigned(per_step);
-  unsigned* done = A.sync + 4;
-  // clear the next launch's sync block (nobody uses it while this launch runs)
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.sync_words; i += gridDim.x * blockDim.x)
-    A.sync_next[i] = 0u;
-
-  auto decode = [&](unsigned tk) {
-    XYItem it;
-    it.plane = -1; it.idx = 0; it.first = false; it.is_rows = false;
-    if (tk >= total) return it;
-    const int step = int(tk / unsigned(per_step));
-    const int r = int(tk % unsigned(per_step));
-    // first group of a step = producers of plane `step`, second = consumers of plane `step - lag`
-    it.first = INVERSE ? (r < n_y) : (r < n_r);
-    const int plane = it.first ? step : step - A.lag;
-    it.is_rows = (it.first != INVERSE);
-    it.idx = it.first ? r : r - (INVERSE ? n_y : n_r);
-    it.plane = (plane >= 0 && plane < nz) ? plane : -1;
-    return it;
-  };
-  // Pull the HBM-resident inputs of an item into L2 one item ahead of its use; the x<->y
-  // intermediate is in L2 anyway, so every load of the item itself then has L2 latency.
-  auto prefetch = [&](const XYItem& it) {
-    if (it.plane < 0) return;
-    if (it.is_rows) {
-      const size_t first_row = size_t(it.plane) * ny + size_t(it.idx) * CF::ROWS;
-      const size_t off = first_row * (2 * M) * sizeof(float) + size_t(threadIdx.x) * 128;
-      constexpr int BYTES = CF::ROWS * 2 * M * int(sizeof(float));  // contiguous rows of one item
-      if (!INVERSE) {
-        if (!WRAPPED)
-          for (int b = 0; b < BYTES; b += kRowThreads * 128)
-            prefetch_l2(reinterpret_cast<const char*>(A.rows.src.data) + off + b);
-      } else if (EPI != gen::EPI_STORE) {
-        const float* pa = (EPI == gen::EPI_QUOTIENT) ? A.rows.ep.view : A.rows.ep.psi;
-        for (int b = 0; b < BYTES; b += kRowThreads * 128) {
-          prefetch_l2(reinterpret_cast<const char*>(pa) + off + b);
-          if (EPI == gen::EPI_UPDATE)
-            prefetch_l2(reinterpret_cast<const char*>(A.rows.ep.weights) + off + b);
-        }
-      }
-    } else if (INVERSE) {
-      constexpr int LINES = COLS / 16;
-      const cplx* tb = A.y.data + (long long)it.plane * A.y.tile_stride + it.idx * COLS;
-      for (int i = threadIdx.x; i < NY * LINES; i += kRowThreads)
-        prefetch_l2(tb + (long long)(i / LINES) * A.y.row_stride + (i % LINES) * 16);
-    }
-  };
-
-  if (threadIdx.x == 0) s_ticket = atomicAdd(A.sync, 1u);
-  __syncthreads();
-  unsigned tk = s_ticket;
-  while (tk < total) {
-    __syncthreads();  // everybody has read s_ticket and is done with the shared-memory tile
-    if (threadIdx.x == 0) s_ticket = atomicAdd(A.sync, 1u);
-    __syncthreads();
-    const unsigned tk_next = s_ticket;
-    const XYItem it = decode(tk);
-    prefetch(decode(tk_next));
-    tk = tk_next;
-    if (it.plane < 0) continue;
-    if (!it.first) {
-      if (threadIdx.x == 0) plane_wait(done + it.plane, unsigned(INVERSE ? n_y : n_r), A.sync + 1);
-      __syncthreads();
-    }
-    if (it.is_rows) {
-      const long long row0 = (long long)it.plane * ny + (long long)it.idx * CF::ROWS + group * CF::RPG;
-      RowTwShared<M> T;
-      T.base = s_tw + lane;
-      if (INVERSE) rows_inv_group<M, EPI>(A.rows, slab, row0, lane, T);
-      else rows_fwd_group<M, WRAPPED>(A.rows, slab, row0, lane, T);
-    } else {
-      const int col = it.idx * COLS + c;
-      const long long base = (long long)it.plane * A.y.tile_stride + col;
-      strided_tile<NY, MODE, LMVN_Y_UNROLL>(A.y, sm + c, A.y.data + base, nullptr, col < A.y.ncols);
-    }
-    if (it.first) {
-      __syncthreads();
-      if (threadIdx.x == 0) plane_signal(done + it.plane);
-    }
-  }
-}
-
 }  // namespace fast
 }  // namespace lmvn

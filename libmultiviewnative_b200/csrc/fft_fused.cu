@@ -9,7 +9,7 @@
 // Inside the RL loop (ConvEngine::chain_*) rows_inv of one convolution and rows_fwd of the next are ONE kernel
 // (rows_inv_fwd), four launches per convolution.  Runtime knobs (environment, read when an engine is created) are
 // A/B switches of measured design decisions, see DESIGN.md section 3.1:
-//   LMVN_CHAIN=0           unchained loop              LMVN_XY_FUSED=1      persistent L2-resident x/y kernel
+//   LMVN_CHAIN=0           unchained loop
 //   LMVN_PREFETCH=<blocks> y-forward look-ahead (148)  LMVN_PREFETCH_ROWS=0 no next-iteration row prefetch
 //   LMVN_NXP_ALIGN=<n>     spectrum pitch alignment (8 complex elements)
 #include <algorithm>
@@ -19,7 +19,6 @@
 
 #include "engine.cuh"
 #include "fft_fast.cuh"
-#include "fft_fused_xy.cuh"
 
 namespace lmvn {
 
@@ -58,25 +57,17 @@ struct FastEngine : ConvEngine, FastOps {
   int y_fwd_prefetch = 148;  // blocks of look-ahead of the L2 prefetch in the forward y pass
   int khat_prefetch = 0;  // measured: hurts the z pass (plane-strided lines), kept as a knob
   int rows_prefetch = 1;
-  // fused x/y launches (fft_fused_xy.cu): ring of sync blocks, each cleared by the launch before it
-  bool xy_ok = false;
-  int xy_grid = 0, xy_lag = 0, xy_sync_words = 0;
-  unsigned xy_seq = 0;
-  unsigned* d_xy_sync = nullptr;
-  static const int kSyncRing = 4;
   cplx* d_tw_m = nullptr;
   cplx* d_tw_nx = nullptr;
   cplx* d_tw_h = nullptr;
   cplx* d_tw_y[2] = {nullptr, nullptr};  // per-stage tables of the y / z passes
   cplx* d_tw_z[2] = {nullptr, nullptr};
 
-  ~FastEngine() override {
-    if (d_xy_sync) cudaFree(d_xy_sync);
-  }
+  ~FastEngine() override {}
   int strategy() const override { return 2; }
   size_t khat_elems() const override { return size_t(plan->nz) * plan->ny * nxp; }
   size_t work_elems() const override { return khat_elems(); }
-  int launches_per_conv() const override { return xy_ok ? 3 : (can_chain() ? 4 : 5); }
+  int launches_per_conv() const override { return can_chain() ? 4 : 5; }
   unsigned long long S() const { return plan->voxels() * sizeof(float); }
   unsigned long long C() const { return plan->spec_elems() * sizeof(cplx); }
 
@@ -127,61 +118,6 @@ struct FastEngine : ConvEngine, FastOps {
     num_sms = tables->num_sms;
     d_tw_m = tables->tw_m; d_tw_nx = tables->tw_nx; d_tw_h = tables->tw_h;
     for (int i = 0; i < 2; ++i) { d_tw_y[i] = tables->tw_y[i]; d_tw_z[i] = tables->tw_z[i]; }
-    LMVN_TRY(init_xy());
-    return 0;
-  }
-
-  int init_xy() {
-    // Off by default: measured on B200, the L2-resident intermediate halves the HBM traffic of the
-    // x/y passes but not their time -- the L2 <-> SM fabric (~6.3 TB/s), not HBM, is what they saturate.
-    bool want = false;
-    if (const char* e = getenv("LMVN_XY_FUSED")) want = (*e != '0');
-    int ctas_per_sm = 0;
-    if (!want || !fast::xy_supported(M, plan->ny, &ctas_per_sm) || ctas_per_sm < 1) return 0;
-    xy_grid = num_sms * ctas_per_sm;
-    if (const char* e = getenv("LMVN_XY_GRID")) xy_grid = std::max(1, atoi(e));
-    const int per_step = fast::xy_items_per_plane(M, plan->ny, nxc);
-    xy_lag = (xy_grid + xy_grid / 4 + per_step - 1) / per_step + 1;
-    if (const char* e = getenv("LMVN_XY_LAG")) xy_lag = std::max(0, atoi(e));
-    xy_sync_words = (4 + plan->nz + 3) / 4 * 4;
-    const size_t bytes = sizeof(unsigned) * size_t(xy_sync_words) * kSyncRing;
-    LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_xy_sync), bytes));
-    LMVN_CUDA_TRY(cudaMemset(d_xy_sync, 0, bytes));
-    xy_ok = true;
-    return 0;
-  }
-
-  // x+y forward (src -> spec) or y+x inverse with epilogue (spec -> out / psi) in one persistent launch
-  int xy(const gen::RealSource* src, cplx* spec, float* out, const gen::Epilogue* ep, cudaStream_t s) {
-    const bool inverse = (src == nullptr);
-    fast::XYArgs a;
-    std::memset(&a, 0, sizeof(a));
-    if (src) a.rows.src = *src;
-    a.rows.spec = spec;
-    a.rows.out = out;
-    if (ep) a.rows.ep = *ep;
-    a.rows.nz = plan->nz; a.rows.ny = plan->ny; a.rows.nxp = nxp;
-    a.rows.tw_m = d_tw_m; a.rows.tw_nx = d_tw_nx;
-    a.y.data = spec;
-    a.y.khat = nullptr;
-    a.y.row_stride = nxp;
-    a.y.tile_stride = (long long)plan->ny * nxp;
-    a.y.ncols = nxc;
-    a.y.tw1 = d_tw_y[0]; a.y.tw2 = d_tw_y[1];
-    a.y.scale = 1.f;
-    a.y.prefetch = 0;
-    a.y.prefetch_khat = 0;
-    a.sync = d_xy_sync + size_t(xy_seq % kSyncRing) * xy_sync_words;
-    a.sync_next = d_xy_sync + size_t((xy_seq + 1) % kSyncRing) * xy_sync_words;
-    a.sync_words = xy_sync_words;
-    a.lag = xy_lag;
-    ++xy_seq;
-    LMVN_TRY(fast::launch_xy(M, plan->ny, inverse, a, xy_grid, s));
-    LMVN_CUDA_TRY(cudaGetLastError());
-    if (!inverse) mark("fast_xy_fwd", S() + C(), s);
-    else mark(ep->mode == gen::EPI_UPDATE ? "fast_yx_inv_update"
-                                          : (ep->mode == gen::EPI_QUOTIENT ? "fast_yx_inv_quotient" : "fast_yx_inv"),
-              C() + S() * (ep->mode == gen::EPI_UPDATE ? 3 : (ep->mode == gen::EPI_QUOTIENT ? 2 : 1)), s);
     return 0;
   }
 
@@ -515,7 +451,7 @@ struct FastEngine : ConvEngine, FastOps {
   // nx = 1024: the chained kernel exists but spills (keeps 32 results live through the epilogue) and measured
   // slower than the two separate passes; LMVN_CHAIN_WIDE=1 selects it for further work
   bool chain_wide = false;
-  bool can_chain() const override { return chain_ok && !xy_ok && (M <= 256 || chain_wide); }
+  bool can_chain() const override { return chain_ok && (M <= 256 || chain_wide); }
   int chain_begin(const float* in, cplx* work, cudaStream_t s) override {
     gen::RealSource src{in, 0, 0, 0, 0};
     return rows_fwd(src, work, s);
@@ -542,12 +478,6 @@ struct FastEngine : ConvEngine, FastOps {
   int convolve(const float* in, cplx* work, const cplx* khat, const gen::Epilogue& ep, float* out,
                cudaStream_t s) override {
     gen::RealSource src{in, 0, 0, 0, 0};
-    if (xy_ok) {
-      LMVN_TRY(xy(&src, work, nullptr, nullptr, s));
-      LMVN_TRY(strided(work, khat, 0, fast::SM_FWD_MUL_INV, 1.f, s));
-      LMVN_TRY(xy(nullptr, work, out, &ep, s));
-      return 0;
-    }
     LMVN_TRY(rows_fwd(src, work, s));
     LMVN_TRY(strided(work, nullptr, 1, fast::SM_FWD, 1.f, s));
     LMVN_TRY(strided(work, khat, 0, fast::SM_FWD_MUL_INV, 1.f, s));

@@ -164,21 +164,3 @@ def test_fused_equals_generic_closely(L):
         outs[strat] = psi
     L.set_default_strategy(capi.STRATEGY_AUTO)
     assert pc.max_rel(outs[capi.STRATEGY_FUSED], outs[capi.STRATEGY_GENERIC]) < 1e-5
-
-
-# ---- optional persistent x/y kernel (ticket-ordered items, per-plane counters) -------------
-@pytest.fixture()
-def LXY(LF, monkeypatch):
-    monkeypatch.setenv("LMVN_XY_FUSED", "1")
-    yield LF
-
-
-@pytest.mark.parametrize("dims,kdims", [((16, 128, 64), (5, 5, 5)), ((16, 128, 128), (3, 9, 5)), ((16, 256, 256), (3, 5, 7))])
-def test_xy_kernel_conv(LXY, dims, kdims):
-    with LXY.plan(dims, 1) as p:
-        assert p.info().launches_per_view_iteration == 6
-    pc.case_conv_random_vs_oracle(LXY, dims, kdims)
-
-
-def test_xy_kernel_deconvolve(LXY):
-    pc.case_deconvolve_vs_oracle(LXY, (16, 128, 64), 2, 5, 0.006, iters_list=(1, 2), n_sources=8)

@@ -192,25 +192,6 @@ def test_full_size_properties(L):
     assert pc.rel_l2(sh, np.roll(ca, (3, -5, 7), axis=(0, 1, 2))) < 2e-6
 
 
-# ---- optional persistent x/y kernel (LMVN_XY_FUSED=1; read when a plan is created) ---------
-@pytest.fixture()
-def LXY(L, monkeypatch):
-    monkeypatch.setenv("LMVN_XY_FUSED", "1")
-    yield L
-
-
-@pytest.mark.parametrize("dims,kdims", [((64, 128, 64), (9, 9, 9)), ((32, 256, 128), (5, 7, 3)),
-                                        ((16, 512, 256), (3, 41, 5)), ((256, 128, 128), (41, 41, 41))])
-def test_xy_kernel_conv_vs_oracle(LXY, dims, kdims):
-    with LXY.plan(dims, 1) as p:
-        assert p.info().launches_per_view_iteration == 6  # 3 launches per convolution
-    pc.case_conv_random_vs_oracle(LXY, dims, kdims)
-
-
-def test_xy_kernel_deconvolve_config1(LXY):
-    pc.case_deconvolve_vs_oracle(LXY, (128, 128, 128), 3, 31, 0.006, iters_list=(1, 10), n_sources=200)
-
-
 # ---- one volume over several ranks (slab-decomposed plans), all ranks on this GPU ------------
 @pytest.mark.parametrize("dims,world", [((64, 64, 64), 2), ((128, 128, 128), 4), ((256, 256, 256), 8)])
 def test_slab_group_equals_single_plan(L, dims, world, monkeypatch):
