@@ -97,6 +97,8 @@ struct StridedGeom {
   int mode = 0;                // fast::StridedMode
   float scale = 1.f;
   Scatter sc{};                // SM_*_SCATTER
+  cplx* nyq = nullptr;         // split layout: Nyquist plane of `data` (nullptr: the column is inside the rows)
+  const cplx* nyq_khat = nullptr;
 };
 struct FastOps {
   virtual ~FastOps() {}

@@ -211,6 +211,17 @@ struct StridedArgs {
   int prefetch;           // > 0: every CTA first pulls the tile of block (id + prefetch) into L2
   int prefetch_khat;      // SM_FWD_MUL_INV: pull the CTA's own K^ tile into L2 at kernel entry
   Scatter sc;             // SM_*_SCATTER
+  // Split layout (single-device engine): the half spectrum is stored as nx/2 columns per row -- a whole number of
+  // tiles, rows of whole 128-byte lines, no pitch padding -- plus the Nyquist column kx = nx/2 as a compact plane
+  // nyq[z'][y'].  The launch is then a flat grid: the first nyq_groups CTAs transform the Nyquist plane (a "column" of
+  // such a CTA is one slow index; element (row r, slow s) sits at nyq + r * nyq_rs + s * nyq_cs), the others are the
+  // tiles_x x slow ordinary tiles.  nyq_groups < 0: 2-D grid (tile, slow), Nyquist column inside the rows.
+  cplx* nyq;
+  const cplx* nyq_khat;
+  int nyq_groups;
+  int nyq_rs, nyq_cs;
+  int tiles_x;
+  unsigned slow;
 };
 
 // number of stages and the radix of stage s for N = R1*R2*R3
@@ -382,7 +393,7 @@ struct Middle {
 // touches the thread's own column only) but still take part in the barriers.
 template <int N, int MODE_, int U>
 __device__ __forceinline__ void strided_tile(const StridedArgs& A, cplx* sm, cplx* g, const cplx* gk, bool live,
-                                             long long sc_tile = 0) {
+                                             long long sc_tile, int rs) {
   typedef Radix<N> RX;
   constexpr int COLS = Cols<N>::V;
   constexpr int R1 = RX::R1, R2 = RX::R2;
@@ -392,7 +403,6 @@ __device__ __forceinline__ void strided_tile(const StridedArgs& A, cplx* sm, cpl
   constexpr int MODE = (MODE_ == SM_FWD_SCATTER) ? SM_FWD : (MODE_ == SM_FWD_MUL_INV_SCATTER ? SM_FWD_MUL_INV : MODE_);
   constexpr int DSTG = SCAT ? W_SCATTER : ((MODE == SM_FWD_SCALE) ? W_GLOBAL_SCALED : W_GLOBAL);
   const Scatter* sc = &A.sc;
-  const int rs = A.row_stride;
   if (MODE == SM_FWD || MODE == SM_FWD_SCALE) {
     if (live) strided_stage<N, R1, N, COLS, false, W_GLOBAL, W_SMEM, U>(sm, g, rs, A.tw1, 1.f);
     __syncthreads();
@@ -443,31 +453,47 @@ static __global__ void __launch_bounds__(Threads<N>::V, StridedBlocks<N, MODE>::
   constexpr int COLS = Cols<N>::V;
   LMVN_DYN_SMEM(cplx, smem);  // [N][COLS]
   const int c = threadIdx.x % COLS;
-  const int col = blockIdx.x * COLS + c;
   constexpr bool ZMUL = (MODE == SM_FWD_MUL_INV || MODE == SM_FWD_MUL_INV_SCATTER);
-  const long long base = (long long)blockIdx.y * A.tile_stride + col;
   constexpr int U = ZMUL ? LMVN_ZMUL_UNROLL : LMVN_Y_UNROLL;
+  constexpr int LINES = (COLS + 15) / 16;  // 128-byte lines per tile row
+  unsigned bx = blockIdx.x, by = blockIdx.y;
+  long long n_tiles = (long long)gridDim.x * gridDim.y, tile_id = (long long)by * gridDim.x + bx;
+  unsigned tiles_x = gridDim.x;
+  if (A.nyq_groups >= 0) {
+    if (int(blockIdx.x) < A.nyq_groups) {
+      // Nyquist plane: this thread's column is slow index s (the plane is small and L2 resident)
+      const unsigned s = blockIdx.x * COLS + c;
+      const long long nb = (long long)s * A.nyq_cs;
+      strided_tile<N, MODE, U>(A, smem + c, A.nyq + nb, A.nyq_khat + nb, s < A.slow, 0, A.nyq_rs);
+      return;
+    }
+    tiles_x = unsigned(A.tiles_x);
+    tile_id = (long long)blockIdx.x - A.nyq_groups;
+    n_tiles = (long long)tiles_x * A.slow;
+    bx = unsigned(tile_id % tiles_x);
+    by = unsigned(tile_id / tiles_x);
+  }
+  const int col = bx * COLS + c;
+  const long long base = (long long)by * A.tile_stride + col;
   if (ZMUL && A.prefetch_khat) {
     // K^ is first needed two stages from now: start its trip from HBM to L2 right away
-    constexpr int LINES = (COLS + 15) / 16;
-    const long long tb = (long long)blockIdx.y * A.tile_stride + blockIdx.x * COLS;
+    const long long tb = (long long)by * A.tile_stride + bx * COLS;
     for (int i = threadIdx.x; i < N * LINES; i += Threads<N>::V)
       prefetch_l2(A.khat + tb + (long long)(i / LINES) * A.row_stride + (i % LINES) * 16);
   }
   if (A.prefetch > 0) {
     // the block that will take this CTA's slot next: its loads then hit L2 instead of waiting for HBM
-    const long long id = (long long)blockIdx.y * gridDim.x + blockIdx.x + A.prefetch;
-    if (id < (long long)gridDim.x * gridDim.y) {
-      const long long fb = (id / gridDim.x) * A.tile_stride + (id % gridDim.x) * COLS;
-      constexpr int LINES = (COLS + 15) / 16;  // 128-byte lines per tile row
+    const long long id = tile_id + A.prefetch;
+    if (id < n_tiles) {
+      const long long fb = (id / tiles_x) * A.tile_stride + (id % tiles_x) * COLS;
       for (int i = threadIdx.x; i < N * LINES; i += Threads<N>::V) {
         const long long off = fb + (long long)(i / LINES) * A.row_stride + (i % LINES) * 16;
         prefetch_l2(A.data + off);
       }
     }
   }
-  const long long sc_tile = A.sc.offset + (long long)blockIdx.y * A.sc.tile_stride + col;
-  strided_tile<N, MODE, U>(A, smem + c, A.data + base, A.khat + base, col < A.ncols, sc_tile);
+  const long long sc_tile = A.sc.offset + (long long)by * A.sc.tile_stride + col;
+  strided_tile<N, MODE, U>(A, smem + c, A.data + base, A.khat + base, col < A.ncols, sc_tile, A.row_stride);
 }
 
 // ------------------------------------------------------------------------------
@@ -497,6 +523,7 @@ struct RowArgs {
   int prefetch;          // pull the next loop iteration's rows into L2 one iteration ahead
   int z0, nz_wrap;       // wrapped source on a slab of planes: global index of plane 0, global nz
   const cplx* tw_h;      // nx = 1024 only: w_{M/2} table (M/2 entries) of the two half-length sub-transforms
+  cplx* nyq;             // split layout: X[nx/2] of row r lives at nyq[r] instead of spec[r * nxp + nx/2]
 };
 
 // a + conj(b) and a - conj(b): one packed FFMA2 each on sm_100
@@ -663,7 +690,7 @@ __device__ __forceinline__ void rows_fwd_from_regs(const RowArgs& A, cplx* slab,
       if (k == 0) {
         const cplx z0 = zr[0];
         st_stream(orow, cmake(z0.x + z0.y, 0.f));
-        st_stream(orow + M, cmake(z0.x - z0.y, 0.f));
+        st_stream(A.nyq ? A.nyq + (row0 + a) : orow + M, cmake(z0.x - z0.y, 0.f));
         st_stream(orow + M / 2, cconj(zr[M / 2]));
       } else {
         cplx xk, xm;
@@ -698,7 +725,7 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
     for (int i = 0; i < PAIRS; ++i) {
       const int k = lane + 16 * i;
       xs[a * PAIRS + i] = ld_stream(irow + k);
-      xm[a * PAIRS + i] = ld_stream(irow + (M - k));  // k = 0 reads X[M]
+      xm[a * PAIRS + i] = ld_stream((k == 0 && A.nyq) ? A.nyq + (row0 + a) : irow + (M - k));  // k = 0 reads X[M]
     }
     if (lane == 0) xh[a] = ld_stream(irow + M / 2);
   }
@@ -993,7 +1020,7 @@ __device__ __forceinline__ void rows_fwd_wide_from_regs(const RowArgs& A, cplx* 
       const cplx e0 = se[0], o0 = so[0];
       const cplx z0 = cadd(e0, o0), zh = csub(e0, o0);  // Z[0], Z[256]
       st_stream(orow, cmake(z0.x + z0.y, 0.f));
-      st_stream(orow + M, cmake(z0.x - z0.y, 0.f));
+      st_stream(A.nyq ? A.nyq + row : orow + M, cmake(z0.x - z0.y, 0.f));
       st_stream(orow + H, cconj(zh));
     } else {
       const cplx w5 = __ldg(A.tw_m + k);  // w_512^k
@@ -1017,7 +1044,7 @@ __device__ __forceinline__ void rows_inv_wide_group(const RowArgs& A, cplx* slab
   for (int i = 0; i < 16; ++i) {
     const int k = lane + 16 * i;
     const cplx xk = ld_stream(irow + k);
-    const cplx xm = ld_stream(irow + (M - k));  // k = 0 reads X[512]
+    const cplx xm = ld_stream((k == 0 && A.nyq) ? A.nyq + row : irow + (M - k));  // k = 0 reads X[512]
     if (k == 0) {
       const cplx xh = ld_stream(irow + H);
       slab[0] = cmake(xk.x + xm.x, xk.x - xm.x);  // imaginary parts ignored (c2r)

@@ -52,6 +52,9 @@ struct FastEngine : ConvEngine, FastOps {
   std::shared_ptr<FastTables> tables;
   int M = 0, nxc = 0, nxp = 0;
   int num_sms = 148;
+  // split layout: nx/2 columns per spectrum row + the Nyquist column as a compact plane behind them (see
+  // fast::StridedArgs); false for the slab-decomposed engine, which scatters whole rows between devices
+  bool split = true;
   int rows_ctas_per_sm = 8;
   int update_ctas_per_sm = 64;
   int y_fwd_prefetch = 148;  // blocks of look-ahead of the L2 prefetch in the forward y pass
@@ -65,7 +68,10 @@ struct FastEngine : ConvEngine, FastOps {
 
   ~FastEngine() override {}
   int strategy() const override { return 2; }
-  size_t khat_elems() const override { return size_t(plan->nz) * plan->ny * nxp; }
+  size_t main_elems() const { return size_t(plan->nz) * plan->ny * nxp; }
+  size_t khat_elems() const override { return main_elems() + (split ? size_t(plan->nz) * plan->ny : 0); }
+  cplx* nyq_of(cplx* spec) const { return split ? spec + main_elems() : nullptr; }
+  const cplx* nyq_of(const cplx* spec) const { return split ? spec + main_elems() : nullptr; }
   size_t work_elems() const override { return khat_elems(); }
   int launches_per_conv() const override { return can_chain() ? 4 : 5; }
   unsigned long long S() const { return plan->voxels() * sizeof(float); }
@@ -90,7 +96,8 @@ struct FastEngine : ConvEngine, FastOps {
       // 32-byte sectors, and the pitch (129 -> 136 instead of 144) moves 5.5 % fewer spectrum bytes (+1.2 % measured)
       int align = 8;
       if (const char* e = getenv("LMVN_NXP_ALIGN")) align = std::max(1, atoi(e));
-      nxp = (nxc + align - 1) / align * align;
+      if (const char* e = getenv("LMVN_SPLIT_NYQUIST")) split = split && (*e != '0');
+      nxp = split ? M : (nxc + align - 1) / align * align;
     }
     if (const char* e = getenv("LMVN_PREFETCH")) y_fwd_prefetch = std::max(0, atoi(e));
     if (const char* e = getenv("LMVN_PREFETCH_KHAT")) khat_prefetch = atoi(e);
@@ -255,6 +262,7 @@ struct FastEngine : ConvEngine, FastOps {
     a.prefetch = rows_prefetch;
     a.z0 = wrap_z0; a.nz_wrap = wrap_nz > 0 ? wrap_nz : plan->nz;
     a.tw_h = d_tw_h;
+    a.nyq = split ? nyq_of(spec) + size_t(z0) * plan->ny : nullptr;
     const bool w = src.wrapped != 0;
     switch (M) {
       case 32: LMVN_TRY(launch_rows_fwd2<32>(a, w, s)); break;
@@ -289,6 +297,7 @@ struct FastEngine : ConvEngine, FastOps {
     a.tw_m = d_tw_m; a.tw_nx = d_tw_nx;
     a.prefetch = rows_prefetch;
     a.tw_h = d_tw_h;
+    a.nyq = split ? const_cast<cplx*>(nyq_of(spec)) + size_t(z0) * plan->ny : nullptr;
     switch (M) {
       case 32: LMVN_TRY(launch_rows_inv2<32>(a, s)); break;
       case 64: LMVN_TRY(launch_rows_inv2<64>(a, s)); break;
@@ -332,6 +341,10 @@ struct FastEngine : ConvEngine, FastOps {
               int nzs = -1) {
     const FftPlan& p = *plan;
     StridedGeom g;
+    if (split) {
+      g.nyq = nyq_of(data) + ((axis == 1 && nzs >= 0) ? size_t(z0) * p.ny : 0);
+      g.nyq_khat = khat ? nyq_of(khat) : nullptr;
+    }
     if (axis == 1 && nzs >= 0) data += size_t(z0) * p.ny * nxp;  // y pass on a slab of planes
     g.data = data;
     g.khat = khat;
@@ -351,11 +364,21 @@ struct FastEngine : ConvEngine, FastOps {
     std::memset(&a, 0, sizeof(a));
     a.data = g.data;
     a.khat = g.khat;
-    a.ncols = nxc;
+    a.ncols = g.nyq ? M : nxc;
     a.scale = g.scale;
     a.row_stride = g.row_stride;
     a.tile_stride = g.tile_stride;
     a.sc = g.sc;
+    a.nyq_groups = -1;
+    a.slow = g.slow;
+    if (g.nyq) {
+      // Nyquist plane nyq[z'][y']: the y pass walks it along y' (row stride 1) with z as the slow index, the z
+      // pass along z (row stride ny) with y' as the slow index
+      a.nyq = g.nyq;
+      a.nyq_khat = g.nyq_khat;
+      a.nyq_rs = (g.tw_axis == 1) ? 1 : plan->ny;
+      a.nyq_cs = (g.tw_axis == 1) ? plan->ny : 1;
+    }
     const int mode = g.mode;
     a.prefetch = (g.tw_axis == 1 && mode == fast::SM_FWD) ? y_fwd_prefetch : 0;
     a.prefetch_khat = khat_prefetch;
@@ -369,7 +392,12 @@ struct FastEngine : ConvEngine, FastOps {
     int rc;
 #define LMVN_STRIDED_CASE(NN)                                                                   \
   case NN: {                                                                                    \
-    const dim3 grid(unsigned(ceil_div(size_t(nxc), size_t(fast::Cols<NN>::V))), slow);          \
+    dim3 grid(unsigned(ceil_div(size_t(nxc), size_t(fast::Cols<NN>::V))), slow);                \
+    if (g.nyq) {                                                                                \
+      a.tiles_x = int(ceil_div(size_t(M), size_t(fast::Cols<NN>::V)));                          \
+      a.nyq_groups = int(ceil_div(size_t(slow), size_t(fast::Cols<NN>::V)));                    \
+      grid = dim3(unsigned(a.nyq_groups) + unsigned(a.tiles_x) * slow);                         \
+    }                                                                                           \
     rc = launch_strided_mode<NN>(a, mode, grid, s);                                             \
   } break;
     switch (g.n) {
@@ -419,6 +447,7 @@ struct FastEngine : ConvEngine, FastOps {
     a.nz = nzs >= 0 ? nzs : plan->nz; a.ny = plan->ny; a.nxp = nxp;
     a.tw_m = d_tw_m; a.tw_nx = d_tw_nx; a.tw_h = d_tw_h;
     a.prefetch = rows_prefetch;
+    a.nyq = split ? nyq_of(spec) : nullptr;
     switch (M) {
       case 32: LMVN_TRY(launch_rows_inv_fwd<32>(a, s)); break;
       case 64: LMVN_TRY(launch_rows_inv_fwd<64>(a, s)); break;
@@ -501,6 +530,7 @@ std::unique_ptr<FastOps> make_fast_ops(std::shared_ptr<FftPlan> plan) {
   }
   std::unique_ptr<FastEngine> e(new FastEngine());
   e->plan = plan;
+  e->split = false;  // whole spectrum rows travel between the devices
   if (cudaSetDevice(plan->device) != cudaSuccess) return nullptr;
   if (e->init() != 0) return nullptr;
   return std::unique_ptr<FastOps>(e.release());
