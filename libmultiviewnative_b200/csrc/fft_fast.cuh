@@ -943,9 +943,7 @@ __device__ __forceinline__ void rows_fwd_wide_from_regs(const RowArgs& A, cplx* 
 
 template <bool WRAPPED>
 __device__ __forceinline__ void rows_fwd_wide_group(const RowArgs& A, cplx* slab, long long row, int lane) {
-  constexpr int H = RowWide::H, M = RowWide::M, nx = RowWide::NX, RS = RowWide::RS;
-  cplx* se = slab;
-  cplx* so = slab + RS;
+  constexpr int nx = RowWide::NX;
   cplx ve[16], vo[16];
   if (!WRAPPED) {
     const float4* in = reinterpret_cast<const float4*>(A.src.data + row * nx);

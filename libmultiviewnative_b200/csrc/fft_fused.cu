@@ -24,8 +24,6 @@ namespace lmvn {
 
 namespace {
 
-bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
-
 // twiddle tables + device facts, cached on the FftPlan (process-wide store): creating an engine for a
 // shape that has been seen before makes no CUDA allocation and no synchronous copy
 struct FastTables {
