@@ -1183,15 +1183,19 @@ static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_inv_wide(RowArgs
   }
 }
 
+// 128 threads per CTA, three CTAs per SM: 170 registers per thread -- the chained form keeps 32 results of the
+// inverse live through the epilogue and spills at 128
+static const int kChainWideThreads = 128;
 template <int EPI>
-static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_inv_fwd_wide(RowArgs A) {
+static __global__ void __launch_bounds__(kChainWideThreads, 3) k_rows_inv_fwd_wide(RowArgs A) {
   LMVN_DYN_SMEM(cplx, sm);
+  constexpr int GROUPS = kChainWideThreads / 16;
   const int lane = threadIdx.x % 16;
   const int group = threadIdx.x / 16;
   cplx* slab = sm + group * RowWide::SLAB;
   const long long rows = (long long)A.nz * A.ny;
-  const long long stride = (long long)gridDim.x * RowWide::ROWS;
-  for (long long row = (long long)blockIdx.x * RowWide::ROWS + group; row < rows; row += stride) {
+  const long long stride = (long long)gridDim.x * GROUPS;
+  for (long long row = (long long)blockIdx.x * GROUPS + group; row < rows; row += stride) {
     if (A.prefetch && row + stride < rows) {
       const long long nr = row + stride;
       const char* sp = reinterpret_cast<const char*>(A.spec + nr * A.nxp);

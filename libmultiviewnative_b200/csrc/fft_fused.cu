@@ -453,16 +453,17 @@ struct FastEngine : ConvEngine, FastOps {
       case 256: LMVN_TRY(launch_rows_inv_fwd<256>(a, s)); break;
       case 512: {
         const size_t rows = size_t(a.nz) * plan->ny;
-        const dim3 grid(unsigned(std::min<size_t>(ceil_div(rows, fast::RowWide::ROWS), size_t(num_sms) * rows_ctas_per_sm)));
-        const size_t smem = fast::RowWide::SMEM;
+        const int groups = fast::kChainWideThreads / 16;
+        const dim3 grid(unsigned(std::min<size_t>(ceil_div(rows, size_t(groups)), size_t(num_sms) * 24)));
+        const size_t smem = size_t(groups) * fast::RowWide::SLAB * sizeof(cplx);
         auto k1 = fast::k_rows_inv_fwd_wide<gen::EPI_QUOTIENT>;
         auto k2 = fast::k_rows_inv_fwd_wide<gen::EPI_UPDATE>;
         LMVN_CUDA_TRY(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         LMVN_CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         if (a.ep.mode == gen::EPI_QUOTIENT) {
-          LMVN_LAUNCH(k1, grid, dim3(fast::kRowThreads), smem, s, a);
+          LMVN_LAUNCH(k1, grid, dim3(fast::kChainWideThreads), smem, s, a);
         } else {
-          LMVN_LAUNCH(k2, grid, dim3(fast::kRowThreads), smem, s, a);
+          LMVN_LAUNCH(k2, grid, dim3(fast::kChainWideThreads), smem, s, a);
         }
       } break;
       default: set_last_error("chained rows pass: unsupported nx"); return -1;
@@ -475,9 +476,9 @@ struct FastEngine : ConvEngine, FastOps {
   }
 
   bool chain_ok = true;
-  // nx = 1024: the chained kernel exists but spills (keeps 32 results live through the epilogue) and measured
-  // slower than the two separate passes; LMVN_CHAIN_WIDE=1 selects it for further work
-  bool chain_wide = false;
+  // nx = 1024: the chained kernel runs 128-thread CTAs (170 registers per thread: it keeps 32 results live through
+  // the epilogue); +3 % over the two separate passes (LMVN_CHAIN_WIDE=0 for A/B)
+  bool chain_wide = true;
   bool can_chain() const override { return chain_ok && (M <= 256 || chain_wide); }
   int chain_begin(const float* in, cplx* work, cudaStream_t s) override {
     gen::RealSource src{in, 0, 0, 0, 0};
