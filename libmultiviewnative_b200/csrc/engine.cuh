@@ -145,6 +145,15 @@ struct Deconv {
   // zero_padd mode (ref: inc/padd_utils.h:102-249, src/gpu_deconvolve_methods.cuh:366-449): the plan works on
   // `dims` = image + kernel - 1 (rounded up to a fast-path extent), the caller's stacks have `logical` extents
   // and sit at `offset` = (kernel - 1) / 2 inside it; uploads zero-fill, downloads crop.
+  // CUDA graph of one sweep over all views (chained loop), replayed for every iteration but the last
+#ifndef LMVN_EMU
+  cudaGraphExec_t sweep_graph = nullptr;
+#endif
+  bool use_graph = true;
+  double graph_lambda = 0.0;
+  float graph_min = 0.f;
+  const float* graph_psi = nullptr;
+
   bool padded = false;
   int logical[3] = {0, 0, 0};
   int offset[3] = {0, 0, 0};
