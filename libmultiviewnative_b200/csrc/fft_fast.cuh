@@ -593,7 +593,7 @@ struct RowTwShared {
   const cplx* base;  // + lane
   // all threads of the block call fill(), then __syncthreads()
   static __device__ __forceinline__ void fill(cplx* table, const RowArgs& A) {
-    for (int i = threadIdx.x; i < ENTRIES * 16; i += kRowThreads) {
+    for (int i = threadIdx.x; i < ENTRIES * 16; i += blockDim.x) {
       const int e = i / 16, l = i % 16;
       table[i] = (e < Row2Cfg<M>::R1) ? __ldg(A.tw_m + l * e) : __ldg(A.tw_nx + l + 16 * (e - Row2Cfg<M>::R1));
     }
@@ -871,9 +871,19 @@ static __global__ void __launch_bounds__(kRowThreads, EPI == gen::EPI_UPDATE ? 2
 }
 
 // inverse x + pointwise + forward x of the next convolution, in place on the spectrum rows
+// CTA shape of the chained kernels: four CTAs of 128 threads per SM instead of two of 256 -- the same 16 warps, but
+// finer units for the hardware CTA scheduler (measured: update link 0.246 -> 0.234 ms, quotient link 0.147 -> 0.143)
+#ifndef LMVN_LINK_THREADS
+#define LMVN_LINK_THREADS 128
+#endif
+#ifndef LMVN_LINK_BLOCKS
+#define LMVN_LINK_BLOCKS 4
+#endif
+static const int kLinkThreads = LMVN_LINK_THREADS;
 template <int M, int EPI>
-static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_inv_fwd(RowArgs A) {
+static __global__ void __launch_bounds__(kLinkThreads, LMVN_LINK_BLOCKS) k_rows_inv_fwd(RowArgs A) {
   typedef Row2Cfg<M> CF;
+  constexpr int GROUPS = kLinkThreads / 16;
   LMVN_DYN_SMEM(cplx, sm);
   __shared__ cplx s_tw[RowTwShared<M>::ENTRIES * 16];
   const int lane = threadIdx.x % 16;
@@ -884,8 +894,8 @@ static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_inv_fwd(RowArgs 
   __syncthreads();
   RowTwShared<M> T;
   T.base = s_tw + lane;
-  const long long stride = (long long)gridDim.x * CF::ROWS;
-  for (long long row0 = ((long long)blockIdx.x * CF::GROUPS + group) * CF::RPG; row0 < rows; row0 += stride) {
+  const long long stride = (long long)gridDim.x * GROUPS * CF::RPG;
+  for (long long row0 = ((long long)blockIdx.x * GROUPS + group) * CF::RPG; row0 < rows; row0 += stride) {
     if (A.prefetch && row0 + stride < rows) {
       const long long nr = row0 + stride;
       const char* sp = reinterpret_cast<const char*>(A.spec + nr * A.nxp);

@@ -177,18 +177,19 @@ struct FastEngine : ConvEngine, FastOps {
   int launch_rows_inv_fwd(const fast::RowArgs& a, cudaStream_t s) {
     typedef fast::Row2Cfg<MM> CF;
     const size_t rows = size_t(a.nz) * plan->ny;
-    const size_t iters = ceil_div(rows, CF::ROWS);
+    const int groups = fast::kLinkThreads / 16;
+    const size_t iters = ceil_div(rows, size_t(groups) * CF::RPG);
     // measured: the update link (four streams per row) runs best with one loop iteration per CTA, i.e. left to the
     // hardware CTA scheduler (0.268 -> 0.242 ms on config 3); the quotient link with a persistent loop of ~7 iterations
     const int per_sm = (a.ep.mode == gen::EPI_UPDATE) ? update_ctas_per_sm : rows_ctas_per_sm;
-    const dim3 grid(unsigned(std::min<size_t>(iters, size_t(num_sms) * per_sm)));
-    const size_t smem = size_t(CF::GROUPS) * CF::RPG * CF::RS * sizeof(cplx);
+    const dim3 grid(unsigned(std::min<size_t>(iters, size_t(num_sms) * per_sm * (fast::kRowThreads / fast::kLinkThreads))));
+    const size_t smem = size_t(groups) * CF::RPG * CF::RS * sizeof(cplx);
     auto k1 = fast::k_rows_inv_fwd<MM, gen::EPI_QUOTIENT>;
     auto k2 = fast::k_rows_inv_fwd<MM, gen::EPI_UPDATE>;
     if (a.ep.mode == gen::EPI_QUOTIENT) {
-      LMVN_LAUNCH(k1, grid, dim3(fast::kRowThreads), smem, s, a);
+      LMVN_LAUNCH(k1, grid, dim3(fast::kLinkThreads), smem, s, a);
     } else {
-      LMVN_LAUNCH(k2, grid, dim3(fast::kRowThreads), smem, s, a);
+      LMVN_LAUNCH(k2, grid, dim3(fast::kLinkThreads), smem, s, a);
     }
     return 0;
   }
