@@ -1,30 +1,26 @@
 // fft_fast.cuh -- power-of-two fast path of the in-house 3-D R2C/C2R convolution.
 //
-// Why it looks the way it does (B200 numbers): one SM's fair share of HBM is
-// ~23 B/clk while its shared-memory/L1 pipe moves 128 B/clk, so a transform that
-// bounces every byte through shared memory five or six times is limited by the
-// on-chip pipe, not by HBM.  Hence:
-//   * butterflies are radix-8 / radix-16 held in REGISTERS, so a 512-point axis
-//     needs two shared-memory exchanges and a 256-point real row needs one;
-//   * the first stage of every pass loads straight from global memory into
-//     registers and the last stage stores straight from registers -- shared
-//     memory only carries the inter-stage exchanges;
-//   * strided (y, z) passes work on tiles of 16 adjacent kx columns, i.e. every
-//     global access of a half-warp is one full, aligned 128-byte line;
-//   * forward passes are decimation-in-frequency (natural in, digit-reversed
-//     out), inverse passes decimation-in-time (digit-reversed in, natural out);
-//     the spectrum lives in HBM in digit-reversed (y, z) order and is never
-//     unscrambled -- the PSF spectra are produced by the same passes, so the
-//     pointwise product is order-agnostic;
-//   * the pointwise work of the iteration is fused into the pass edges: kernel
-//     wrap-around into the first pass's loads (ref: inc/padd_utils.h:11-40), the
-//     1/N scale into K^ (ref: inc/cpu_convolve.h:271-278), the spectrum product
-//     between the last forward and first inverse z stage (ref:
-//     inc/cpu_convolve.h:257-266), quotient / RL update into the last pass's
-//     stores (ref: inc/cpu_kernels.h:19-90).
-//
-// Spectrum layout: [z'][y'][kx] complex64, row pitch nxp = roundup(nx/2+1, 16)
-// so that every 16-column tile starts on a 128-byte line.
+// Why it looks the way it does (B200 numbers, all measured): one SM's fair share of HBM is
+// ~23 B/clk while its shared-memory/L1 pipe moves 128 B/clk and it holds only 16 warps of these kernels, so a
+// transform that bounces every byte through shared memory five or six times, or that spends instructions on
+// address arithmetic and range-checked divisions, is limited on chip, not by HBM.  Hence:
+//   * butterflies are radix-8 / 16 / 32 held in REGISTERS: a 512-point axis needs ONE shared-memory exchange
+//     (32 x 16), a 256-point real row two warp-private ones;
+//   * the first stage of every pass loads straight from global memory into registers and the last stage stores
+//     straight from registers -- shared memory only carries the inter-stage exchanges; every strided access costs
+//     one IMAD.WIDE (opaque pointer bump), not five integer instructions;
+//   * strided (y, z) passes work on tiles of 16 adjacent kx columns, i.e. every global access of a half-warp is one
+//     full 128-byte line; the spectrum is stored as nx/2 columns per row (whole tiles, whole lines) plus the Nyquist
+//     column as a compact plane that the first CTAs of each launch transform;
+//   * forward passes are decimation-in-frequency (natural in, digit-reversed out), inverse passes
+//     decimation-in-time (digit-reversed in, natural out); the spectrum lives in HBM in digit-reversed (y, z) order
+//     and is never unscrambled -- the PSF spectra are produced by the same passes, so the pointwise product is
+//     order-agnostic;
+//   * the pointwise work of the iteration is fused into the pass edges: kernel wrap-around into the first pass's
+//     loads (ref: inc/padd_utils.h:11-40), the 1/N scale into K^ (ref: inc/cpu_convolve.h:271-278), the spectrum
+//     product between the last forward and first inverse z stage (ref: inc/cpu_convolve.h:257-266), quotient / RL
+//     update into the x-inverse pass (ref: inc/cpu_kernels.h:19-90) -- which, inside the loop, also runs the
+//     x-forward pass of the NEXT convolution on the same rows (k_rows_inv_fwd), so the quotient never reaches HBM.
 #pragma once
 #include "fft_types.cuh"
 #include "lmvn_common.cuh"
