@@ -59,9 +59,15 @@ size_t align_up_(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // Cross-GPU barrier: every rank raises its flag in every peer's exchange region, then waits for
 // all of its own flags.  One CTA, one thread per peer.  Bounded spin: a lost peer must not hang
 // the device (the error flag is reported by the next host call).
-__global__ void k_peer_barrier(unsigned* const* peer_flags, unsigned* my_flags, int rank, int world, unsigned epoch,
+__global__ void k_peer_barrier(unsigned* const* peer_flags, unsigned* my_flags, int rank, int world, unsigned* epoch_counter,
                                unsigned* err) {
 #ifndef LMVN_EMU
+  // the epoch lives on the device (every rank launches the same sequence of barriers), so that a captured
+  // launch sequence can be replayed as a CUDA graph
+  __shared__ unsigned s_epoch;
+  if (threadIdx.x == 0) s_epoch = ++(*epoch_counter);
+  __syncthreads();
+  const unsigned epoch = s_epoch;
   const int t = threadIdx.x;
   if (t < world) {
     __threadfence_system();
@@ -80,7 +86,7 @@ __global__ void k_peer_barrier(unsigned* const* peer_flags, unsigned* my_flags, 
     __threadfence_system();
   }
 #else
-  (void)peer_flags; (void)my_flags; (void)rank; (void)world; (void)epoch; (void)err;
+  (void)peer_flags; (void)my_flags; (void)rank; (void)world; (void)epoch_counter; (void)err;
 #endif
 }
 
@@ -107,7 +113,13 @@ struct DistDeconv {
   unsigned char* peer[kMaxRanks] = {nullptr};
   bool peer_ipc[kMaxRanks] = {false};
   bool multi_process = false;
-  unsigned epoch = 0;
+  unsigned* d_epoch = nullptr;  // device-side barrier epoch
+#ifndef LMVN_EMU
+  cudaGraphExec_t sweep_graph = nullptr;  // one sweep over all views of the chained loop
+#endif
+  bool use_graph = true;
+  double graph_lambda = 0.0;
+  float graph_min = 0.f;
   unsigned** d_peer_flags = nullptr;  // device array of kMaxRanks pointers
   unsigned* d_err = nullptr;
   // comparator: exchanges staged through local buffers and moved by the caller (NCCL all-to-all)
@@ -162,6 +174,10 @@ struct DistDeconv {
     if (stage_recv) cudaFree(stage_recv);
     if (d_peer_flags) cudaFree(d_peer_flags);
     if (d_err) cudaFree(d_err);
+    if (d_epoch) cudaFree(d_epoch);
+#ifndef LMVN_EMU
+    if (sweep_graph) cudaGraphExecDestroy(sweep_graph);
+#endif
     if (arena) cudaFree(arena);
 #ifndef LMVN_EMU
     if (xchg) cudaFree(xchg);
@@ -219,6 +235,9 @@ struct DistDeconv {
     LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_peer_flags), sizeof(unsigned*) * kMaxRanks));
     LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_err), sizeof(unsigned)));
     LMVN_CUDA_TRY(cudaMemset(d_err, 0, sizeof(unsigned)));
+    LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_epoch), sizeof(unsigned)));
+    LMVN_CUDA_TRY(cudaMemset(d_epoch, 0, sizeof(unsigned)));
+    if (const char* e = getenv("LMVN_GRAPH")) use_graph = (*e != '0');
     unsigned char* p = arena;
     auto take = [&](size_t bytes) { unsigned char* r = p; p += bytes; return r; };
     psi = reinterpret_cast<float*>(take(S));
@@ -347,8 +366,7 @@ struct DistDeconv {
   int barrier() {
     if (!multi_process || world == 1) return 0;  // one process: stream order is the barrier
     LMVN_CUDA_TRY(cudaSetDevice(device));
-    ++epoch;
-    LMVN_LAUNCH(k_peer_barrier, dim3(1), dim3(32), 0, stream, d_peer_flags, flags(rank), rank, world, epoch, d_err);
+    LMVN_LAUNCH(k_peer_barrier, dim3(1), dim3(32), 0, stream, d_peer_flags, flags(rank), rank, world, d_epoch, d_err);
     LMVN_CUDA_TRY(cudaGetLastError());
     return 0;
   }
@@ -388,12 +406,10 @@ struct DistDeconv {
     if (ops->can_chain_rows() && !staged && iterations > 0) {
       // chained loop (see Deconv::iterate): the x-inverse pass also runs the x-forward pass of the next
       // convolution, in place on the slab's spectrum rows
-      gen::RealSource src{psi, 0, 0, 0, 0};
-      LMVN_TRY(ops->rows_fwd_planes(src, slab_work(rank), nz_l, rank * nz_l, nz, stream));
-      for (int it = 0; it < iterations; ++it)
+      auto sweep = [&](bool ends_call) -> int {  // one iteration = one sweep over all views
         for (int v = 0; v < num_views; ++v)
           for (int which = 1; which <= 2; ++which) {
-            const bool last = (it == iterations - 1 && v == num_views - 1 && which == 2);
+            const bool last = (ends_call && v == num_views - 1 && which == 2);
             LMVN_TRY(ops->strided_geom(y_geom(fast::SM_FWD_SCATTER), stream));
             LMVN_TRY(barrier());
             LMVN_TRY(conv_phase(v, which, 1, up));
@@ -404,6 +420,36 @@ struct DistDeconv {
             if (last) LMVN_TRY(ops->rows_inv_planes(slab_work(rank), psi, e, nz_l, stream));
             else LMVN_TRY(ops->rows_inv_fwd_planes(slab_work(rank), e, nz_l, stream));
           }
+        return 0;
+      };
+      gen::RealSource src{psi, 0, 0, 0, 0};
+      LMVN_TRY(ops->rows_fwd_planes(src, slab_work(rank), nz_l, rank * nz_l, nz, stream));
+      int done = 0;
+#ifndef LMVN_EMU
+      // every rank captures and replays the same sequence (kernels, device-side barriers included)
+      if (use_graph && iterations > 2) {
+        if (!sweep_graph || graph_lambda != lambda || graph_min != min_value) {
+          if (sweep_graph) { cudaGraphExecDestroy(sweep_graph); sweep_graph = nullptr; }
+          cudaGraph_t g = nullptr;
+          LMVN_CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+          const int rc = sweep(false);
+          const cudaError_t ce = cudaStreamEndCapture(stream, &g);
+          if (rc != 0 || ce != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            (void)cudaGetLastError();
+            use_graph = false;
+          } else {
+            if (cudaGraphInstantiate(&sweep_graph, g, 0) != cudaSuccess) { sweep_graph = nullptr; use_graph = false; (void)cudaGetLastError(); }
+            cudaGraphDestroy(g);
+            graph_lambda = lambda;
+            graph_min = min_value;
+          }
+        }
+        if (sweep_graph)
+          for (; done < iterations - 1; ++done) LMVN_CUDA_TRY(cudaGraphLaunch(sweep_graph, stream));
+      }
+#endif
+      for (; done < iterations; ++done) LMVN_TRY(sweep(done == iterations - 1));
     } else {
       for (int it = 0; it < iterations; ++it)
         for (int v = 0; v < num_views; ++v)

@@ -41,7 +41,7 @@ def main():
     dist.gather(mine, parts, dst=0)
     # timing: restart from psi0, more iterations
     plan.set_psi_slab(slab_of(d["psi0"], rank, world))
-    plan.iterate(2, 0.006, 1e-4)
+    plan.iterate(3, 0.006, 1e-4)  # warm-up; also captures the CUDA graph of one sweep
     t = torch.tensor([plan.iterate(10, 0.006, 1e-4)], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     # comparator: the same exchanges through NCCL all_to_all_single
@@ -67,7 +67,7 @@ def main():
             for v in range(nv):
                 p.set_view(v, d["views"][v], d["weights"][v], d["kernels1"][v], d["kernels2"][v])
             p.set_psi(d["psi0"])
-            p.iterate(2, 0.006, 1e-4)
+            p.iterate(3, 0.006, 1e-4)
             t1 = p.iterate(10, 0.006, 1e-4)
         nvox = float(np.prod(dims))
         print("slab_mp_check dims=%s world=%d views=%d: identical=%s max_rel=%.3g first_call_ms=%.3f | %d ranks %.3f ms/(view,iter) "
