@@ -810,6 +810,15 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
   if (CHAIN) rows_fwd_from_regs<M>(A, slab, row0, lane, T, v);
 }
 
+// CTA shape of the rows kernels (chained and plain): four CTAs of 128 threads per SM instead of two of 256 -- the same 16 warps, but
+// finer units for the hardware CTA scheduler (measured: update link 0.246 -> 0.234 ms, quotient link 0.147 -> 0.143)
+#ifndef LMVN_LINK_THREADS
+#define LMVN_LINK_THREADS 128
+#endif
+#ifndef LMVN_LINK_BLOCKS
+#define LMVN_LINK_BLOCKS 4
+#endif
+static const int kLinkThreads = LMVN_LINK_THREADS;
 #ifndef LMVN_ROWS_FWD_BLOCKS
 #define LMVN_ROWS_FWD_BLOCKS 2
 #endif
@@ -817,8 +826,9 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
 #define LMVN_ROWS_INVQ_BLOCKS 2
 #endif
 template <int M, bool WRAPPED>
-static __global__ void __launch_bounds__(kRowThreads, LMVN_ROWS_FWD_BLOCKS) k_rows_fwd2(RowArgs A) {
+static __global__ void __launch_bounds__(kLinkThreads, LMVN_LINK_BLOCKS) k_rows_fwd2(RowArgs A) {
   typedef Row2Cfg<M> CF;
+  constexpr int GROUPS = kLinkThreads / 16;
   LMVN_DYN_SMEM(cplx, sm);
   const int lane = threadIdx.x % 16;
   const int group = threadIdx.x / 16;
@@ -826,8 +836,8 @@ static __global__ void __launch_bounds__(kRowThreads, LMVN_ROWS_FWD_BLOCKS) k_ro
   const long long rows = (long long)A.nz * A.ny;
   RowTw<M> T;
   T.load(A, lane);
-  const long long stride = (long long)gridDim.x * CF::ROWS;
-  for (long long row0 = ((long long)blockIdx.x * CF::GROUPS + group) * CF::RPG; row0 < rows; row0 += stride) {
+  const long long stride = (long long)gridDim.x * GROUPS * CF::RPG;
+  for (long long row0 = ((long long)blockIdx.x * GROUPS + group) * CF::RPG; row0 < rows; row0 += stride) {
     if (!WRAPPED && A.prefetch && row0 + stride < rows)  // next iteration's RPG rows = 16 lines
       prefetch_l2(reinterpret_cast<const char*>(A.src.data + (row0 + stride) * (2 * M)) + lane * (CF::RPG * M / 2));
     rows_fwd_group<M, WRAPPED>(A, slab, row0, lane, T);
@@ -835,8 +845,9 @@ static __global__ void __launch_bounds__(kRowThreads, LMVN_ROWS_FWD_BLOCKS) k_ro
 }
 
 template <int M, int EPI>
-static __global__ void __launch_bounds__(kRowThreads, EPI == gen::EPI_UPDATE ? 2 : LMVN_ROWS_INVQ_BLOCKS) k_rows_inv2(RowArgs A) {
+static __global__ void __launch_bounds__(kLinkThreads, LMVN_LINK_BLOCKS) k_rows_inv2(RowArgs A) {
   typedef Row2Cfg<M> CF;
+  constexpr int GROUPS = kLinkThreads / 16;
   LMVN_DYN_SMEM(cplx, sm);
   __shared__ cplx s_tw[RowTwShared<M>::ENTRIES * 16];
   const int lane = threadIdx.x % 16;
@@ -847,8 +858,8 @@ static __global__ void __launch_bounds__(kRowThreads, EPI == gen::EPI_UPDATE ? 2
   __syncthreads();
   RowTwShared<M> T;
   T.base = s_tw + lane;
-  const long long stride = (long long)gridDim.x * CF::ROWS;
-  for (long long row0 = ((long long)blockIdx.x * CF::GROUPS + group) * CF::RPG; row0 < rows; row0 += stride) {
+  const long long stride = (long long)gridDim.x * GROUPS * CF::RPG;
+  for (long long row0 = ((long long)blockIdx.x * GROUPS + group) * CF::RPG; row0 < rows; row0 += stride) {
     if (A.prefetch && row0 + stride < rows) {
       // next iteration: RPG spectrum rows (RPG * nxp * 8 bytes) and RPG operand rows (16 lines each)
       const long long nr = row0 + stride;
@@ -867,15 +878,6 @@ static __global__ void __launch_bounds__(kRowThreads, EPI == gen::EPI_UPDATE ? 2
 }
 
 // inverse x + pointwise + forward x of the next convolution, in place on the spectrum rows
-// CTA shape of the chained kernels: four CTAs of 128 threads per SM instead of two of 256 -- the same 16 warps, but
-// finer units for the hardware CTA scheduler (measured: update link 0.246 -> 0.234 ms, quotient link 0.147 -> 0.143)
-#ifndef LMVN_LINK_THREADS
-#define LMVN_LINK_THREADS 128
-#endif
-#ifndef LMVN_LINK_BLOCKS
-#define LMVN_LINK_BLOCKS 4
-#endif
-static const int kLinkThreads = LMVN_LINK_THREADS;
 template <int M, int EPI>
 static __global__ void __launch_bounds__(kLinkThreads, LMVN_LINK_BLOCKS) k_rows_inv_fwd(RowArgs A) {
   typedef Row2Cfg<M> CF;

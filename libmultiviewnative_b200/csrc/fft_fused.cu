@@ -161,15 +161,16 @@ struct FastEngine : ConvEngine, FastOps {
   int launch_rows_fwd2(const fast::RowArgs& a, bool wrapped, cudaStream_t s) {
     typedef fast::Row2Cfg<MM> CF;
     const size_t rows = size_t(a.nz) * plan->ny;
-    const size_t iters = ceil_div(rows, CF::ROWS);
-    const dim3 grid(unsigned(std::min<size_t>(iters, size_t(num_sms) * rows_ctas_per_sm)));
-    const size_t smem = size_t(CF::GROUPS) * CF::RPG * CF::RS * sizeof(cplx);
+    const int groups = fast::kLinkThreads / 16;
+    const size_t iters = ceil_div(rows, size_t(groups) * CF::RPG);
+    const dim3 grid(unsigned(std::min<size_t>(iters, size_t(num_sms) * rows_ctas_per_sm * (fast::kRowThreads / fast::kLinkThreads))));
+    const size_t smem = size_t(groups) * CF::RPG * CF::RS * sizeof(cplx);
     auto kw = fast::k_rows_fwd2<MM, true>;
     auto kp = fast::k_rows_fwd2<MM, false>;
     if (wrapped) {
-      LMVN_LAUNCH(kw, grid, dim3(fast::kRowThreads), smem, s, a);
+      LMVN_LAUNCH(kw, grid, dim3(fast::kLinkThreads), smem, s, a);
     } else {
-      LMVN_LAUNCH(kp, grid, dim3(fast::kRowThreads), smem, s, a);
+      LMVN_LAUNCH(kp, grid, dim3(fast::kLinkThreads), smem, s, a);
     }
     return 0;
   }
@@ -232,16 +233,17 @@ struct FastEngine : ConvEngine, FastOps {
   int launch_rows_inv2(const fast::RowArgs& a, cudaStream_t s) {
     typedef fast::Row2Cfg<MM> CF;
     const size_t rows = size_t(a.nz) * plan->ny;
-    const size_t iters = ceil_div(rows, CF::ROWS);
-    const dim3 grid(unsigned(std::min<size_t>(iters, size_t(num_sms) * rows_ctas_per_sm)));
-    const size_t smem = size_t(CF::GROUPS) * CF::RPG * CF::RS * sizeof(cplx);
+    const int groups = fast::kLinkThreads / 16;
+    const size_t iters = ceil_div(rows, size_t(groups) * CF::RPG);
+    const dim3 grid(unsigned(std::min<size_t>(iters, size_t(num_sms) * rows_ctas_per_sm * (fast::kRowThreads / fast::kLinkThreads))));
+    const size_t smem = size_t(groups) * CF::RPG * CF::RS * sizeof(cplx);
     auto k0 = fast::k_rows_inv2<MM, gen::EPI_STORE>;
     auto k1 = fast::k_rows_inv2<MM, gen::EPI_QUOTIENT>;
     auto k2 = fast::k_rows_inv2<MM, gen::EPI_UPDATE>;
     switch (a.ep.mode) {
-      case gen::EPI_QUOTIENT: LMVN_LAUNCH(k1, grid, dim3(fast::kRowThreads), smem, s, a); break;
-      case gen::EPI_UPDATE: LMVN_LAUNCH(k2, grid, dim3(fast::kRowThreads), smem, s, a); break;
-      default: LMVN_LAUNCH(k0, grid, dim3(fast::kRowThreads), smem, s, a); break;
+      case gen::EPI_QUOTIENT: LMVN_LAUNCH(k1, grid, dim3(fast::kLinkThreads), smem, s, a); break;
+      case gen::EPI_UPDATE: LMVN_LAUNCH(k2, grid, dim3(fast::kLinkThreads), smem, s, a); break;
+      default: LMVN_LAUNCH(k0, grid, dim3(fast::kLinkThreads), smem, s, a); break;
     }
     return 0;
   }
