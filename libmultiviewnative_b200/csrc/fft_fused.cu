@@ -56,6 +56,7 @@ struct FastEngine : ConvEngine, FastOps {
   int rows_ctas_per_sm = 8;
   int update_ctas_per_sm = 64;
   int y_fwd_prefetch = 148;  // blocks of look-ahead of the L2 prefetch in the forward y pass
+  int y_inv_prefetch = 0, z_prefetch = 0;  // measured: no gain for these two
   int khat_prefetch = 0;  // measured: hurts the z pass (plane-strided lines), kept as a knob
   int rows_prefetch = 1;
   cplx* d_tw_m = nullptr;
@@ -98,6 +99,8 @@ struct FastEngine : ConvEngine, FastOps {
       nxp = split ? M : (nxc + align - 1) / align * align;
     }
     if (const char* e = getenv("LMVN_PREFETCH")) y_fwd_prefetch = std::max(0, atoi(e));
+    if (const char* e = getenv("LMVN_PREFETCH_YINV")) y_inv_prefetch = std::max(0, atoi(e));
+    if (const char* e = getenv("LMVN_PREFETCH_Z")) z_prefetch = std::max(0, atoi(e));
     if (const char* e = getenv("LMVN_PREFETCH_KHAT")) khat_prefetch = atoi(e);
     if (const char* e = getenv("LMVN_PREFETCH_ROWS")) rows_prefetch = atoi(e);
     if (const char* e = getenv("LMVN_CHAIN")) chain_ok = (*e != '0');
@@ -381,7 +384,9 @@ struct FastEngine : ConvEngine, FastOps {
       a.nyq_cs = (g.tw_axis == 1) ? plan->ny : 1;
     }
     const int mode = g.mode;
-    a.prefetch = (g.tw_axis == 1 && mode == fast::SM_FWD) ? y_fwd_prefetch : 0;
+    a.prefetch = (g.tw_axis == 1 && mode == fast::SM_FWD) ? y_fwd_prefetch
+                 : (g.tw_axis == 1 && mode == fast::SM_INV) ? y_inv_prefetch
+                 : (mode == fast::SM_FWD_MUL_INV) ? z_prefetch : 0;
     a.prefetch_khat = khat_prefetch;
     if (g.tw_axis == 1) { a.tw1 = d_tw_y[0]; a.tw2 = d_tw_y[1]; }
     else { a.tw1 = d_tw_z[0]; a.tw2 = d_tw_z[1]; }
