@@ -66,6 +66,17 @@ enum lmvn_padding { LMVN_PAD_NONE = 0, LMVN_PAD_ZERO = 1 };
 LMVN_EXPORT int lmvn_set_padding(int mode);
 LMVN_EXPORT int lmvn_plan_create_zero_padded(lmvn_plan** out, const int* image_dims_zyx, const int* max_kernel_dims_zyx,
                                              int num_views, int device);
+/* Periodic embedding: CIRCULAR convolution at the image extents (the CPU path's semantics, like lmvn_plan_create) for
+ * extents the power-of-two fast path does not take.  The stacks sit inside power-of-two extents >= image + kernel - 1;
+ * before every convolution the exterior is refilled with the periodic continuation of the interior, so the result inside
+ * the image equals the circular convolution at the image extents.  The one-shot entry points choose it by themselves when
+ * the image extents are not fast-path extents and the embedding costs at most 8x the voxels (and fits the device) (env LMVN_EMBED=0 disables,
+ * LMVN_EMBED_MAX_BLOWUP changes the bound); otherwise they use the generic passes.  lmvn_last_geometry(): what the last
+ * one-shot call of this thread used. */
+enum lmvn_geometry { LMVN_GEOMETRY_NONE = 0, LMVN_GEOMETRY_NATIVE = 1, LMVN_GEOMETRY_EMBEDDED = 2, LMVN_GEOMETRY_ZERO_PADDED = 3 };
+LMVN_EXPORT int lmvn_plan_create_embedded(lmvn_plan** out, const int* image_dims_zyx, const int* max_kernel_dims_zyx,
+                                          int num_views, int device);
+LMVN_EXPORT int lmvn_last_geometry(void);
 LMVN_EXPORT void lmvn_plan_destroy(lmvn_plan* plan);
 LMVN_EXPORT int lmvn_plan_get_info(const lmvn_plan* plan, lmvn_plan_info* info);
 

@@ -69,7 +69,8 @@ REFERENCE_SYMBOLS = [
 ]
 EXTENSION_SYMBOLS = [
     "lmvn_last_error", "lmvn_clear_error", "lmvn_version", "lmvn_set_default_strategy", "lmvn_release_cached_memory",
-    "lmvn_plan_create", "lmvn_set_padding", "lmvn_plan_create_zero_padded",
+    "lmvn_plan_create", "lmvn_set_padding", "lmvn_plan_create_zero_padded", "lmvn_plan_create_embedded",
+    "lmvn_last_geometry",
     "lmvn_plan_destroy", "lmvn_plan_get_info", "lmvn_plan_set_view", "lmvn_plan_set_psi", "lmvn_plan_get_psi",
     "lmvn_plan_iterate", "lmvn_plan_convolve", "lmvn_plan_profile", "lmvn_plan_synchronize", "lmvn_debug_rfftn", "lmvn_debug_irfftn",
     "lmvn_dist_create", "lmvn_dist_destroy", "lmvn_dist_get_info", "lmvn_dist_export_handle", "lmvn_dist_connect_ipc",
@@ -174,6 +175,10 @@ class Library:
     def set_padding(self, mode: int):
         """0: circular at the image extents (the CPU path, default); 1: zero_padd (the reference's GPU geometry)."""
         self._check(self.lib.lmvn_set_padding(int(mode)), "lmvn_set_padding")
+
+    def last_geometry(self) -> int:
+        """1: native extents, 2: periodic embedding into power-of-two extents, 3: zero padded (last one-shot call)."""
+        return int(self.lib.lmvn_last_geometry())
 
     def release_cached_memory(self):
         self.lib.lmvn_release_cached_memory()

@@ -3,6 +3,7 @@
 #include "engine.cuh"
 #include "fft_generic.cuh"
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -430,6 +431,14 @@ int Deconv::set_logical(const int* image_dims, const int* off) {
   return 0;
 }
 
+int Deconv::wrap_exterior(float* vol) {
+  // exterior rows read interior rows only and interior rows only write their own x margins: no ordering hazard
+  LMVN_LAUNCH(k_wrap_exterior, dim3(unsigned(dims[1]), unsigned(dims[0])), dim3(128), 0, stream, vol, dims[0], dims[1], dims[2],
+              logical[0], logical[1], logical[2], offset[0], offset[1], offset[2]);
+  LMVN_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 // host stack (logical extents) -> device volume (plan extents), zero filled around it
 int Deconv::upload_stack(float* dst, const float* src_h) {
   const size_t n = engine->plan->voxels();
@@ -437,14 +446,14 @@ int Deconv::upload_stack(float* dst, const float* src_h) {
     LMVN_CUDA_TRY(cudaMemcpyAsync(dst, src_h, n * sizeof(float), cudaMemcpyHostToDevice, stream));
     return 0;
   }
-  LMVN_CUDA_TRY(cudaMemsetAsync(dst, 0, n * sizeof(float), stream));
-  // one 2-D copy per plane: rows of logical[2] floats into rows of dims[2] floats
-  for (int z = 0; z < logical[0]; ++z) {
-    float* d = dst + (size_t(z + offset[0]) * dims[1] + offset[1]) * dims[2] + offset[2];
-    const float* s = src_h + size_t(z) * logical[1] * logical[2];
-    LMVN_CUDA_TRY(cudaMemcpy2DAsync(d, size_t(dims[2]) * sizeof(float), s, size_t(logical[2]) * sizeof(float),
-                                    size_t(logical[2]) * sizeof(float), size_t(logical[1]), cudaMemcpyHostToDevice, stream));
-  }
+  // one contiguous copy into the (idle) spectrum work buffer, then a kernel places the box and zero fills the rest
+  (void)n;
+  float* stage = reinterpret_cast<float*>(work);
+  const size_t ln = size_t(logical[0]) * logical[1] * logical[2];
+  LMVN_CUDA_TRY(cudaMemcpyAsync(stage, src_h, ln * sizeof(float), cudaMemcpyHostToDevice, stream));
+  LMVN_LAUNCH(k_place_box, dim3(unsigned(dims[1]), unsigned(dims[0])), dim3(128), 0, stream, dst, stage, dims[1], dims[2],
+              logical[0], logical[1], logical[2], offset[0], offset[1], offset[2]);
+  LMVN_CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
@@ -453,12 +462,12 @@ int Deconv::download_stack(float* dst_h, const float* src) {
     LMVN_CUDA_TRY(cudaMemcpyAsync(dst_h, src, engine->plan->voxels() * sizeof(float), cudaMemcpyDeviceToHost, stream));
     return 0;
   }
-  for (int z = 0; z < logical[0]; ++z) {
-    const float* s = src + (size_t(z + offset[0]) * dims[1] + offset[1]) * dims[2] + offset[2];
-    float* d = dst_h + size_t(z) * logical[1] * logical[2];
-    LMVN_CUDA_TRY(cudaMemcpy2DAsync(d, size_t(logical[2]) * sizeof(float), s, size_t(dims[2]) * sizeof(float),
-                                    size_t(logical[2]) * sizeof(float), size_t(logical[1]), cudaMemcpyDeviceToHost, stream));
-  }
+  float* stage = reinterpret_cast<float*>(work);
+  LMVN_LAUNCH(k_gather_box, dim3(unsigned(logical[1]), unsigned(logical[0])), dim3(128), 0, stream, src, stage, dims[1], dims[2],
+              logical[1], logical[2], offset[0], offset[1], offset[2]);
+  LMVN_CUDA_TRY(cudaGetLastError());
+  LMVN_CUDA_TRY(cudaMemcpyAsync(dst_h, stage, size_t(logical[0]) * logical[1] * logical[2] * sizeof(float),
+                                cudaMemcpyDeviceToHost, stream));
   return 0;
 }
 
@@ -536,7 +545,19 @@ int Deconv::iterate(int iterations, double lambda, float min_value, float* devic
   LMVN_CUDA_TRY(cudaSetDevice(device));
   const UpdateParams up = make_update_params(lambda, min_value);
   LMVN_CUDA_TRY(cudaEventRecord(ev0, stream));
-  if (engine->can_chain() && iterations > 0) {
+  if (periodic) {
+    // periodic embedding: both inputs of a step get their exterior refilled; the convolutions are the plain five-pass form
+    for (int it = 0; it < iterations; ++it) {
+      for (int v = 0; v < num_views; ++v) {
+        LMVN_TRY(wrap_exterior(psi));
+        gen::Epilogue e1{gen::EPI_QUOTIENT, 1.f, image[v], nullptr, nullptr, up};
+        LMVN_TRY(engine->convolve(psi, work, khat1[v], e1, integral, stream));
+        LMVN_TRY(wrap_exterior(integral));
+        gen::Epilogue e2{gen::EPI_UPDATE, 1.f, nullptr, psi, weights[v], up};
+        LMVN_TRY(engine->convolve(integral, work, khat2[v], e2, psi, stream));
+      }
+    }
+  } else if (engine->can_chain() && iterations > 0) {
     // chained loop: every x-inverse pass also runs the x-forward pass of the convolution that follows it
     auto sweep = [&](bool ends_call) -> int {  // one iteration = one sweep over all views
       for (int v = 0; v < num_views; ++v) {
@@ -613,6 +634,7 @@ int Deconv::convolve_psi(int view, int which, int repeats, float* device_ms) {
   LMVN_CUDA_TRY(cudaEventRecord(ev0, stream));
   for (int r = 0; r < repeats; ++r) {
     gen::Epilogue e{gen::EPI_STORE, 1.f, nullptr, nullptr, nullptr, up};
+    if (periodic) LMVN_TRY(wrap_exterior(psi));
     LMVN_TRY(engine->convolve(psi, work, kh, e, integral, stream));
     std::swap(psi, integral);
   }
@@ -658,7 +680,7 @@ int Deconv::profile(double lambda, float min_value, std::vector<std::string>& na
   const UpdateParams up = make_update_params(lambda, min_value);
   PassTimer t;
   int rc = 0;
-  const bool chain = engine->can_chain();
+  const bool chain = engine->can_chain() && !periodic;
   // chained loop: the steady state of iterate() is profiled (the one x-forward pass that opens a call is not part of it)
   if (chain) rc = engine->chain_begin(psi, work, stream);
   if (rc == 0) rc = t.begin(stream);

@@ -118,6 +118,7 @@ std::unique_ptr<FastOps> make_fast_ops(std::shared_ptr<FftPlan> plan_global);
 std::unique_ptr<ConvEngine> make_generic_engine(std::shared_ptr<FftPlan> plan);
 // nullptr when the shape is not eligible (no error set)
 std::unique_ptr<ConvEngine> make_fused_engine(std::shared_ptr<FftPlan> plan);
+bool fused_shape_ok(int nz, int ny, int nx);  // extents the power-of-two fast path takes
 
 int default_strategy();
 void set_default_strategy(int s);
@@ -155,9 +156,14 @@ struct Deconv {
   const float* graph_psi = nullptr;
 
   bool padded = false;
+  // periodic embedding: the exterior of the logical box is refilled by periodic continuation before every
+  // convolution, so that the result inside the box is the CIRCULAR convolution at the logical extents (the CPU
+  // path's semantics) although the transform runs at power-of-two extents
+  bool periodic = false;
   int logical[3] = {0, 0, 0};
   int offset[3] = {0, 0, 0};
   int set_logical(const int* image_dims, const int* off);
+  int wrap_exterior(float* vol);
   int upload_stack(float* dst, const float* src_h);
   int download_stack(float* dst_h, const float* src);
 

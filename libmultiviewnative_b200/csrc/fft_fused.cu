@@ -543,6 +543,10 @@ std::unique_ptr<FastOps> make_fast_ops(std::shared_ptr<FftPlan> plan) {
   return std::unique_ptr<FastOps>(e.release());
 }
 
+bool fused_shape_ok(int nz, int ny, int nx) {
+  return nx_ok(nx) && axis_ok(ny) && axis_ok(nz) && (size_t(nz) * ny) % 128 == 0;
+}
+
 std::unique_ptr<ConvEngine> make_fused_engine(std::shared_ptr<FftPlan> plan) {
   const int nx = plan->nx;
   if (!nx_ok(nx)) return nullptr;

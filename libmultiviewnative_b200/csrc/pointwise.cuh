@@ -75,6 +75,48 @@ __device__ __forceinline__ float rl_update(float psi, float integral, float weig
   return __fadd_rn(__fmul_rn(weight, __fadd_rn(next, -last)), last);
 }
 
+// Periodic embedding: a volume of logical extents (lz, ly, lx) sits at offset (oz, oy, ox) inside a larger
+// power-of-two volume (nz, ny, nx).  Every voxel OUTSIDE the logical box is overwritten with the logical voxel it
+// aliases under periodic continuation.  A circular convolution at the large extents then equals, inside the box,
+// the circular convolution at the logical extents (ref semantics: inc/cpu_convolve.h:24) as long as the margins are
+// at least the kernel half-widths -- which lets arbitrary stack sizes run on the power-of-two fast path.
+static __global__ void k_wrap_exterior(float* __restrict__ vol, int nz, int ny, int nx, int lz, int ly, int lx, int oz,
+                                       int oy, int ox) {
+  // one block per row (z, y): the source row is computed once, interior rows only touch their x margins
+  const int y = blockIdx.x, z = blockIdx.y;
+  int sz = (z - oz) % lz, sy = (y - oy) % ly;
+  if (sz < 0) sz += lz;
+  if (sy < 0) sy += ly;
+  const bool interior_row = (z >= oz && z < oz + lz && y >= oy && y < oy + ly);
+  float* dst = vol + (size_t(z) * ny + y) * nx;
+  const float* src = vol + (size_t(sz + oz) * ny + (sy + oy)) * nx + ox;
+  for (int x = threadIdx.x; x < nx; x += blockDim.x) {
+    if (interior_row && x >= ox && x < ox + lx) continue;
+    int sx = (x - ox) % lx;
+    if (sx < 0) sx += lx;
+    dst[x] = src[sx];
+  }
+  (void)nz;
+}
+
+// Padded plans move host stacks with ONE contiguous copy through a staging buffer; these two kernels place the
+// stack into its box inside the (zero filled) volume and gather it back.  One block per row (z, y) of the volume.
+static __global__ void k_place_box(float* __restrict__ vol, const float* __restrict__ box, int ny, int nx, int lz, int ly,
+                                   int lx, int oz, int oy, int ox) {
+  const int y = blockIdx.x, z = blockIdx.y;
+  const bool row_in = (z >= oz && z < oz + lz && y >= oy && y < oy + ly);
+  float* dst = vol + (size_t(z) * ny + y) * nx;
+  const float* src = box + (size_t(row_in ? z - oz : 0) * ly + (row_in ? y - oy : 0)) * lx;
+  for (int x = threadIdx.x; x < nx; x += blockDim.x) dst[x] = (row_in && x >= ox && x < ox + lx) ? src[x - ox] : 0.f;
+}
+static __global__ void k_gather_box(const float* __restrict__ vol, float* __restrict__ box, int ny, int nx, int ly, int lx,
+                                    int oz, int oy, int ox) {
+  const int y = blockIdx.x, z = blockIdx.y;  // box coordinates
+  const float* src = vol + (size_t(z + oz) * ny + (y + oy)) * nx + ox;
+  float* dst = box + (size_t(z) * ly + y) * lx;
+  for (int x = threadIdx.x; x < lx; x += blockDim.x) dst[x] = src[x];
+}
+
 // ---- standalone kernels (legacy API only) -------------------------------------
 static __global__ void k_divide(const float* __restrict__ in, float* __restrict__ out, size_t n) {
   size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;

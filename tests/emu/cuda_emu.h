@@ -187,6 +187,22 @@ static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* 
     std::memmove(static_cast<char*>(d) + r * dpitch, static_cast<const char*>(s) + r * spitch, width);
   return 0;
 }
+struct cudaPitchedPtr { void* ptr; size_t pitch, xsize, ysize; };
+struct cudaPos { size_t x, y, z; };
+struct cudaExtent { size_t width, height, depth; };
+struct cudaMemcpy3DParms { cudaPitchedPtr srcPtr, dstPtr; cudaPos srcPos, dstPos; cudaExtent extent; cudaMemcpyKind kind; };
+static inline cudaPitchedPtr make_cudaPitchedPtr(void* p, size_t pitch, size_t xs, size_t ys) { return cudaPitchedPtr{p, pitch, xs, ys}; }
+static inline cudaPos make_cudaPos(size_t x, size_t y, size_t z) { return cudaPos{x, y, z}; }
+static inline cudaExtent make_cudaExtent(size_t w, size_t h, size_t d) { return cudaExtent{w, h, d}; }
+static inline cudaError_t cudaMemcpy3DAsync(const cudaMemcpy3DParms* p, cudaStream_t = 0) {
+  for (size_t z = 0; z < p->extent.depth; ++z)
+    for (size_t y = 0; y < p->extent.height; ++y) {
+      const char* s = static_cast<const char*>(p->srcPtr.ptr) + ((p->srcPos.z + z) * p->srcPtr.ysize + p->srcPos.y + y) * p->srcPtr.pitch + p->srcPos.x;
+      char* d = static_cast<char*>(p->dstPtr.ptr) + ((p->dstPos.z + z) * p->dstPtr.ysize + p->dstPos.y + y) * p->dstPtr.pitch + p->dstPos.x;
+      std::memmove(d, s, p->extent.width);
+    }
+  return 0;
+}
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return 0; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = 0) { std::memset(d, v, n); return 0; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return 0; }

@@ -268,3 +268,32 @@ def case_zero_padd_deconvolve(L, dims, ksize, lam=0.006, iters=2):
     finally:
         L.set_padding(0)
     assert max_rel(got, exp) < PER_VOXEL_TOL_1_ITER
+
+
+# ---- periodic embedding: circular semantics on the fast path for arbitrary extents ---------------
+GEOMETRY_NATIVE, GEOMETRY_EMBEDDED, GEOMETRY_ZERO_PADDED = 1, 2, 3
+
+
+def case_embedded_convolution(L, dims, kdims, expect_embedded=True):
+    rng = np.random.default_rng(31)
+    img = (rng.random(dims, dtype=F32) + 1).astype(F32)
+    k = rng.random(kdims, dtype=F32)
+    k /= k.sum()
+    exp = orc.inplace_cpu_convolution(img, k)
+    got = img.copy()
+    L.inplace_gpu_convolution(got, k)
+    assert L.last_geometry() == (GEOMETRY_EMBEDDED if expect_embedded else GEOMETRY_NATIVE)
+    assert rel_l2(got, exp) < 1e-5
+    assert float(np.max(np.abs(got - exp))) < 1e-4 * float(np.max(np.abs(exp)))
+
+
+def case_embedded_deconvolve(L, dims, ksize, lam=0.006, iters_list=(1, 3)):
+    d = make_views(dims, num_views=2, kernel_size=ksize, n_sources=10, workers=1)
+    for iters in iters_list:
+        exp = orc.inplace_cpu_deconvolve(d["psi0"], d["views"], d["kernels1"], d["kernels2"], d["weights"], iters, lam, 1e-4)
+        got = d["psi0"].copy()
+        L.inplace_gpu_deconvolve(got, d["views"], d["kernels1"], d["kernels2"], d["weights"], iters, lam, 1e-4)
+        assert L.last_geometry() == GEOMETRY_EMBEDDED
+        if iters == 1:
+            assert max_rel(got, exp) < PER_VOXEL_TOL_1_ITER
+        assert rel_l2(got, exp) < REL_L2_TOL_10_ITER

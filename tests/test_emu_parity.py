@@ -57,6 +57,21 @@ def test_zero_padd_deconvolve(L):
     pc.case_zero_padd_deconvolve(L, (10, 12, 14), 5)
 
 
+@pytest.mark.parametrize("dims,kdims", [((20, 24, 50), (5, 7, 9)), ((28, 30, 50), (4, 3, 2)), ((27, 27, 27), (3, 3, 3))])
+def test_embedded_convolution(L, dims, kdims):
+    pc.case_embedded_convolution(L, dims, kdims)
+
+
+def test_embedding_not_used_when_it_costs_too_much(L, monkeypatch):
+    pc.case_embedded_convolution(L, (9, 10, 15), (3, 3, 3), expect_embedded=False)  # 16 x 16 x 64 would be 12x the voxels
+    monkeypatch.setenv("LMVN_EMBED", "0")
+    pc.case_embedded_convolution(L, (20, 24, 50), (5, 7, 9), expect_embedded=False)
+
+
+def test_embedded_deconvolve(L):
+    pc.case_embedded_deconvolve(L, (30, 28, 40), 5)
+
+
 def test_pointwise(L):
     pc.case_pointwise(L)
 

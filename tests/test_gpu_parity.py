@@ -89,6 +89,16 @@ def test_zero_padd_deconvolve(L):
     pc.case_zero_padd_deconvolve(L, (100, 100, 100), 21)
 
 
+@pytest.mark.parametrize("dims,kdims", [((20, 24, 50), (5, 7, 9)), ((28, 30, 50), (4, 3, 2)), ((100, 120, 200), (21, 21, 21)),
+                                        ((200, 200, 200), (41, 41, 41))])
+def test_embedded_convolution(L, dims, kdims):
+    pc.case_embedded_convolution(L, dims, kdims)
+
+
+def test_embedded_deconvolve(L):
+    pc.case_embedded_deconvolve(L, (100, 90, 120), 21, iters_list=(1, 10))
+
+
 def test_pointwise(L):
     pc.case_pointwise(L)
 
