@@ -140,6 +140,7 @@ class Library:
         L.getMemDeviceCUDA.restype = C.c_longlong
         L.lmvn_plan_create.argtypes = [C.POINTER(C.c_void_p), c_int_p, C.c_int, C.c_int]
         L.lmvn_plan_create_zero_padded.argtypes = [C.POINTER(C.c_void_p), c_int_p, c_int_p, C.c_int, C.c_int]
+        L.lmvn_plan_create_embedded.argtypes = [C.POINTER(C.c_void_p), c_int_p, c_int_p, C.c_int, C.c_int]
         L.lmvn_plan_destroy.argtypes = [C.c_void_p]
         L.lmvn_plan_destroy.restype = None
         L.lmvn_plan_get_info.argtypes = [C.c_void_p, C.POINTER(PlanInfo)]
@@ -336,20 +337,32 @@ class Library:
                                                int(device)), "lmvn_debug_irfftn")
         return out
 
-    def plan(self, dims, num_views, device=-1) -> "Plan":
-        return Plan(self, dims, num_views, device)
+    def plan(self, dims, num_views, device=-1, max_kernel_dims=None, geometry: str = "native") -> "Plan":
+        return Plan(self, dims, num_views, device, max_kernel_dims, geometry)
 
 
 class Plan:
     """Persistent deconvolution handle (lmvn_plan_*): views, weights and PSF spectra stay
     on the device; only psi moves."""
 
-    def __init__(self, library: Library, dims, num_views: int, device: int = -1):
+    def __init__(self, library: Library, dims, num_views: int, device: int = -1, max_kernel_dims=None,
+                 geometry: str = "native"):
+        """geometry "native": the plan works at `dims` (circular there); "embedded" / "zero": `dims` are the stack
+        extents, the plan works at power-of-two extents >= dims + max_kernel_dims - 1 with periodic refill (same circular
+        semantics) or zero padding (the reference GPU path's linear convolution at the borders)."""
         self.L = library
         self.dims = tuple(int(d) for d in dims)
         self.handle = C.c_void_p()
-        library._check(library.lib.lmvn_plan_create(C.byref(self.handle), C.cast(_dims(self.dims), c_int_p),
-                                                    int(num_views), int(device)), "lmvn_plan_create")
+        if geometry == "native":
+            library._check(library.lib.lmvn_plan_create(C.byref(self.handle), C.cast(_dims(self.dims), c_int_p),
+                                                        int(num_views), int(device)), "lmvn_plan_create")
+        else:
+            if max_kernel_dims is None:
+                raise ValueError("padded geometries need max_kernel_dims")
+            fn = {"embedded": library.lib.lmvn_plan_create_embedded, "zero": library.lib.lmvn_plan_create_zero_padded}[geometry]
+            library._check(fn(C.byref(self.handle), C.cast(_dims(self.dims), c_int_p),
+                              C.cast(_dims(tuple(max_kernel_dims)), c_int_p), int(num_views), int(device)),
+                           "lmvn_plan_create_" + geometry)
 
     def close(self):
         if self.handle:

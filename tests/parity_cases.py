@@ -297,3 +297,22 @@ def case_embedded_deconvolve(L, dims, ksize, lam=0.006, iters_list=(1, 3)):
         if iters == 1:
             assert max_rel(got, exp) < PER_VOXEL_TOL_1_ITER
         assert rel_l2(got, exp) < REL_L2_TOL_10_ITER
+
+
+def case_embedded_plan_equals_one_shot(L, dims=(30, 28, 40), ksize=5):
+    """persistent handle with periodic embedding == the one-shot call that embeds by itself"""
+    d = make_views(dims, num_views=2, kernel_size=ksize, n_sources=10, workers=1)
+    one = d["psi0"].copy()
+    L.inplace_gpu_deconvolve(one, d["views"], d["kernels1"], d["kernels2"], d["weights"], 4, 0.006, 1e-4)
+    assert L.last_geometry() == GEOMETRY_EMBEDDED
+    kmax = [max(k.shape[a] for k in d["kernels1"] + d["kernels2"]) for a in range(3)]
+    with L.plan(dims, 2, 0, max_kernel_dims=kmax, geometry="embedded") as p:
+        info = p.info()
+        assert tuple(info.dims) != tuple(dims) and all(n >= m + k - 1 for n, m, k in zip(info.dims, dims, kmax))
+        for v in range(2):
+            p.set_view(v, d["views"][v], d["weights"][v], d["kernels1"][v], d["kernels2"][v])
+        p.set_psi(d["psi0"])
+        p.iterate(2, 0.006, 1e-4)
+        p.iterate(2, 0.006, 1e-4)
+        got = p.get_psi()
+    np.testing.assert_array_equal(got, one)

@@ -72,6 +72,10 @@ def test_embedded_deconvolve(L):
     pc.case_embedded_deconvolve(L, (30, 28, 40), 5)
 
 
+def test_embedded_plan_equals_one_shot(L):
+    pc.case_embedded_plan_equals_one_shot(L)
+
+
 def test_pointwise(L):
     pc.case_pointwise(L)
 

@@ -99,6 +99,10 @@ def test_embedded_deconvolve(L):
     pc.case_embedded_deconvolve(L, (100, 90, 120), 21, iters_list=(1, 10))
 
 
+def test_embedded_plan_equals_one_shot(L):
+    pc.case_embedded_plan_equals_one_shot(L)
+
+
 def test_pointwise(L):
     pc.case_pointwise(L)
 
