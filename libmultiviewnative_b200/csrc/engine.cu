@@ -362,7 +362,10 @@ int Deconv::init(const int* d, int nviews, int dev, int strategy) {
   const size_t W = align_up(engine->work_elems() * sizeof(cplx), 256);
   kernel_stage_elems = std::min(kMaxKernelVoxels, fp->voxels());
   const size_t KS = align_up(kernel_stage_elems * sizeof(float), 256);
-  arena_bytes = 2 * S + W + KS + size_t(nviews) * (2 * S + 2 * K);
+  // `integral` is sized like a spectrum buffer: the chained loop of an embedded plan never stores the quotient
+  // and uses it as its second spectrum buffer
+  const size_t SI = std::max(S, W);
+  arena_bytes = 3 * SI + W + KS + size_t(nviews) * (2 * S + 2 * K);
   arena = take_parked(device, arena_bytes, &arena_capacity);
   if (!arena) {
     size_t free_b = 0, total_b = 0;
@@ -379,8 +382,9 @@ int Deconv::init(const int* d, int nviews, int dev, int strategy) {
   lap("arena");
   unsigned char* p = arena;
   auto take = [&](size_t bytes) { unsigned char* r = p; p += bytes; return r; };
-  psi = reinterpret_cast<float*>(take(S));
-  integral = reinterpret_cast<float*>(take(S));
+  psi = reinterpret_cast<float*>(take(SI));   // psi, psi2 and integral can change roles (lmvn_plan_convolve swaps
+  psi2 = reinterpret_cast<float*>(take(SI));  // psi and integral): all three have the spectrum-buffer size
+  integral = reinterpret_cast<float*>(take(SI));
   work = reinterpret_cast<cplx*>(take(W));
   kernel_stage = reinterpret_cast<float*>(take(KS));
   image.resize(nviews); weights.resize(nviews); khat1.resize(nviews); khat2.resize(nviews);
@@ -545,7 +549,32 @@ int Deconv::iterate(int iterations, double lambda, float min_value, float* devic
   LMVN_CUDA_TRY(cudaSetDevice(device));
   const UpdateParams up = make_update_params(lambda, min_value);
   LMVN_CUDA_TRY(cudaEventRecord(ev0, stream));
-  if (periodic) {
+  if (periodic && engine->can_chain_embedded() && iterations > 0) {
+    // periodic embedding, chained: the link kernel itself continues the stack periodically (rows outside the box
+    // recompute the interior row they alias and write to the other spectrum buffer), no refill pass in the loop
+    LMVN_TRY(wrap_exterior(psi));
+    LMVN_TRY(engine->chain_begin(psi, work, stream));
+    cplx* cur = work;
+    cplx* other = reinterpret_cast<cplx*>(integral);  // the quotient is never stored in this loop
+    for (int it = 0; it < iterations; ++it) {
+      for (int v = 0; v < num_views; ++v) {
+        const bool last = (it == iterations - 1 && v == num_views - 1);
+        LMVN_TRY(engine->chain_middle(cur, khat1[v], stream));
+        gen::Epilogue e1{gen::EPI_QUOTIENT, 1.f, image[v], nullptr, nullptr, up};
+        LMVN_TRY(engine->chain_link_embedded(cur, other, e1, nullptr, logical, offset, stream));
+        std::swap(cur, other);
+        LMVN_TRY(engine->chain_middle(cur, khat2[v], stream));
+        gen::Epilogue e2{gen::EPI_UPDATE, 1.f, nullptr, psi, weights[v], up};
+        if (last) {
+          LMVN_TRY(engine->chain_end(cur, e2, psi, stream));
+        } else {
+          LMVN_TRY(engine->chain_link_embedded(cur, other, e2, psi2, logical, offset, stream));
+          std::swap(cur, other);
+          std::swap(psi, psi2);  // the interior of psi2 now holds the new estimate; the exterior is never read
+        }
+      }
+    }
+  } else if (periodic) {
     // periodic embedding: both inputs of a step get their exterior refilled; the convolutions are the plain five-pass form
     for (int it = 0; it < iterations; ++it) {
       for (int v = 0; v < num_views; ++v) {

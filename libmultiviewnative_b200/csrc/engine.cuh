@@ -82,6 +82,12 @@ struct ConvEngine {
   virtual int chain_middle(cplx*, const cplx*, cudaStream_t) { return -1; }
   virtual int chain_link(cplx*, const gen::Epilogue&, cudaStream_t) { return -1; }
   virtual int chain_end(cplx*, const gen::Epilogue&, float*, cudaStream_t) { return -1; }
+  // chain_link for a periodically embedded stack (logical box inside the plan extents): rows outside the box recompute
+  // the interior row they alias, so the result goes to a second buffer `out` (same size as `work`)
+  virtual bool can_chain_embedded() const { return false; }
+  // (EPI_UPDATE: the new psi is written to `psi_out`, the old one in ep.psi stays intact)
+  virtual int chain_link_embedded(cplx*, cplx*, const gen::Epilogue&, float* /*psi_out*/, const int*, const int*,
+                                  cudaStream_t) { return -1; }
 };
 
 // What the slab-decomposed (multi-GPU) engine needs from the power-of-two fast path: the same
@@ -134,6 +140,7 @@ struct Deconv {
   size_t arena_bytes = 0;
   size_t arena_capacity = 0;  // bytes of the underlying allocation (>= arena_bytes when taken from the park)
   float* psi = nullptr;
+  float* psi2 = nullptr;          // embedded plans, chained loop: the update link writes the new psi out of place
   float* integral = nullptr;
   cplx* work = nullptr;
   float* kernel_stage = nullptr;  // device staging for the unpadded PSFs

@@ -520,6 +520,12 @@ struct RowArgs {
   int z0, nz_wrap;       // wrapped source on a slab of planes: global index of plane 0, global nz
   const cplx* tw_h;      // nx = 1024 only: w_{M/2} table (M/2 entries) of the two half-length sub-transforms
   cplx* nyq;             // split layout: X[nx/2] of row r lives at nyq[r] instead of spec[r * nxp + nx/2]
+  // chained kernel on a periodically embedded stack (EMBED): the logical box (lz, ly, lx) sits at (oz, oy, ox); a row
+  // outside the box recomputes the interior row it aliases, x positions outside the box take the aliased interior
+  // sample, and the forward transform of the result goes to spec_out / nyq_out (the sources are read by other CTAs)
+  cplx* spec_out;
+  cplx* nyq_out;
+  int lz, ly, lx, oz, oy, ox;
 };
 
 // a + conj(b) and a - conj(b): one packed FFMA2 each on sm_100
@@ -703,7 +709,7 @@ __device__ __forceinline__ void rows_fwd_from_regs(const RowArgs& A, cplx* slab,
 // CHAIN: the real samples the epilogue produces are not (only) stored but forward transformed again and
 // written back as the row's spectrum -- the x pass of the NEXT convolution, fused: `integral` never goes to
 // HBM at all and the new psi is not read back (saves 3S of the 7S + 18C per (view, iteration)).
-template <int M, int EPI, typename TW, bool CHAIN = false>
+template <int M, int EPI, typename TW, bool CHAIN = false, bool EMBED = false>
 __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, long long row0, int lane,
                                                const TW& T) {
   typedef Row2Cfg<M> CF;
@@ -711,17 +717,30 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
   constexpr int nx = 2 * M;
   const int q_blk = lane % R1, r_blk = lane / R1;
   constexpr int mode = EPI;  // compile time: no branches, no dead operand registers
+  // rows the data comes from: the row itself, or (EMBED) the interior row it aliases
+  long long srow[RPG];
+#pragma unroll
+  for (int a = 0; a < RPG; ++a) {
+    srow[a] = row0 + a;
+    if (EMBED) {
+      const int z = int(srow[a] / A.ny), y = int(srow[a] % A.ny);
+      int sz = (z - A.oz) % A.lz, sy = (y - A.oy) % A.ly;
+      if (sz < 0) sz += A.lz;
+      if (sy < 0) sy += A.ly;
+      srow[a] = (long long)(sz + A.oz) * A.ny + (sy + A.oy);
+    }
+  }
   // ---- spectrum loads (full lines) ----
   cplx xs[RPG * PAIRS], xm[RPG * PAIRS];
   cplx xh[RPG];
 #pragma unroll
   for (int a = 0; a < RPG; ++a) {
-    const cplx* irow = A.spec + (row0 + a) * A.nxp;
+    const cplx* irow = A.spec + srow[a] * A.nxp;
 #pragma unroll
     for (int i = 0; i < PAIRS; ++i) {
       const int k = lane + 16 * i;
       xs[a * PAIRS + i] = ld_stream(irow + k);
-      xm[a * PAIRS + i] = ld_stream((k == 0 && A.nyq) ? A.nyq + (row0 + a) : irow + (M - k));  // k = 0 reads X[M]
+      xm[a * PAIRS + i] = ld_stream((k == 0 && A.nyq) ? A.nyq + srow[a] : irow + (M - k));  // k = 0 reads X[M]
     }
     if (lane == 0) xh[a] = ld_stream(irow + M / 2);
   }
@@ -732,7 +751,7 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
     const float* pa = (mode == gen::EPI_QUOTIENT) ? A.ep.view : A.ep.psi;
 #pragma unroll
     for (int a = 0; a < RPG; ++a) {
-      const float2* p2 = reinterpret_cast<const float2*>(pa + (row0 + a) * nx);
+      const float2* p2 = reinterpret_cast<const float2*>(pa + srow[a] * nx);
 #pragma unroll
       for (int r = 0; r < R1; ++r) oa[a * R1 + r] = ld_stream(p2 + lane + 16 * r);
     }
@@ -762,7 +781,7 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
     // its latency still overlaps the radix-16 stage and the second exchange
 #pragma unroll
     for (int a = 0; a < RPG; ++a) {
-      const float2* p2 = reinterpret_cast<const float2*>(A.ep.weights + (row0 + a) * nx);
+      const float2* p2 = reinterpret_cast<const float2*>(A.ep.weights + srow[a] * nx);
 #pragma unroll
       for (int r = 0; r < R1; ++r) ob[a * R1 + r] = ld_stream(p2 + lane + 16 * r);
     }
@@ -781,7 +800,9 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
     for (int j = 0; j < 16; ++j) p[j] = v[j];
   }
   __syncwarp();
-  float* obase = (mode == gen::EPI_UPDATE) ? A.ep.psi : A.out;
+  // EMBED: rows outside the box read the psi of the interior row they alias while that row's own CTA updates it,
+  // so the new psi goes to a second buffer (A.out)
+  float* obase = (mode == gen::EPI_UPDATE) ? ((EMBED && A.out) ? A.out : A.ep.psi) : A.out;
 #pragma unroll
   for (int a = 0; a < RPG; ++a) {
 #pragma unroll
@@ -791,7 +812,8 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
       v[a * R1 + q] = x;
     }
     Bfly<R1, true>::run(v + a * R1);
-    float2* orow = reinterpret_cast<float2*>(obase + (row0 + a) * nx);
+    float2* orow = reinterpret_cast<float2*>(obase + srow[a] * nx);
+    const bool own_row = !EMBED || srow[a] == row0 + a;  // aliases recompute, only the interior row stores psi
 #pragma unroll
     for (int r = 0; r < R1; ++r) {
       float2 val = v[a * R1 + r];  // 1/N lives in K^: no scale here (the host rejects ep.scale != 1)
@@ -802,12 +824,44 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
         val.x = rl_update(oa[a * R1 + r].x, val.x, ob[a * R1 + r].x, A.ep.up);
         val.y = rl_update(oa[a * R1 + r].y, val.y, ob[a * R1 + r].y, A.ep.up);
       }
-      if (!CHAIN || mode == gen::EPI_UPDATE) st_stream(orow + lane + 16 * r, val);  // psi is always stored
+      if ((!CHAIN || mode == gen::EPI_UPDATE) && own_row) st_stream(orow + lane + 16 * r, val);  // psi is always stored
       if (CHAIN) v[a * R1 + r] = val;
     }
   }
   __syncwarp();
-  if (CHAIN) rows_fwd_from_regs<M>(A, slab, row0, lane, T, v);
+  if (CHAIN && EMBED) {
+    // periodic continuation along x inside the row: samples outside [ox, ox + lx) take the interior sample they alias
+#pragma unroll
+    for (int a = 0; a < RPG; ++a)
+#pragma unroll
+      for (int r = 0; r < R1; ++r) slab[a * RS + lane + 16 * r] = v[a * R1 + r];
+    __syncwarp();
+#pragma unroll
+    for (int a = 0; a < RPG; ++a) {
+      const float* rowf = reinterpret_cast<const float*>(slab + a * RS);
+#pragma unroll
+      for (int r = 0; r < R1; ++r) {
+        const int p0 = 2 * (lane + 16 * r);
+        if (p0 < A.ox || p0 >= A.ox + A.lx) {
+          int sx = (p0 - A.ox) % A.lx;
+          if (sx < 0) sx += A.lx;
+          v[a * R1 + r].x = rowf[sx + A.ox];
+        }
+        if (p0 + 1 < A.ox || p0 + 1 >= A.ox + A.lx) {
+          int sx = (p0 + 1 - A.ox) % A.lx;
+          if (sx < 0) sx += A.lx;
+          v[a * R1 + r].y = rowf[sx + A.ox];
+        }
+      }
+    }
+    __syncwarp();
+    RowArgs B = A;  // the forward transform writes the OTHER spectrum buffer, at the row's own position
+    B.spec = A.spec_out;
+    B.nyq = A.nyq_out;
+    rows_fwd_from_regs<M>(B, slab, row0, lane, T, v);
+  } else if (CHAIN) {
+    rows_fwd_from_regs<M>(A, slab, row0, lane, T, v);
+  }
 }
 
 // CTA shape of the rows kernels (chained and plain): four CTAs of 128 threads per SM instead of two of 256 -- the same 16 warps, but
@@ -878,7 +932,7 @@ static __global__ void __launch_bounds__(kLinkThreads, LMVN_LINK_BLOCKS) k_rows_
 }
 
 // inverse x + pointwise + forward x of the next convolution, in place on the spectrum rows
-template <int M, int EPI>
+template <int M, int EPI, bool EMBED = false>
 static __global__ void __launch_bounds__(kLinkThreads, LMVN_LINK_BLOCKS) k_rows_inv_fwd(RowArgs A) {
   typedef Row2Cfg<M> CF;
   constexpr int GROUPS = kLinkThreads / 16;
@@ -906,7 +960,7 @@ static __global__ void __launch_bounds__(kLinkThreads, LMVN_LINK_BLOCKS) k_rows_
         prefetch_l2(reinterpret_cast<const char*>(A.ep.weights + nr * (2 * M)) + ob);
       }
     }
-    rows_inv_group<M, EPI, RowTwShared<M>, true>(A, slab, row0, lane, T);
+    rows_inv_group<M, EPI, RowTwShared<M>, true, EMBED>(A, slab, row0, lane, T);
   }
 }
 

@@ -190,10 +190,15 @@ struct FastEngine : ConvEngine, FastOps {
     const size_t smem = size_t(groups) * CF::RPG * CF::RS * sizeof(cplx);
     auto k1 = fast::k_rows_inv_fwd<MM, gen::EPI_QUOTIENT>;
     auto k2 = fast::k_rows_inv_fwd<MM, gen::EPI_UPDATE>;
+    auto e1 = fast::k_rows_inv_fwd<MM, gen::EPI_QUOTIENT, true>;
+    auto e2 = fast::k_rows_inv_fwd<MM, gen::EPI_UPDATE, true>;
+    const bool emb = a.spec_out != nullptr;
     if (a.ep.mode == gen::EPI_QUOTIENT) {
-      LMVN_LAUNCH(k1, grid, dim3(fast::kLinkThreads), smem, s, a);
+      if (emb) { LMVN_LAUNCH(e1, grid, dim3(fast::kLinkThreads), smem, s, a); }
+      else { LMVN_LAUNCH(k1, grid, dim3(fast::kLinkThreads), smem, s, a); }
     } else {
-      LMVN_LAUNCH(k2, grid, dim3(fast::kLinkThreads), smem, s, a);
+      if (emb) { LMVN_LAUNCH(e2, grid, dim3(fast::kLinkThreads), smem, s, a); }
+      else { LMVN_LAUNCH(k2, grid, dim3(fast::kLinkThreads), smem, s, a); }
     }
     return 0;
   }
@@ -441,7 +446,8 @@ struct FastEngine : ConvEngine, FastOps {
   }
 
   // x inverse + pointwise + x forward of the result, in place on the rows of `spec`
-  int rows_inv_fwd(cplx* spec, const gen::Epilogue& ep, cudaStream_t s, int nzs = -1) {
+  int rows_inv_fwd(cplx* spec, const gen::Epilogue& ep, cudaStream_t s, int nzs = -1, cplx* spec_out = nullptr,
+                   const int* logical = nullptr, const int* offset = nullptr, float* psi_out = nullptr) {
     if (ep.scale != 1.f || (ep.mode != gen::EPI_QUOTIENT && ep.mode != gen::EPI_UPDATE)) {
       set_last_error("chained rows pass: quotient or update epilogue with unit scale expected");
       return -1;
@@ -454,6 +460,15 @@ struct FastEngine : ConvEngine, FastOps {
     a.tw_m = d_tw_m; a.tw_nx = d_tw_nx; a.tw_h = d_tw_h;
     a.prefetch = rows_prefetch;
     a.nyq = split ? nyq_of(spec) : nullptr;
+    if (spec_out) {
+      if (M > 256 || !logical || !offset) { set_last_error("chained embedded rows pass: unsupported"); return -1; }
+      a.spec_out = spec_out;
+      a.nyq_out = split ? nyq_of(spec_out) : nullptr;
+      a.out = psi_out;
+      a.lz = logical[0]; a.ly = logical[1]; a.lx = logical[2];
+      a.oz = offset[0]; a.oy = offset[1]; a.ox = offset[2];
+      a.prefetch = 0;  // the rows read are not the rows of the next loop iteration
+    }
     switch (M) {
       case 32: LMVN_TRY(launch_rows_inv_fwd<32>(a, s)); break;
       case 64: LMVN_TRY(launch_rows_inv_fwd<64>(a, s)); break;
@@ -500,6 +515,11 @@ struct FastEngine : ConvEngine, FastOps {
   int chain_link(cplx* work, const gen::Epilogue& ep, cudaStream_t s) override { return rows_inv_fwd(work, ep, s); }
   int chain_end(cplx* work, const gen::Epilogue& ep, float* out, cudaStream_t s) override {
     return rows_inv(work, out, ep, s);
+  }
+  bool can_chain_embedded() const override { return chain_ok && M <= 256; }
+  int chain_link_embedded(cplx* in, cplx* out, const gen::Epilogue& ep, float* psi_out, const int* logical,
+                          const int* offset, cudaStream_t s) override {
+    return rows_inv_fwd(in, ep, s, -1, out, logical, offset, psi_out);
   }
 
   int kernel_spectrum(const float* d_kernel, const int kd[3], cplx* khat, cplx*, cudaStream_t s) override {

@@ -183,3 +183,20 @@ def test_fused_equals_generic_closely(L):
         outs[strat] = psi
     L.set_default_strategy(capi.STRATEGY_AUTO)
     assert pc.max_rel(outs[capi.STRATEGY_FUSED], outs[capi.STRATEGY_GENERIC]) < 1e-5
+
+
+def test_embedded_chained_equals_unchained(L, monkeypatch):
+    """the chained link kernel continues the stack periodically by itself (aliased rows recompute their interior row,
+    out-of-place spectrum and psi): bit-identical to refilling the exterior before every five-pass convolution"""
+    from libmultiviewnative_b200.synthetic import make_views
+
+    dims = (30, 28, 40)
+    d = make_views(dims, num_views=3, kernel_size=5, n_sources=10, workers=1)
+    outs = {}
+    for chain in ("1", "0"):
+        monkeypatch.setenv("LMVN_CHAIN", chain)
+        psi = d["psi0"].copy()
+        L.inplace_gpu_deconvolve(psi, d["views"], d["kernels1"], d["kernels2"], d["weights"], 3, 0.006, 1e-4)
+        assert L.last_geometry() == pc.GEOMETRY_EMBEDDED
+        outs[chain] = psi
+    np.testing.assert_array_equal(outs["1"], outs["0"])
