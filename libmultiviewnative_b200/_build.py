@@ -75,25 +75,33 @@ def build_cuda(force: bool = False, verbose: bool = False, out: str = None, defi
     return target
 
 
-def build_emu(force: bool = False) -> str:
+EMU_ASAN_PATH = os.path.join(EMU_DIR, "_lmvn_emu_asan.so")
+
+
+def build_emu(force: bool = False, asan: bool = False) -> str:
+    """asan=True: the same library under AddressSanitizer with red zones between the sub-buffers of the device
+    arenas (-DLMVN_ARENA_REDZONE) -- the bounds check of the kernels' index math (tests/test_emu_asan.py)."""
     emu_srcs = [os.path.join(EMU_DIR, "cuda_emu.cpp"), os.path.join(EMU_DIR, "cuda_emu.h")]
-    if not force and not _stale(EMU_PATH, emu_srcs):
-        return EMU_PATH
+    target = EMU_ASAN_PATH if asan else EMU_PATH
+    if not force and not _stale(target, emu_srcs):
+        return target
     cxx = shutil.which("g++") or "g++"
     cmd = [cxx, "-O2", "-g", "-std=c++17", "-shared", "-fPIC", "-fopenmp", "-DLMVN_EMU",
            "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function",
            "-I", EMU_DIR, "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    if asan:
+        cmd += ["-fsanitize=address", "-fno-omit-frame-pointer", "-DLMVN_ARENA_REDZONE"]
     srcs = list(CUDA_SOURCES)
     cmd += ["-DLMVN_HAVE_FUSED"]
     for s in srcs:
         cmd += ["-x", "c++", os.path.join(CSRC, s)]
     cmd += ["-x", "c++", os.path.join(CSRC, "cpu_path.cpp"), os.path.join(EMU_DIR, "cuda_emu.cpp")]
-    cmd += ["-o", EMU_PATH]
+    cmd += ["-o", target]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("g++ build of the emulated test library failed")
-    return EMU_PATH
+    return target
 
 
 if __name__ == "__main__":

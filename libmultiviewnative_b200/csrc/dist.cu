@@ -178,7 +178,10 @@ struct DistDeconv {
 #ifndef LMVN_EMU
     if (sweep_graph) cudaGraphExecDestroy(sweep_graph);
 #endif
-    if (arena) cudaFree(arena);
+    if (arena) {
+      arena_unpoison(arena, arena_bytes);
+      cudaFree(arena);
+    }
 #ifndef LMVN_EMU
     if (xchg) cudaFree(xchg);
 #endif
@@ -213,7 +216,7 @@ struct DistDeconv {
     const size_t K = align_up_(pencil_spec() * sizeof(cplx), 256);
     kernel_stage_elems = std::min<size_t>(size_t(1) << 24, size_t(nz) * ny * nx);
     const size_t KS = align_up_(kernel_stage_elems * sizeof(float), 256);
-    arena_bytes = 2 * S + KS + size_t(nviews) * (2 * S + 2 * K);
+    arena_bytes = 2 * S + KS + size_t(nviews) * (2 * S + 2 * K) + kArenaRedzone * (3 + 4 * size_t(nviews));
     slab_off = 0;
     pencil_off = align_up_(slab_spec() * sizeof(cplx), 256);
     flags_off = pencil_off + align_up_(pencil_spec() * sizeof(cplx), 256);
@@ -239,7 +242,13 @@ struct DistDeconv {
     LMVN_CUDA_TRY(cudaMemset(d_epoch, 0, sizeof(unsigned)));
     if (const char* e = getenv("LMVN_GRAPH")) use_graph = (*e != '0');
     unsigned char* p = arena;
-    auto take = [&](size_t bytes) { unsigned char* r = p; p += bytes; return r; };
+    auto take = [&](size_t bytes) {
+      unsigned char* r = p;
+      p += bytes;
+      arena_poison(p, kArenaRedzone);
+      p += kArenaRedzone;
+      return r;
+    };
     psi = reinterpret_cast<float*>(take(S));
     integral = reinterpret_cast<float*>(take(S));
     kernel_stage = reinterpret_cast<float*>(take(KS));

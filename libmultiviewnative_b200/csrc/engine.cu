@@ -317,7 +317,10 @@ Deconv::~Deconv() {
   if (sweep_graph) cudaGraphExecDestroy(sweep_graph);
 #endif
   if (stream) cudaStreamDestroy(stream);
-  if (arena) park(device, arena, arena_capacity);
+  if (arena) {
+    arena_unpoison(arena, arena_capacity);
+    park(device, arena, arena_capacity);
+  }
 }
 
 static const size_t kMaxKernelVoxels = size_t(1) << 24;
@@ -365,7 +368,7 @@ int Deconv::init(const int* d, int nviews, int dev, int strategy) {
   // `integral` is sized like a spectrum buffer: the chained loop of an embedded plan never stores the quotient
   // and uses it as its second spectrum buffer
   const size_t SI = std::max(S, W);
-  arena_bytes = 3 * SI + W + KS + size_t(nviews) * (2 * S + 2 * K);
+  arena_bytes = 3 * SI + W + KS + size_t(nviews) * (2 * S + 2 * K) + kArenaRedzone * (5 + 4 * size_t(nviews));
   arena = take_parked(device, arena_bytes, &arena_capacity);
   if (!arena) {
     size_t free_b = 0, total_b = 0;
@@ -381,7 +384,14 @@ int Deconv::init(const int* d, int nviews, int dev, int strategy) {
   }
   lap("arena");
   unsigned char* p = arena;
-  auto take = [&](size_t bytes) { unsigned char* r = p; p += bytes; return r; };
+  arena_unpoison(arena, arena_capacity);
+  auto take = [&](size_t bytes) {
+    unsigned char* r = p;
+    p += bytes;
+    arena_poison(p, kArenaRedzone);
+    p += kArenaRedzone;
+    return r;
+  };
   psi = reinterpret_cast<float*>(take(SI));   // psi, psi2 and integral can change roles (lmvn_plan_convolve swaps
   psi2 = reinterpret_cast<float*>(take(SI));  // psi and integral): all three have the spectrum-buffer size
   integral = reinterpret_cast<float*>(take(SI));
@@ -587,12 +597,13 @@ int Deconv::iterate(int iterations, double lambda, float min_value, float* devic
       }
     }
   } else if (engine->can_chain() && iterations > 0) {
+    const int zero_guard = padded ? 1 : 0;  // zero-padded stacks: see Epilogue::zero_view_guard
     // chained loop: every x-inverse pass also runs the x-forward pass of the convolution that follows it
     auto sweep = [&](bool ends_call) -> int {  // one iteration = one sweep over all views
       for (int v = 0; v < num_views; ++v) {
         LMVN_TRY(engine->chain_middle(work, khat1[v], stream));
         // (view_v / (psi (*) kernel1_v)) stays on chip and is transformed again   ref: src/multiviewnative.cpp:195-205
-        gen::Epilogue e1{gen::EPI_QUOTIENT, 1.f, image[v], nullptr, nullptr, up};
+        gen::Epilogue e1{gen::EPI_QUOTIENT, 1.f, image[v], nullptr, nullptr, up, zero_guard};
         LMVN_TRY(engine->chain_link(work, e1, stream));
         LMVN_TRY(engine->chain_middle(work, khat2[v], stream));
         // psi = update(psi, ., weights_v); the new psi is stored AND transformed for the next view   ref: :209-227
@@ -636,7 +647,7 @@ int Deconv::iterate(int iterations, double lambda, float min_value, float* devic
     for (int it = 0; it < iterations; ++it) {
       for (int v = 0; v < num_views; ++v) {
         // integral = view_v / (psi (*) kernel1_v)      ref: src/multiviewnative.cpp:195-205
-        gen::Epilogue e1{gen::EPI_QUOTIENT, 1.f, image[v], nullptr, nullptr, up};
+        gen::Epilogue e1{gen::EPI_QUOTIENT, 1.f, image[v], nullptr, nullptr, up, padded ? 1 : 0};
         LMVN_TRY(engine->convolve(psi, work, khat1[v], e1, integral, stream));
         // psi = update(psi, integral (*) kernel2_v, weights_v)   ref: :209-227
         gen::Epilogue e2{gen::EPI_UPDATE, 1.f, nullptr, psi, weights[v], up};
@@ -714,7 +725,7 @@ int Deconv::profile(double lambda, float min_value, std::vector<std::string>& na
   if (chain) rc = engine->chain_begin(psi, work, stream);
   if (rc == 0) rc = t.begin(stream);
   engine->timer = &t;
-  gen::Epilogue e1{gen::EPI_QUOTIENT, 1.f, image[0], nullptr, nullptr, up};
+  gen::Epilogue e1{gen::EPI_QUOTIENT, 1.f, image[0], nullptr, nullptr, up, (padded && !periodic) ? 1 : 0};
   gen::Epilogue e2{gen::EPI_UPDATE, 1.f, nullptr, psi, weights[0], up};
   if (chain) {
     if (rc == 0) rc = engine->chain_middle(work, khat1[0], stream);

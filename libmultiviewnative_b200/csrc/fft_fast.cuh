@@ -818,8 +818,8 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
     for (int r = 0; r < R1; ++r) {
       float2 val = v[a * R1 + r];  // 1/N lives in K^: no scale here (the host rejects ep.scale != 1)
       if (mode == gen::EPI_QUOTIENT) {
-        val.x = quotient(oa[a * R1 + r].x, val.x);
-        val.y = quotient(oa[a * R1 + r].y, val.y);
+        val.x = quotient(oa[a * R1 + r].x, val.x, A.ep.zero_view_guard);
+        val.y = quotient(oa[a * R1 + r].y, val.y, A.ep.zero_view_guard);
       } else if (mode == gen::EPI_UPDATE) {
         val.x = rl_update(oa[a * R1 + r].x, val.x, ob[a * R1 + r].x, A.ep.up);
         val.y = rl_update(oa[a * R1 + r].y, val.y, ob[a * R1 + r].y, A.ep.up);
@@ -1175,8 +1175,9 @@ __device__ __forceinline__ void rows_inv_wide_group(const RowArgs& A, cplx* slab
       const int rr = CH * h + r;
       float4 val = make_float4(ve[rr].x, ve[rr].y, vo[rr].x, vo[rr].y);  // 1/N lives in K^: no scale here
       if (EPI == gen::EPI_QUOTIENT) {
-        val.x = quotient(oa[r].x, val.x); val.y = quotient(oa[r].y, val.y);
-        val.z = quotient(oa[r].z, val.z); val.w = quotient(oa[r].w, val.w);
+        const int zg = A.ep.zero_view_guard;
+        val.x = quotient(oa[r].x, val.x, zg); val.y = quotient(oa[r].y, val.y, zg);
+        val.z = quotient(oa[r].z, val.z, zg); val.w = quotient(oa[r].w, val.w, zg);
       } else if (EPI == gen::EPI_UPDATE) {
         val.x = rl_update(oa[r].x, val.x, ob[r].x, A.ep.up); val.y = rl_update(oa[r].y, val.y, ob[r].y, A.ep.up);
         val.z = rl_update(oa[r].z, val.z, ob[r].z, A.ep.up); val.w = rl_update(oa[r].w, val.w, ob[r].w, A.ep.up);

@@ -166,7 +166,7 @@ static __global__ void k_rows_inv(const cplx* __restrict__ spec, float* __restri
     if (ep.mode == EPI_STORE) {
       out[idx] = val;
     } else if (ep.mode == EPI_QUOTIENT) {
-      out[idx] = quotient(ep.view[idx], val);
+      out[idx] = quotient(ep.view[idx], val, ep.zero_view_guard);
     } else {
       ep.psi[idx] = rl_update(ep.psi[idx], val, ep.weights[idx], ep.up);
     }

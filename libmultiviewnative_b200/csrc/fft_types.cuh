@@ -62,6 +62,11 @@ struct Epilogue {
   float* psi;            // EPI_UPDATE: psi = update(psi, value, weights) (out is ignored)
   const float* weights;
   UpdateParams up;
+  // EPI_QUOTIENT on zero-padded stacks: a zero of the view gives a zero quotient whatever the blurred value is.
+  // The padding of the view is exactly zero and the blurred estimate there is round-off noise that may be exactly
+  // zero too (extents rounded up to a fast-path size leave padding no kernel tap reaches); 0 * (1 / 0) would be a
+  // NaN that the second convolution spreads over the whole stack.
+  int zero_view_guard;
 };
 
 // Source index of target position t for a kernel of extent k wrapped into n

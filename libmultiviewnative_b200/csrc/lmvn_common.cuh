@@ -24,6 +24,23 @@
 #include <cstring>
 #include <string>
 
+// Test builds under AddressSanitizer (host emulation, -DLMVN_ARENA_REDZONE): poisoned red zones between the
+// sub-buffers carved out of a device arena, so that index math that strays into a neighbouring buffer is reported.
+#if defined(LMVN_EMU) && defined(LMVN_ARENA_REDZONE)
+#include <sanitizer/asan_interface.h>
+namespace lmvn {
+static const size_t kArenaRedzone = 4096;
+inline void arena_poison(void* p, size_t n) { ASAN_POISON_MEMORY_REGION(p, n); }
+inline void arena_unpoison(void* p, size_t n) { ASAN_UNPOISON_MEMORY_REGION(p, n); }
+}  // namespace lmvn
+#else
+namespace lmvn {
+static const size_t kArenaRedzone = 0;
+inline void arena_poison(void*, size_t) {}
+inline void arena_unpoison(void*, size_t) {}
+}  // namespace lmvn
+#endif
+
 namespace lmvn {
 
 typedef float2 cplx;

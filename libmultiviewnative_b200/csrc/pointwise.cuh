@@ -28,6 +28,12 @@ __device__ __forceinline__ float quotient(float view, float blurred) {
 #endif
 }
 
+// zero-padded stacks (Epilogue::zero_view_guard): the quotient of a zero voxel of the view is zero
+__device__ __forceinline__ float quotient(float view, float blurred, int zero_view_guard) {
+  const float q = quotient(view, blurred);
+  return (zero_view_guard && view == 0.f) ? 0.f : q;
+}
+
 // Building blocks of the update.  It runs once per voxel inside the last transform pass; with IEEE-rounded
 // division and square root (range checks, slow paths: FCHK, BSSY/BSYNC, ~120 instructions per voxel) that
 // pass was bound by instruction issue, not by memory.  The MUFU approximations are within 1-2 ulp, three

@@ -114,7 +114,12 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
   }
   s.ctx.resize(s.nthreads);
   s.done.assign(s.nthreads, 0);
+#ifdef __SANITIZE_ADDRESS__
+  // exact, fresh allocation: AddressSanitizer then sees every access past the shared memory a launch asked for
+  std::vector<unsigned char>(smem ? smem : 1).swap(s.dyn_smem);
+#else
   s.dyn_smem.resize(smem + 16);
+#endif
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {

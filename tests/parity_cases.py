@@ -217,6 +217,9 @@ def case_legacy_iterate(L):
     assert rel_l2(im, orc.inplace_cpu_convolution(inp, k1)) <= 1e-5
 
 
+GEOMETRY_NATIVE, GEOMETRY_EMBEDDED, GEOMETRY_ZERO_PADDED = 1, 2, 3
+
+
 # ---- zero_padd mode (ref: inc/padd_utils.h:102-249; the reference's GPU geometry) ----------------
 def _zero_pad(a, kmax):
     ext = [a.shape[i] + kmax[i] - 1 for i in range(3)]
@@ -270,8 +273,33 @@ def case_zero_padd_deconvolve(L, dims, ksize, lam=0.006, iters=2):
     assert max_rel(got, exp) < PER_VOXEL_TOL_1_ITER
 
 
+def case_zero_padd_unreached_padding(L, dims=(12, 12, 28), k=5, iters=3, lam=0.006):
+    """Constant views and box kernels on extents that round up to a fast-path size (x: 32 -> 64): part of the
+    padding is out of reach of every kernel tap, the blurred estimate there is round-off noise with exact zeros, and
+    0 * (1 / 0) must not poison the stack.  Expected: the same deconvolution at the reference's own extents
+    (image + kernel - 1, where every padding voxel is within reach)."""
+    nv = 2
+    views = [np.full(dims, 16 + 4 * v, dtype=F32) for v in range(nv)]
+    weights = [np.ones(dims, dtype=F32) for _ in range(nv)]
+    k1 = [np.full((k, k, k), (v + 1) / k ** 3, dtype=F32) for v in range(nv)]
+    k2 = [np.full((k, k, k), (v + 2) / k ** 3, dtype=F32) for v in range(nv)]
+    psi0 = np.full(dims, 16, dtype=F32)
+    kmax = [k, k, k]
+    ppsi, off = _zero_pad(psi0, kmax)
+    exp = _crop(orc.inplace_cpu_deconvolve(ppsi, [_zero_pad(v, kmax)[0] for v in views], k1, k2,
+                                           [_zero_pad(w, kmax)[0] for w in weights], iters, lam, 1e-3), off, dims)
+    assert np.isfinite(exp).all() and exp.min() > 0.1
+    L.set_padding(1)
+    try:
+        got = psi0.copy()
+        L.inplace_gpu_deconvolve(got, views, k1, k2, weights, iters, lam, 1e-3)
+        assert L.last_geometry() == GEOMETRY_ZERO_PADDED
+    finally:
+        L.set_padding(0)
+    assert max_rel(got, exp) < 1e-4
+
+
 # ---- periodic embedding: circular semantics on the fast path for arbitrary extents ---------------
-GEOMETRY_NATIVE, GEOMETRY_EMBEDDED, GEOMETRY_ZERO_PADDED = 1, 2, 3
 
 
 def case_embedded_convolution(L, dims, kdims, expect_embedded=True):

@@ -57,6 +57,10 @@ def test_zero_padd_deconvolve(L):
     pc.case_zero_padd_deconvolve(L, (10, 12, 14), 5)
 
 
+def test_zero_padd_padding_out_of_reach_of_the_kernels(L):
+    pc.case_zero_padd_unreached_padding(L)
+
+
 @pytest.mark.parametrize("dims,kdims", [((20, 24, 50), (5, 7, 9)), ((28, 30, 50), (4, 3, 2)), ((27, 27, 27), (3, 3, 3))])
 def test_embedded_convolution(L, dims, kdims):
     pc.case_embedded_convolution(L, dims, kdims)

@@ -89,6 +89,10 @@ def test_zero_padd_deconvolve(L):
     pc.case_zero_padd_deconvolve(L, (100, 100, 100), 21)
 
 
+def test_zero_padd_padding_out_of_reach_of_the_kernels(L):
+    pc.case_zero_padd_unreached_padding(L)
+
+
 @pytest.mark.parametrize("dims,kdims", [((20, 24, 50), (5, 7, 9)), ((28, 30, 50), (4, 3, 2)), ((100, 120, 200), (21, 21, 21)),
                                         ((200, 200, 200), (41, 41, 41))])
 def test_embedded_convolution(L, dims, kdims):
