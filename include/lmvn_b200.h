@@ -60,7 +60,9 @@ LMVN_EXPORT int lmvn_plan_create(lmvn_plan** out, const int* dims_zyx, int num_v
 /* zero_padd mode of the reference's GPU path (ref: inc/padd_utils.h:102-249, src/gpu_deconvolve_methods.cuh:366-449):
  * the plan works on image + kernel - 1 extents (rounded up to a fast-path extent when that is cheap), the caller's
  * stacks keep the image extents and sit at offset (kernel - 1) / 2; uploads zero-fill, get_psi crops.  Linear instead of
- * circular convolution at the image borders.  lmvn_set_padding / env LMVN_PAD=zero switch the one-shot entry points
+ * circular convolution at the image borders.  One rule differs from the reference's arithmetic: the quotient of a voxel
+ * whose view is exactly zero (all of the padding) is zero; the reference computes 0 * (1 / blurred) there, which is the
+ * same number unless blurred is exactly zero -- then it is a NaN that the second convolution spreads over the stack.  lmvn_set_padding / env LMVN_PAD=zero switch the one-shot entry points
  * (inplace_gpu_deconvolve, inplace_gpu_convolution) to it; the default is the CPU path's circular geometry. */
 enum lmvn_padding { LMVN_PAD_NONE = 0, LMVN_PAD_ZERO = 1 };
 LMVN_EXPORT int lmvn_set_padding(int mode);

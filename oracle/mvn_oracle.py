@@ -159,8 +159,13 @@ def _workers(nthreads: int) -> int:
 
 
 def inplace_cpu_deconvolve(psi, views, kernels1, kernels2, weights, num_iterations,
-                           lam=0.0, min_value=1e-4, nthreads=1, khats=None):
+                           lam=0.0, min_value=1e-4, nthreads=1, khats=None, zero_view_guard=False):
     """Multi-view Richardson-Lucy (Tikhonov if lam > 0).
+
+    zero_view_guard (NOT in the reference; the rule of the new build's zero_padd mode): the
+    quotient of a voxel whose view is exactly zero is zero, whatever the blurred estimate is.  Explicitly
+    zero-padded stacks otherwise hit 0 * (1 / 0) = NaN in padding the kernels barely reach, and the second
+    convolution spreads it over the stack (the reference's GPU path does, ref: inc/cuda_kernels.cuh:14-31).
 
     psi: (nz,ny,nx) float32 start value; views/weights: sequences of the same
     shape; kernels1/kernels2: sequences of small 3-D PSFs.  Returns the new psi.
@@ -183,6 +188,8 @@ def inplace_cpu_deconvolve(psi, views, kernels1, kernels2, weights, num_iteratio
         for v in range(nviews):
             integral = half_inplace(psi, k1[v], w)  # :195-201
             integral = compute_quotient(np.asarray(views[v], dtype=F32), integral)  # :204
+            if zero_view_guard:
+                integral = np.where(np.asarray(views[v]) == 0, F32(0), integral).astype(F32, copy=False)
             integral = half_inplace(integral, k2[v], w)  # :209-211
             if lam > 0:  # :216
                 psi = regularized_final_values(psi, integral, np.asarray(weights[v], dtype=F32), lam, min_value)
