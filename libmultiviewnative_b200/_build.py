@@ -76,13 +76,16 @@ def build_cuda(force: bool = False, verbose: bool = False, out: str = None, defi
 
 
 EMU_ASAN_PATH = os.path.join(EMU_DIR, "_lmvn_emu_asan.so")
+EMU_UBSAN_PATH = os.path.join(EMU_DIR, "_lmvn_emu_ubsan.so")
 
 
-def build_emu(force: bool = False, asan: bool = False) -> str:
+def build_emu(force: bool = False, asan: bool = False, ubsan: bool = False) -> str:
     """asan=True: the same library under AddressSanitizer with red zones between the sub-buffers of the device
-    arenas (-DLMVN_ARENA_REDZONE) -- the bounds check of the kernels' index math (tests/test_emu_asan.py)."""
+    arenas (-DLMVN_ARENA_REDZONE) -- the bounds check of the kernels' index math (tests/test_abi_walk.py).
+    ubsan=True: under UndefinedBehaviorSanitizer, trapping -- misaligned float2 / float4 accesses (they fault on the
+    device), signed overflow in index arithmetic, out-of-range shifts."""
     emu_srcs = [os.path.join(EMU_DIR, "cuda_emu.cpp"), os.path.join(EMU_DIR, "cuda_emu.h")]
-    target = EMU_ASAN_PATH if asan else EMU_PATH
+    target = EMU_ASAN_PATH if asan else (EMU_UBSAN_PATH if ubsan else EMU_PATH)
     if not force and not _stale(target, emu_srcs):
         return target
     cxx = shutil.which("g++") or "g++"
@@ -91,6 +94,8 @@ def build_emu(force: bool = False, asan: bool = False) -> str:
            "-I", EMU_DIR, "-I", os.path.join(ROOT, "include"), "-I", CSRC]
     if asan:
         cmd += ["-fsanitize=address", "-fno-omit-frame-pointer", "-DLMVN_ARENA_REDZONE"]
+    elif ubsan:
+        cmd += ["-fsanitize=undefined", "-fno-sanitize-recover=all", "-fno-omit-frame-pointer"]
     srcs = list(CUDA_SOURCES)
     cmd += ["-DLMVN_HAVE_FUSED"]
     for s in srcs:

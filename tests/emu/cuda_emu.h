@@ -28,7 +28,7 @@
 #include <vector>
 
 // ---- vector types ---------------------------------------------------------
-struct float2 { float x, y; };
+struct alignas(8) float2 { float x, y; };  // CUDA's alignment: a misaligned access faults on the device
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(16) int4 { int x, y, z, w; };
 struct uint3 { unsigned x, y, z; };
