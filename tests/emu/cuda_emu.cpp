@@ -112,6 +112,20 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
     s.stacks.resize(s.nthreads);
     for (size_t i = old; i < s.nthreads; ++i) s.stacks[i] = static_cast<char*>(std::malloc(kStack));
   }
+  static const int order = [] {
+    const char* e = std::getenv("LMVN_EMU_ORDER");
+    return !e ? 0 : (e[0] == 'r' ? 1 : (e[0] == 's' ? 2 : 0));
+  }();
+  static std::vector<unsigned> perm;
+  if (order == 2 && perm.size() != s.nthreads) {
+    perm.resize(s.nthreads);
+    for (unsigned i = 0; i < s.nthreads; ++i) perm[i] = i;
+    unsigned long long x = 0x2545F4914F6CDD1Dull;  // fixed seed: runs are reproducible
+    for (unsigned i = s.nthreads; i > 1; --i) {
+      x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+      std::swap(perm[i - 1], perm[x % i]);
+    }
+  }
   s.ctx.resize(s.nthreads);
   s.done.assign(s.nthreads, 0);
 #ifdef __SANITIZE_ADDRESS__
@@ -142,7 +156,11 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
         unsigned long spins = 0;
         while (remaining) {
           unsigned before = remaining;
-          for (unsigned t = 0; t < s.nthreads; ++t) {
+          for (unsigned k = 0; k < s.nthreads; ++k) {
+            // LMVN_EMU_ORDER=reverse | shuffle: threads run one after the other up to their next barrier, so a missing
+            // barrier shows as a stale or poisoned read under one of the orders (the race check of the shared-memory
+            // exchanges; tools/run_emu_sanitized.py --order)
+            const unsigned t = order == 1 ? s.nthreads - 1 - k : (order == 2 ? perm[k] : k);
             if (s.done[t]) continue;
             set_thread(t);
             swapcontext(&s.main_ctx, &s.ctx[t]);

@@ -49,6 +49,20 @@ def test_abi_walk_under_address_sanitizer(tmp_path):
     assert out.count(" OK") >= 12, out
 
 
+@pytest.mark.parametrize("order", ["reverse", "shuffle"])
+def test_abi_walk_with_other_thread_orders(tmp_path, order):
+    """The emulated threads of a block run one after the other up to their next barrier; under another order a missing
+    barrier in a shared-memory exchange reads stale or poisoned data (tools/run_emu_sanitized.py --order runs all
+    emulator parity cases this way)."""
+    exe = _compile(os.path.join(str(tmp_path), "abi_walk_emu"), _build.build_emu())
+    env = dict(os.environ, LMVN_EMU_ORDER=order)
+    res = subprocess.run([exe, "fast/32x64x64", "conv/fast", "embedded/20x24x28", "slabs/32x32x64"], capture_output=True,
+                         text=True, timeout=900, env=env)
+    out = res.stdout + res.stderr
+    assert res.returncode == 0 and "0 case(s) failed" in out and "MISMATCH" not in out, out[-6000:]
+    assert out.count(" OK") >= 5, out
+
+
 @pytest.mark.gpu
 def test_abi_walk_on_the_gpu(tmp_path):
     lib = _build.build_cuda()

@@ -6,7 +6,12 @@ AddressSanitizer (red zones between the arena sub-buffers, exactly sized shared 
 UndefinedBehaviorSanitizer, trapping (misaligned float2 / float4 accesses, signed overflow, shifts):
     python tools/run_emu_sanitized.py --ubsan
 
-About 5 minutes each; the CPU suite itself runs the shorter tests/test_abi_walk.py.
+Race check of the shared-memory exchanges (plain emulator build; the emulated threads of a block run one after the
+other up to their next barrier, in this order -- a missing barrier gives a stale or poisoned read under one of them):
+    python tools/run_emu_sanitized.py --order reverse
+    python tools/run_emu_sanitized.py --order shuffle
+
+A few minutes each; the CPU suite itself runs the shorter tests/test_abi_walk.py.
 """
 import os
 import sys
@@ -20,9 +25,15 @@ from libmultiviewnative_b200 import _build  # noqa: E402
 args = sys.argv[1:]
 ubsan = "--ubsan" in args
 args = [a for a in args if a != "--ubsan"]
-if not ubsan and "libasan" not in os.environ.get("LD_PRELOAD", ""):
+order = None
+if "--order" in args:
+    i = args.index("--order")
+    order = args[i + 1]
+    del args[i:i + 2]
+    os.environ["LMVN_EMU_ORDER"] = order
+if order is None and not ubsan and "libasan" not in os.environ.get("LD_PRELOAD", ""):
     sys.exit("preload libasan (see the docstring): the interpreter itself is not an AddressSanitizer build")
-_path = _build.build_emu(ubsan=True) if ubsan else _build.build_emu(asan=True)
+_path = _build.build_emu() if order else (_build.build_emu(ubsan=True) if ubsan else _build.build_emu(asan=True))
 _build.build_emu = lambda force=False, asan=False, ubsan=False: _path  # the fixtures load whatever build_emu() returns
 
 import pytest  # noqa: E402
