@@ -236,6 +236,11 @@ template <> struct Radix<128> { static const int S = 3, R1 = 8, R2 = 4, R3 = 4; 
 // 1024 keeps three stages: a 32 x 32 plan would need 64 registers of K^ next to 64 of data in the merged z pass
 template <> struct Radix<1024> { static const int S = 3, R1 = 16, R2 = 16, R3 = 4; };
 template <> struct Radix<64> { static const int S = 2, R1 = 8, R2 = 8, R3 = 1; };
+// ALT = 1: the plan of passes that never merge with the spectrum product (the y passes).  1024 = 32 x 32 there: two
+// stages, one exchange.  The digit-reversed order of an axis depends on its plan, so an axis uses ONE plan everywhere
+// (forward, inverse, PSF spectra): y may take ALT, z (merged pass, K^ in registers) never does.
+template <int N, int ALT> struct Plan : Radix<N> {};
+template <> struct Plan<1024, 1> { static const int S = 2, R1 = 32, R2 = 32, R3 = 1; };
 template <> struct Radix<32> { static const int S = 2, R1 = 8, R2 = 4, R3 = 1; };
 template <> struct Radix<16> { static const int S = 2, R1 = 4, R2 = 4, R3 = 1; };
 
@@ -387,10 +392,10 @@ struct Middle {
 // One tile of a strided pass.  `sm`, `g`, `gk` already point at this thread's column; threads of
 // the padding columns of a ragged last tile pass live = false: they skip the stages (every stage
 // touches the thread's own column only) but still take part in the barriers.
-template <int N, int MODE_, int U>
+template <int N, int MODE_, int U, int ALT = 0>
 __device__ __forceinline__ void strided_tile(const StridedArgs& A, cplx* sm, cplx* g, const cplx* gk, bool live,
                                              long long sc_tile, int rs) {
-  typedef Radix<N> RX;
+  typedef Plan<N, ALT> RX;
   constexpr int COLS = Cols<N>::V;
   constexpr int R1 = RX::R1, R2 = RX::R2;
   constexpr int R3 = (RX::R3 > 1 ? RX::R3 : 2);  // placeholder radix for the dead 3-stage code of 2-stage sizes
@@ -443,9 +448,10 @@ __device__ __forceinline__ void strided_tile(const StridedArgs& A, cplx* sm, cpl
   }
 }
 
-template <int N, int MODE>
+template <int N, int MODE, int ALT = 0>
 static __global__ void __launch_bounds__(Threads<N>::V, StridedBlocks<N, MODE>::V * (kStridedThreads / Threads<N>::V))
     k_strided(StridedArgs A) {
+  static_assert(ALT == 0 || (MODE != SM_FWD_MUL_INV && MODE != SM_FWD_MUL_INV_SCATTER), "the merged pass keeps the default plan");
   constexpr int COLS = Cols<N>::V;
   LMVN_DYN_SMEM(cplx, smem);  // [N][COLS]
   const int c = threadIdx.x % COLS;
@@ -460,7 +466,7 @@ static __global__ void __launch_bounds__(Threads<N>::V, StridedBlocks<N, MODE>::
       // Nyquist plane: this thread's column is slow index s (the plane is small and L2 resident)
       const unsigned s = blockIdx.x * COLS + c;
       const long long nb = (long long)s * A.nyq_cs;
-      strided_tile<N, MODE, U>(A, smem + c, A.nyq + nb, A.nyq_khat + nb, s < A.slow, 0, A.nyq_rs);
+      strided_tile<N, MODE, U, ALT>(A, smem + c, A.nyq + nb, A.nyq_khat + nb, s < A.slow, 0, A.nyq_rs);
       return;
     }
     tiles_x = unsigned(A.tiles_x);
@@ -489,7 +495,7 @@ static __global__ void __launch_bounds__(Threads<N>::V, StridedBlocks<N, MODE>::
     }
   }
   const long long sc_tile = A.sc.offset + (long long)by * A.sc.tile_stride + col;
-  strided_tile<N, MODE, U>(A, smem + c, A.data + base, A.khat + base, col < A.ncols, sc_tile, A.row_stride);
+  strided_tile<N, MODE, U, ALT>(A, smem + c, A.data + base, A.khat + base, col < A.ncols, sc_tile, A.row_stride);
 }
 
 // ------------------------------------------------------------------------------

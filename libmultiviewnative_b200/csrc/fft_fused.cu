@@ -34,6 +34,7 @@ struct FastTables {
   cplx* tw_h = nullptr;  // nx = 1024: w_{M/2}
   cplx* tw_y[2] = {nullptr, nullptr};
   cplx* tw_z[2] = {nullptr, nullptr};
+  bool y_alt = false;  // ny = 1024: the y passes run the 32 x 32 plan (fast::Plan<1024, 1>), tw_y holds its tables
   ~FastTables() {
     cudaSetDevice(device);
     if (tw_h) cudaFree(tw_h);
@@ -62,6 +63,7 @@ struct FastEngine : ConvEngine, FastOps {
   cplx* d_tw_m = nullptr;
   cplx* d_tw_nx = nullptr;
   cplx* d_tw_h = nullptr;
+  bool y_alt = false;
   cplx* d_tw_y[2] = {nullptr, nullptr};  // per-stage tables of the y / z passes
   cplx* d_tw_z[2] = {nullptr, nullptr};
 
@@ -117,23 +119,29 @@ struct FastEngine : ConvEngine, FastOps {
         LMVN_TRY(upload_table(&t->tw_m, M, M));
         LMVN_TRY(upload_table(&t->tw_nx, plan->nx, M + 1));
         if (M == 512) LMVN_TRY(upload_table(&t->tw_h, M / 2, M / 2));
-        LMVN_TRY(upload_stage_tables(t->tw_y, plan->ny));
-        LMVN_TRY(upload_stage_tables(t->tw_z, plan->nz));
+        t->y_alt = (plan->ny == 1024);
+        if (const char* e = getenv("LMVN_Y1024_WIDE")) t->y_alt = t->y_alt && (*e != '0');
+        LMVN_TRY(upload_stage_tables(t->tw_y, plan->ny, t->y_alt));
+        LMVN_TRY(upload_stage_tables(t->tw_z, plan->nz, false));
         plan->fast_tables = t;
       }
       tables = std::static_pointer_cast<FastTables>(plan->fast_tables);
     }
     num_sms = tables->num_sms;
+    y_alt = tables->y_alt;
     d_tw_m = tables->tw_m; d_tw_nx = tables->tw_nx; d_tw_h = tables->tw_h;
     for (int i = 0; i < 2; ++i) { d_tw_y[i] = tables->tw_y[i]; d_tw_z[i] = tables->tw_z[i]; }
     return 0;
   }
 
   // [j][q] = w_L^{jq} for the first two stages of the radix plan of length n
-  static int upload_stage_tables(cplx** dst, int n) {
+  static int upload_stage_tables(cplx** dst, int n, bool alt) {
     int r1, r2;
     switch (n) {
-      case 1024: r1 = fast::Radix<1024>::R1; r2 = fast::Radix<1024>::R2; break;
+      case 1024:
+        r1 = alt ? fast::Plan<1024, 1>::R1 : fast::Radix<1024>::R1;
+        r2 = alt ? fast::Plan<1024, 1>::R2 : fast::Radix<1024>::R2;
+        break;
       case 512: r1 = fast::Radix<512>::R1; r2 = fast::Radix<512>::R2; break;
       case 256: r1 = fast::Radix<256>::R1; r2 = fast::Radix<256>::R2; break;
       case 128: r1 = fast::Radix<128>::R1; r2 = fast::Radix<128>::R2; break;
@@ -322,11 +330,11 @@ struct FastEngine : ConvEngine, FastOps {
     return 0;
   }
 
-  template <int N, int MODE>
+  template <int N, int MODE, int ALT = 0>
   int launch_strided(const fast::StridedArgs& a, dim3 grid, cudaStream_t s) {
     constexpr int COLS = fast::Cols<N>::V;
     const size_t smem = size_t(N) * COLS * sizeof(cplx);
-    auto kfn = fast::k_strided<N, MODE>;
+    auto kfn = fast::k_strided<N, MODE, ALT>;
     if (smem > 48 * 1024) {  // per device, cheap: set every time
       LMVN_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     }
@@ -342,6 +350,25 @@ struct FastEngine : ConvEngine, FastOps {
       case fast::SM_FWD_SCATTER: return launch_strided<N, fast::SM_FWD_SCATTER>(a, grid, s);
       case fast::SM_FWD_MUL_INV_SCATTER: return launch_strided<N, fast::SM_FWD_MUL_INV_SCATTER>(a, grid, s);
       default: return launch_strided<N, fast::SM_FWD_SCALE>(a, grid, s);
+    }
+  }
+  template <int N>
+  int launch_strided_axis(const fast::StridedArgs& a, int mode, dim3 grid, cudaStream_t s, bool alt) {
+    if constexpr (N == 1024) {  // the only length with an alternate plan: nothing else is instantiated twice
+      if (alt) return launch_strided_alt<N>(a, mode, grid, s);
+    }
+    (void)alt;
+    return launch_strided_mode<N>(a, mode, grid, s);
+  }
+  // passes of an axis on the alternate plan (never the merged pass)
+  template <int N>
+  int launch_strided_alt(const fast::StridedArgs& a, int mode, dim3 grid, cudaStream_t s) {
+    switch (mode) {
+      case fast::SM_FWD: return launch_strided<N, fast::SM_FWD, 1>(a, grid, s);
+      case fast::SM_INV: return launch_strided<N, fast::SM_INV, 1>(a, grid, s);
+      case fast::SM_FWD_SCATTER: return launch_strided<N, fast::SM_FWD_SCATTER, 1>(a, grid, s);
+      case fast::SM_FWD_SCALE: return launch_strided<N, fast::SM_FWD_SCALE, 1>(a, grid, s);
+      default: set_last_error("strided pass: mode %d has no alternate plan", mode); return -1;
     }
   }
 
@@ -409,7 +436,7 @@ struct FastEngine : ConvEngine, FastOps {
       a.nyq_groups = int(ceil_div(size_t(slow), size_t(fast::Cols<NN>::V)));                    \
       grid = dim3(unsigned(a.nyq_groups) + unsigned(a.tiles_x) * slow);                         \
     }                                                                                           \
-    rc = launch_strided_mode<NN>(a, mode, grid, s);                                             \
+    rc = launch_strided_axis<NN>(a, mode, grid, s, y_alt && g.tw_axis == 1);                    \
   } break;
     switch (g.n) {
       LMVN_STRIDED_CASE(16)
