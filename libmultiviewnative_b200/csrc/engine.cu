@@ -4,6 +4,9 @@
 #include "fft_generic.cuh"
 
 #include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -298,7 +301,12 @@ void park(int device, unsigned char* p, size_t bytes) {
 }
 }  // namespace
 
+namespace {
+void release_stagers();  // pinned staging rings (below)
+}
+
 void release_cached_memory() {
+  release_stagers();
   std::lock_guard<std::mutex> lk(g_arena_mu);
   for (auto& kv : g_parked)
     if (kv.second.p) {
@@ -454,17 +462,189 @@ int Deconv::wrap_exterior(float* vol) {
 }
 
 // host stack (logical extents) -> device volume (plan extents), zero filled around it
+// ---------------------------------------------------------------------------------
+// Host staging for PAGEABLE caller buffers.  Fiji hands the library JNA / malloc'ed memory (ref:
+// src/multiviewnative.cu:66); a cudaMemcpyAsync from such memory is staged by the driver on one thread at a
+// fraction of the PCIe rate.  Here: a small ring of pinned chunks per device, filled by several host threads
+// while the DMA of the previous chunk runs.  Pinned or registered buffers (cudaPointerGetAttributes) and small
+// copies take the direct path.  LMVN_STAGED_COPY=0 disables.
+// ---------------------------------------------------------------------------------
+namespace {
+#ifndef LMVN_EMU
+struct HostStager {
+  static const size_t kChunk = size_t(16) << 20;
+  static const int kSlots = 3;
+  std::mutex mu;
+  unsigned char* pinned[kSlots] = {nullptr, nullptr, nullptr};
+  cudaEvent_t done[kSlots] = {nullptr, nullptr, nullptr};
+  bool inflight[kSlots] = {false, false, false};  // the slot's last DMA may still be running (any stream of the device)
+  bool ready = false, failed = false;
+
+  int wait_slot(int slot) {
+    if (inflight[slot]) {
+      LMVN_CUDA_TRY(cudaEventSynchronize(done[slot]));
+      inflight[slot] = false;
+    }
+    return 0;
+  }
+  void release() {
+    std::lock_guard<std::mutex> lk(mu);
+    for (int i = 0; i < kSlots; ++i) {
+      if (inflight[i]) cudaEventSynchronize(done[i]);
+      inflight[i] = false;
+      if (pinned[i]) cudaFreeHost(pinned[i]);
+      if (done[i]) cudaEventDestroy(done[i]);
+      pinned[i] = nullptr;
+      done[i] = nullptr;
+    }
+    ready = false;
+  }
+  int init() {
+    if (ready) return 0;
+    if (failed) return -1;
+    for (int i = 0; i < kSlots; ++i) {
+      if (cudaHostAlloc(reinterpret_cast<void**>(&pinned[i]), kChunk, cudaHostAllocDefault) != cudaSuccess ||
+          cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) {
+        (void)cudaGetLastError();
+        failed = true;
+        return -1;
+      }
+    }
+    ready = true;
+    return 0;
+  }
+  static void parallel_copy(void* dst, const void* src, size_t bytes) {
+    const size_t piece = size_t(1) << 20;
+    const long long pieces = (long long)((bytes + piece - 1) / piece);
+    int threads = 1;
+#ifdef _OPENMP
+    threads = std::max(1, std::min(8, omp_get_max_threads()));
+#endif
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (long long i = 0; i < pieces; ++i) {
+      const size_t off = size_t(i) * piece;
+      std::memcpy(static_cast<unsigned char*>(dst) + off, static_cast<const unsigned char*>(src) + off,
+                  std::min(piece, bytes - off));
+    }
+  }
+  // host -> device, stream ordered on s; returns when src_h has been read completely (like a pageable cudaMemcpyAsync)
+  int upload(void* dst_d, const void* src_h, size_t bytes, cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(mu);
+    LMVN_TRY(init());
+    size_t off = 0;
+    for (int i = 0; off < bytes; ++i, off += kChunk) {
+      const int slot = i % kSlots;
+      const size_t len = std::min(kChunk, bytes - off);
+      LMVN_TRY(wait_slot(slot));
+      parallel_copy(pinned[slot], static_cast<const unsigned char*>(src_h) + off, len);
+      LMVN_CUDA_TRY(cudaMemcpyAsync(static_cast<unsigned char*>(dst_d) + off, pinned[slot], len, cudaMemcpyHostToDevice, s));
+      LMVN_CUDA_TRY(cudaEventRecord(done[slot], s));
+      inflight[slot] = true;
+    }
+    return 0;
+  }
+  // device -> host; returns when dst_h is complete
+  int download(void* dst_h, const void* src_d, size_t bytes, cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(mu);
+    LMVN_TRY(init());
+    const long long chunks = (long long)((bytes + kChunk - 1) / kChunk);
+    auto issue = [&](long long i) -> int {
+      const size_t off = size_t(i) * kChunk;
+      LMVN_TRY(wait_slot(int(i % kSlots)));
+      LMVN_CUDA_TRY(cudaMemcpyAsync(pinned[i % kSlots], static_cast<const unsigned char*>(src_d) + off,
+                                    std::min(kChunk, bytes - off), cudaMemcpyDeviceToHost, s));
+      LMVN_CUDA_TRY(cudaEventRecord(done[i % kSlots], s));
+      inflight[i % kSlots] = true;
+      return 0;
+    };
+    for (long long i = 0; i < std::min<long long>(chunks, kSlots - 1); ++i) LMVN_TRY(issue(i));
+    for (long long i = 0; i < chunks; ++i) {
+      if (i + kSlots - 1 < chunks) LMVN_TRY(issue(i + kSlots - 1));  // keep the DMA engine ahead of the host copy
+      LMVN_TRY(wait_slot(int(i % kSlots)));
+      const size_t off = size_t(i) * kChunk;
+      parallel_copy(static_cast<unsigned char*>(dst_h) + off, pinned[i % kSlots], std::min(kChunk, bytes - off));
+    }
+    return 0;
+  }
+};
+
+std::mutex g_stager_mu;
+std::map<int, HostStager*> g_stagers;  // per device, lives as long as the process (pinned memory is expensive to get)
+
+bool staged_copy_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LMVN_STAGED_COPY");
+    v = (e && *e == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// the stager of `device` when `host_ptr` is pageable and the copy is large enough to pay for it
+HostStager* stager_for(int device, const void* host_ptr, size_t bytes) {
+  if (bytes < (size_t(4) << 20) || !staged_copy_enabled()) return nullptr;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, host_ptr) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  if (attr.type != cudaMemoryTypeUnregistered) return nullptr;  // pinned / registered / managed: direct copy
+  std::lock_guard<std::mutex> lk(g_stager_mu);
+  HostStager*& st = g_stagers[device];
+  if (!st) st = new HostStager();
+  return st->failed ? nullptr : st;
+}
+
+void release_stagers() {
+  std::lock_guard<std::mutex> lk(g_stager_mu);
+  for (auto& kv : g_stagers)
+    if (kv.second) {
+      cudaSetDevice(kv.first);
+      kv.second->release();
+    }
+}
+
+int copy_to_device(int device, void* dst_d, const void* src_h, size_t bytes, cudaStream_t s) {
+  if (HostStager* st = stager_for(device, src_h, bytes)) {
+    if (st->upload(dst_d, src_h, bytes, s) == 0) return 0;
+    if (!st->failed) return -1;  // a copy failed: the error is set
+  }
+  LMVN_CUDA_TRY(cudaMemcpyAsync(dst_d, src_h, bytes, cudaMemcpyHostToDevice, s));
+  return 0;
+}
+
+int copy_to_host(int device, void* dst_h, const void* src_d, size_t bytes, cudaStream_t s) {
+  if (HostStager* st = stager_for(device, dst_h, bytes)) {
+    if (st->download(dst_h, src_d, bytes, s) == 0) return 0;
+    if (!st->failed) return -1;
+  }
+  LMVN_CUDA_TRY(cudaMemcpyAsync(dst_h, src_d, bytes, cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+#else   // host emulation: plain copies
+void release_stagers() {}
+int copy_to_device(int, void* dst_d, const void* src_h, size_t bytes, cudaStream_t s) {
+  LMVN_CUDA_TRY(cudaMemcpyAsync(dst_d, src_h, bytes, cudaMemcpyHostToDevice, s));
+  return 0;
+}
+int copy_to_host(int, void* dst_h, const void* src_d, size_t bytes, cudaStream_t s) {
+  LMVN_CUDA_TRY(cudaMemcpyAsync(dst_h, src_d, bytes, cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+#endif
+}  // namespace
+
 int Deconv::upload_stack(float* dst, const float* src_h) {
   const size_t n = engine->plan->voxels();
   if (!padded) {
-    LMVN_CUDA_TRY(cudaMemcpyAsync(dst, src_h, n * sizeof(float), cudaMemcpyHostToDevice, stream));
+    LMVN_TRY(copy_to_device(device, dst, src_h, n * sizeof(float), stream));
     return 0;
   }
   // one contiguous copy into the (idle) spectrum work buffer, then a kernel places the box and zero fills the rest
   (void)n;
   float* stage = reinterpret_cast<float*>(work);
   const size_t ln = size_t(logical[0]) * logical[1] * logical[2];
-  LMVN_CUDA_TRY(cudaMemcpyAsync(stage, src_h, ln * sizeof(float), cudaMemcpyHostToDevice, stream));
+  LMVN_TRY(copy_to_device(device, stage, src_h, ln * sizeof(float), stream));
   LMVN_LAUNCH(k_place_box, dim3(unsigned(dims[1]), unsigned(dims[0])), dim3(128), 0, stream, dst, stage, dims[1], dims[2],
               logical[0], logical[1], logical[2], offset[0], offset[1], offset[2]);
   LMVN_CUDA_TRY(cudaGetLastError());
@@ -473,15 +653,14 @@ int Deconv::upload_stack(float* dst, const float* src_h) {
 
 int Deconv::download_stack(float* dst_h, const float* src) {
   if (!padded) {
-    LMVN_CUDA_TRY(cudaMemcpyAsync(dst_h, src, engine->plan->voxels() * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    LMVN_TRY(copy_to_host(device, dst_h, src, engine->plan->voxels() * sizeof(float), stream));
     return 0;
   }
   float* stage = reinterpret_cast<float*>(work);
   LMVN_LAUNCH(k_gather_box, dim3(unsigned(logical[1]), unsigned(logical[0])), dim3(128), 0, stream, src, stage, dims[1], dims[2],
               logical[1], logical[2], offset[0], offset[1], offset[2]);
   LMVN_CUDA_TRY(cudaGetLastError());
-  LMVN_CUDA_TRY(cudaMemcpyAsync(dst_h, stage, size_t(logical[0]) * logical[1] * logical[2] * sizeof(float),
-                                cudaMemcpyDeviceToHost, stream));
+  LMVN_TRY(copy_to_host(device, dst_h, stage, size_t(logical[0]) * logical[1] * logical[2] * sizeof(float), stream));
   return 0;
 }
 

@@ -16,7 +16,11 @@ def main():
     nv, iters = 6, 50
     lib = load()
     rng = np.random.default_rng(0)
-    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    # PAGEABLE=1: plain numpy (malloc) buffers, what a JNA caller hands over; the library then stages them through its
+    # own pinned ring (LMVN_STAGED_COPY=0: the driver's pageable path)
+    pageable = os.environ.get("PAGEABLE", "0") != "0"
+    pin = (lambda a: a) if pageable else (lambda a: torch.from_numpy(a).pin_memory().numpy())
+    print("host buffers: %s, LMVN_STAGED_COPY=%s" % ("pageable" if pageable else "pinned", os.environ.get("LMVN_STAGED_COPY", "1")))
     img = pin((rng.random(dims, dtype=np.float32) + 1.0))
     w = pin(np.full(dims, 1.0 / nv, np.float32))
     psi = pin(img.copy())
