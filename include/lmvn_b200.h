@@ -53,7 +53,9 @@ LMVN_EXPORT const char* lmvn_version(void);
 LMVN_EXPORT int lmvn_set_default_strategy(int strategy);
 
 /* A destroyed plan (and every one-shot inplace_gpu_* call) parks its device arena for the next plan on
- * that device instead of returning it to the driver (env LMVN_CACHE_ARENA=0 disables).  This frees it. */
+ * that device instead of returning it to the driver (env LMVN_CACHE_ARENA=0 disables).  Pageable host stacks of
+ * 4 MB and more are staged through a per-device ring of pinned chunks (3 x 16 MiB, env LMVN_STAGED_COPY=0 leaves the
+ * staging to the driver).  This frees both. */
 LMVN_EXPORT void lmvn_release_cached_memory(void);
 
 LMVN_EXPORT int lmvn_plan_create(lmvn_plan** out, const int* dims_zyx, int num_views, int device);
