@@ -394,7 +394,7 @@ struct DistDeconv {
   int upload_slab(float* dst, const float* src_h) {
     if (!src_h) { set_last_error("null slab buffer"); return -1; }
     LMVN_CUDA_TRY(cudaSetDevice(device));
-    LMVN_CUDA_TRY(cudaMemcpyAsync(dst, src_h, slab_real() * sizeof(float), cudaMemcpyHostToDevice, stream));
+    LMVN_TRY(copy_to_device(device, dst, src_h, slab_real() * sizeof(float), stream));
     return 0;
   }
 
@@ -619,7 +619,7 @@ extern "C" int lmvn_dist_get_psi_slab(lmvn_dist* h, float* psi_slab) {
   DistDeconv& d = h->d;
   if (!psi_slab) { set_last_error("psi is null"); return -1; }
   LMVN_CUDA_TRY(cudaSetDevice(d.device));
-  LMVN_CUDA_TRY(cudaMemcpyAsync(psi_slab, d.psi, d.slab_real() * sizeof(float), cudaMemcpyDeviceToHost, d.stream));
+  LMVN_TRY(copy_to_host(d.device, psi_slab, d.psi, d.slab_real() * sizeof(float), d.stream));
   LMVN_CUDA_TRY(cudaStreamSynchronize(d.stream));
   return 0;
 }

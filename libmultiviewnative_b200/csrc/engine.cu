@@ -604,35 +604,39 @@ void release_stagers() {
     }
 }
 
+#else   // host emulation: plain copies
+void release_stagers() {}
+#endif
+}  // namespace
+
+// host <-> device copies of whole stacks on stream s: pageable host memory goes through the staging ring
 int copy_to_device(int device, void* dst_d, const void* src_h, size_t bytes, cudaStream_t s) {
+#ifndef LMVN_EMU
   if (HostStager* st = stager_for(device, src_h, bytes)) {
     if (st->upload(dst_d, src_h, bytes, s) == 0) return 0;
     if (!st->failed) return -1;  // a copy failed: the error is set
   }
+#else
+  (void)device;
+#endif
   LMVN_CUDA_TRY(cudaMemcpyAsync(dst_d, src_h, bytes, cudaMemcpyHostToDevice, s));
   return 0;
 }
 
+// returns when dst_h is complete if the copy was staged; otherwise it is stream ordered like cudaMemcpyAsync
 int copy_to_host(int device, void* dst_h, const void* src_d, size_t bytes, cudaStream_t s) {
+#ifndef LMVN_EMU
   if (HostStager* st = stager_for(device, dst_h, bytes)) {
     if (st->download(dst_h, src_d, bytes, s) == 0) return 0;
     if (!st->failed) return -1;
   }
-  LMVN_CUDA_TRY(cudaMemcpyAsync(dst_h, src_d, bytes, cudaMemcpyDeviceToHost, s));
-  return 0;
-}
-#else   // host emulation: plain copies
-void release_stagers() {}
-int copy_to_device(int, void* dst_d, const void* src_h, size_t bytes, cudaStream_t s) {
-  LMVN_CUDA_TRY(cudaMemcpyAsync(dst_d, src_h, bytes, cudaMemcpyHostToDevice, s));
-  return 0;
-}
-int copy_to_host(int, void* dst_h, const void* src_d, size_t bytes, cudaStream_t s) {
-  LMVN_CUDA_TRY(cudaMemcpyAsync(dst_h, src_d, bytes, cudaMemcpyDeviceToHost, s));
-  return 0;
-}
+#else
+  (void)device;
 #endif
-}  // namespace
+  LMVN_CUDA_TRY(cudaMemcpyAsync(dst_h, src_d, bytes, cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
 
 int Deconv::upload_stack(float* dst, const float* src_h) {
   const size_t n = engine->plan->voxels();

@@ -198,4 +198,10 @@ int quotient_impl(const float* in, float* out, size_t n, int dev);
 int final_values_impl(float* image, const float* integral, const float* weight, size_t n, float min_value,
                       double lambda, int dev);
 
+// Whole-stack copies between caller memory and the device on stream s.  Pageable host memory (what JNA hands over)
+// is staged through a per-device ring of pinned chunks filled by several host threads (engine.cu, HostStager);
+// pinned / registered memory and small copies go straight to cudaMemcpyAsync.
+int copy_to_device(int device, void* dst_d, const void* src_h, size_t bytes, cudaStream_t s);
+int copy_to_host(int device, void* dst_h, const void* src_d, size_t bytes, cudaStream_t s);
+
 }  // namespace lmvn
