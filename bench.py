@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--workload", default="deconv", choices=["deconv", "conv_sweep", "blocks", "volume"],
                     help="deconv = config 3 (the headline, default); conv_sweep = config 2; blocks = config 4; volume = config 5")
     ap.add_argument("--blocks", type=int, default=64)
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the config-4 / config-5 sub-records of the default run (blocks batch, 1024^3 volume)")
     return ap.parse_args()
 
 
@@ -73,35 +75,10 @@ def peaks():
 
 
 def fast_views(dims, num_views, ksize, seed, workers):
-    """Config-3 style inputs with float32 FFTs for the blur so that the
-    full-size set is generated in seconds."""
-    import scipy.fft as sfft
+    """Config-3 style inputs, see libmultiviewnative_b200.synthetic.make_views_fast."""
+    from libmultiviewnative_b200.synthetic import make_views_fast
 
-    from libmultiviewnative_b200.synthetic import _ORIENT, gaussian_psf
-
-    rng = np.random.default_rng(seed)
-    n_sources = max(50, int(np.prod(dims) // 3355))  # 20 000 at 512x512x256
-    truth = np.full(dims, 10.0, dtype=np.float32)
-    pos = [rng.integers(0, d, size=n_sources) for d in dims]
-    np.add.at(truth, tuple(pos), rng.uniform(500.0, 5000.0, size=n_sources).astype(np.float32))
-    tf = sfft.rfftn(truth, workers=workers)
-    out = dict(views=[], kernels1=[], kernels2=[], weights=[])
-    for v in range(num_views):
-        psf = gaussian_psf(ksize, _ORIENT[v % len(_ORIENT)])
-        pad = np.zeros(dims, dtype=np.float32)
-        idx = []
-        for ax in range(3):
-            i = np.arange(ksize) - ksize // 2
-            idx.append(np.where(i < 0, i + dims[ax], i))
-        pad[np.ix_(*idx)] = psf
-        blurred = sfft.irfftn(tf * sfft.rfftn(pad, workers=workers), s=dims, workers=workers)
-        noise = np.random.default_rng(seed + 1 + v).standard_normal(dims, dtype=np.float32) * np.float32(0.5)
-        out["views"].append(np.maximum(blurred + noise, np.float32(0.1)).astype(np.float32))
-        out["kernels1"].append(psf)
-        out["kernels2"].append(np.ascontiguousarray(psf[::-1, ::-1, ::-1]))
-        out["weights"].append(np.full(dims, 1.0 / num_views, dtype=np.float32))
-    out["psi0"] = np.full(dims, out["views"][0].mean(dtype=np.float64), dtype=np.float32)
-    return out
+    return make_views_fast(dims, num_views, ksize, seed, workers)
 
 
 class ClockSampler:
@@ -154,43 +131,24 @@ class ClockSampler:
 
 
 def cpu_reference_sample(data, dims, views_per_step, steps, warmup, threads):
-    """Times the CPU restatement of inplace_cpu_deconvolve (oracle, torch/MKL FFT twin) on a
-    bounded sample: `views_per_step` (view, iteration) units of the same workload per step."""
-    import torch
+    """Times the CPU restatement of inplace_cpu_deconvolve -- the oracle's checked torch/MKL twin
+    (oracle.mvn_oracle.inplace_cpu_deconvolve_torch, the function the full-size parity test compares the GPU
+    with) -- on a bounded sample: `views_per_step` consecutive (view, iteration) units of the same workload
+    per step, psi carried from step to step.  The PSF spectra are built before the clock starts (in the full
+    workload they are 12 of 1212 transforms); the result is normalised per unit, so it reads in the same
+    G voxel*view*iteration/s as the whole 300-unit job."""
+    from oracle import mvn_oracle as orc  # checker code, allowed here (cpu_baseline / reference leg)
 
-    from oracle.mvn_oracle import wrap_kernel  # checker code, allowed here (cpu_baseline leg)
-
-    torch.set_num_threads(threads)
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
-    nvox = int(np.prod(dims))
-    scale = float(np.float32(1.0 / nvox))
     nv = len(data["views"])
-    k1 = [torch.fft.rfftn(t(wrap_kernel(data["kernels1"][v], dims))) for v in range(min(nv, views_per_step))]
-    k2 = [torch.fft.rfftn(t(wrap_kernel(data["kernels2"][v], dims))) for v in range(min(nv, views_per_step))]
-    views = [t(data["views"][v]) for v in range(min(nv, views_per_step))]
-    weights = [t(data["weights"][v]) for v in range(min(nv, views_per_step))]
-    psi = t(data["psi0"]).clone()
-    lam_inv = float(np.float32(1.0 / LAMBDA))
-    mv = float(np.float32(MIN_VALUE))
-
-    def conv(a, k):
-        return torch.fft.irfftn(torch.fft.rfftn(a) * k, s=dims, norm="forward") * scale
-
-    def unit(psi, v):
-        integ = conv(psi, k1[v])
-        integ = views[v] * (1.0 / integ.double()).float()
-        integ = conv(integ, k2[v])
-        val = psi * integ
-        pos = val > 0
-        reg = (lam_inv * (torch.sqrt(1.0 + 2.0 * LAMBDA * val.double().clamp_min(0)) - 1.0)).float()
-        val = torch.where(pos, reg, torch.full_like(val, mv))
-        val = torch.where(torch.isfinite(val), val.clamp_min(mv), torch.full_like(val, mv))
-        return weights[v] * (val - psi) + psi
+    nvox = int(np.prod(dims))
+    khats = (orc.torch_forwarded_kernels(data["kernels1"], dims, threads),
+             orc.torch_forwarded_kernels(data["kernels2"], dims, threads))
+    its = -(-views_per_step // nv)
+    psi = data["psi0"]
 
     def step(psi):
-        for u in range(views_per_step):
-            psi = unit(psi, u % len(views))
-        return psi
+        return orc.inplace_cpu_deconvolve_torch(psi, data["views"], None, None, data["weights"], its, LAMBDA, MIN_VALUE,
+                                                nthreads=threads, max_units=views_per_step, khats=khats)
 
     for _ in range(warmup):
         psi = step(psi)
@@ -199,6 +157,16 @@ def cpu_reference_sample(data, dims, views_per_step, steps, warmup, threads):
         psi = step(psi)
     dt = time.perf_counter() - t0
     return dt, nvox * views_per_step * steps
+
+
+def config_of(args, dims, workload):
+    """The workload description, identical in both arms (native and --impl reference)."""
+    return {"workload": workload, "dims_zyx": list(dims), "views": args.views, "kernel": args.kernel,
+            "iterations_per_step": args.iterations, "lambda": LAMBDA, "min_value": MIN_VALUE,
+            "l2": "inputs larger than L2: the working set of one step is > 7 GiB per GPU against 126 MB of L2, no flush needed",
+            "parallelism": "independent volumes, one per GPU, no collective",
+            "reference_arm": "times a bounded sample of consecutive (view, iteration) units of THIS workload on the host "
+                             "cores and reports it in the same unit (units / s); the native arm times all of them"}
 
 
 def main():
@@ -224,12 +192,14 @@ def main():
         vps = int(max(1, min(args.views, budget // max(dt1, 1e-3))))
         dt, units = cpu_reference_sample(data, dims, vps, args.steps, args.warmup, threads)
         value = units / dt / 1e9
-        sample = "%d (view,iteration) units of the %s workload per step, torch/MKL restatement of inplace_cpu_deconvolve" % (vps, workload)
+        sample = ("%d consecutive (view,iteration) units of the workload per step (of its %d per step), through "
+                  "oracle.mvn_oracle.inplace_cpu_deconvolve_torch (torch/MKL restatement of inplace_cpu_deconvolve, all "
+                  "host cores; the FFTW reference is not buildable here)" % (vps, args.views * args.iterations))
         line = {
             "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "sample": sample},
+            "config": config_of(args, dims, workload),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
@@ -352,26 +322,38 @@ def main():
     plan.close()
 
     # ---- e2e through the reference-facing C-ABI call, host buffers ----
+    # headline: PAGEABLE numpy buffers, which is what a JNA caller hands over (the library stages them through its
+    # pinned ring); the same call with pinned buffers is reported beside it
     e2e = None
     if not args.no_e2e:
-        def call():
-            np.copyto(psi_host, data["psi0"])  # fresh psi for every call; host-side reset, not part of the call
-            t0 = time.perf_counter()
-            lib.inplace_gpu_deconvolve(psi_host, data["views"], data["kernels1"], data["kernels2"], data["weights"],
-                                       args.iterations, LAMBDA, MIN_VALUE, device)
-            return time.perf_counter() - t0  # the call returns after psi has been copied back (synchronous)
-        call()  # warm-up (plan store, allocator)
-        barrier()
-        e2e_s = 0.0
-        for _ in range(args.steps):
-            e2e_s += call()
-        barrier()
-        e2e_s = max_over_ranks(e2e_s)
         ksz = sum(k.size for k in data["kernels1"]) + sum(k.size for k in data["kernels2"])
-        e2e = {"value": world * units_per_rank / e2e_s / 1e9, "unit": UNIT,
+
+        def measure(views, weights, psi_buf):
+            def call():
+                np.copyto(psi_buf, data["psi0"])  # fresh psi for every call; host-side reset, not part of the call
+                t0 = time.perf_counter()
+                lib.inplace_gpu_deconvolve(psi_buf, views, data["kernels1"], data["kernels2"], weights,
+                                           args.iterations, LAMBDA, MIN_VALUE, device)
+                return time.perf_counter() - t0  # the call returns after psi has been copied back (synchronous)
+            call()  # warm-up (plan store, allocator)
+            barrier()
+            sec = 0.0
+            for _ in range(args.steps):
+                sec += call()
+            barrier()
+            return max_over_ranks(sec)
+
+        pinned_s = measure(data["views"], data["weights"], psi_host)
+        pageable_views = [np.array(a, copy=True) for a in data["views"]]      # plain malloc'ed numpy memory
+        pageable_weights = [np.array(a, copy=True) for a in data["weights"]]
+        pageable_s = measure(pageable_views, pageable_weights, np.array(data["psi0"], copy=True))
+        del pageable_views, pageable_weights
+        e2e = {"value": world * units_per_rank / pageable_s / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int((2 * args.views + 1) * nvox * 4 + ksz * 4), "d2h_bytes_per_step": int(nvox * 4),
-               "ms_per_step": e2e_s / args.steps * 1e3,
-               "api": "inplace_gpu_deconvolve(psi, workspace, device) with pinned host buffers"}
+               "ms_per_step": pageable_s / args.steps * 1e3,
+               "api": "inplace_gpu_deconvolve(psi, workspace, device) with PAGEABLE host buffers (numpy arrays, like JNA's)",
+               "pinned": {"value": world * units_per_rank / pinned_s / 1e9, "ms_per_step": pinned_s / args.steps * 1e3,
+                          "api": "the same call with page-locked host buffers"}}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -380,21 +362,41 @@ def main():
         vps = int(max(1, min(args.views, 20.0 // max(dt1, 1e-3))))
         dt, units = cpu_reference_sample(data, dims, vps, 1, 0, threads)
         cpu_baseline = {"value": units / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": "%d (view,iteration) units of the same workload, torch/MKL restatement of "
-                                  "inplace_cpu_deconvolve (FFTW reference not buildable here)" % vps}
+                        "sample": "%d consecutive (view,iteration) units of the same workload through "
+                                  "oracle.mvn_oracle.inplace_cpu_deconvolve_torch (torch/MKL restatement of "
+                                  "inplace_cpu_deconvolve; FFTW reference not buildable here)" % vps}
+
+    # ---- configs 4 and 5 as sub-records (every N; N = 1 gives the single-GPU baselines) ----
+    config4 = config5 = None
+    if not args.no_extra and not args.dims:
+        from tools import workloads
+
+        del data["views"][:], data["weights"][:]
+        keep.clear()
+        lib.release_cached_memory()
+        try:
+            config4 = workloads.blocks_record(lib, torch, dist, rank, world, device, barrier, max_over_ranks,
+                                              n_blocks=args.blocks)
+        except Exception as exc:  # a sub-record must not take the headline down
+            config4 = {"error": repr(exc)} if rank == 0 else None
+        lib.release_cached_memory()
+        try:
+            config5 = workloads.volume_record(lib, torch, dist, rank, world, device, barrier, max_over_ranks, peaks()[0])
+        except Exception as exc:
+            config5 = {"error": repr(exc)} if rank == 0 else None
+        lib.release_cached_memory()
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "dims_zyx": list(dims), "views": args.views, "kernel": args.kernel,
-                       "iterations_per_step": args.iterations, "lambda": LAMBDA, "min_value": MIN_VALUE,
-                       "strategy": {1: "generic (5 launches/conv)", 2: "fast power-of-two path (%d launches/conv)" % (info.launches_per_view_iteration // 2)}.get(info.strategy, "?"),
-                       "l2": "working set %.1f GiB per GPU >> 126 MB L2, no flush needed" % (info.arena_bytes / 2**30),
-                       "parallelism": "independent volumes, one per GPU, no collective"},
+            "config": config_of(args, dims, workload),
+            "engine": {"strategy": {1: "generic (5 launches/conv)", 2: "fast power-of-two path (%d launches/conv)" % (info.launches_per_view_iteration // 2)}.get(info.strategy, "?"),
+                       "arena_GiB": info.arena_bytes / 2**30},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(info.launches_per_view_iteration * args.views * args.iterations * args.steps),
             "wall_ms_timed_region": wall_ms, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "config4": config4, "config5": config5,
         }
         print(json.dumps(line))
     if dist is not None:

@@ -85,7 +85,11 @@ LMVN_EXPORT void lmvn_plan_destroy(lmvn_plan* plan);
 LMVN_EXPORT int lmvn_plan_get_info(const lmvn_plan* plan, lmvn_plan_info* info);
 
 /* Host pointers.  Uploads image and weights of one view and precomputes both PSF spectra
- * (kernel wrap-around + forward transform + 1/N, ref: src/multiviewnative.cpp:146-174). */
+ * (kernel wrap-around + forward transform + 1/N, ref: src/multiviewnative.cpp:146-174).
+ * BUFFER LIFETIME: lmvn_plan_set_view / lmvn_plan_set_psi (and lmvn_dist_set_*_slab) return once the copy is QUEUED on
+ * the plan's stream.  Pageable buffers have been read completely by then (they go through the library's pinned staging
+ * ring); PINNED or cudaHostRegister'ed buffers are read by the DMA engine asynchronously and must stay unmodified
+ * until lmvn_plan_synchronize (or any call that returns results: lmvn_plan_iterate with device_ms, lmvn_plan_get_psi). */
 LMVN_EXPORT int lmvn_plan_set_view(lmvn_plan* plan, int view, const float* image,
                                    const float* weights, const float* kernel1,
                                    const int* kernel1_dims, const float* kernel2,
@@ -113,7 +117,7 @@ LMVN_EXPORT int lmvn_plan_synchronize(lmvn_plan* plan);
  * ONE volume over several GPUs (BASELINE config 5; the reference has no such path): slabs of
  * nz/G planes in real space, pencils of ny/G rows for the z pass, both all-to-all exchanges of a
  * convolution fused into the transform kernels as stores into peer memory over NVLink.
- * Power-of-two fast-path shapes only (nx in {64,128,256}; ny, nz in {16..512}); G a power of two <= 8.
+ * Power-of-two fast-path shapes only (nx in {64,128,256,512,1024}; ny, nz in {16..1024}); G a power of two <= 8.
  *
  * One handle per rank.  Ranks are separate processes (one per GPU: exchange the 64-byte handles of
  * lmvn_dist_export_handle with any transport and pass them to lmvn_dist_connect_ipc, then use
@@ -157,6 +161,10 @@ LMVN_EXPORT int lmvn_dist_conv_phase(lmvn_dist* plan, int view, int which_conv, 
                                      float min_value);
 /* device-side cross-GPU barrier on the plan's stream (no-op for in-process groups) */
 LMVN_EXPORT int lmvn_dist_barrier(lmvn_dist* plan);
+/* A device-side barrier waits at most LMVN_BARRIER_TIMEOUT_S seconds (default 600) for its peers.  After a timeout
+ * lmvn_dist_iterate fails, the result of that call is invalid and the plan refuses further work until EVERY rank has
+ * called lmvn_dist_reset_barrier (collective: line the ranks up on the host before and after it). */
+LMVN_EXPORT int lmvn_dist_reset_barrier(lmvn_dist* plan);
 /* the whole loop, barriers on the device, no host round trip (one process per rank) */
 LMVN_EXPORT int lmvn_dist_iterate(lmvn_dist* plan, int iterations, double lambda, float min_value,
                                   float* device_ms);

@@ -14,6 +14,23 @@
  *   - convolutions are CIRCULAR at the image extents with the kernel centre
  *     (index k/2 per axis) at the origin (ref: inc/padd_utils.h:11-40, 57-100).
  *
+ * !! BORDER SEMANTICS OF inplace_gpu_deconvolve -- DEVIATION FROM THE REFERENCE'S GPU BUILD !!
+ *   The reference's two implementations of the loop do not agree at the borders: inplace_cpu_deconvolve
+ *   convolves circularly at the image extents (PaddingT = no_padd, ref: inc/cpu_convolve.h:24), while the
+ *   reference's inplace_gpu_deconvolve zero-pads every stack to image + kernel - 1 whenever the data fits 90 %
+ *   of device memory (ref: src/multiviewnative.cu:119-129 -> all_on_device<wrap_around_padding>,
+ *   inc/padd_utils.h:102-249) -- on a B200 practically always.  This build's inplace_gpu_deconvolve follows
+ *   the CPU implementation BY DEFAULT (it is the parity target the results are checked against, DESIGN.md
+ *   section 1): voxels closer to a border than the PSF half-width see the opposite border, not zeros.
+ *   A caller that depended on the old GPU geometry selects it WITHOUT touching this header:
+ *       environment  LMVN_PAD=zero          (read at every call), or
+ *       lmvn_set_padding(LMVN_PAD_ZERO)     (include/lmvn_b200.h; process wide), or
+ *       lmvn_plan_create_zero_padded(...)   (persistent handle).
+ *   Both geometries are tested against the correspondingly padded oracle
+ *   (tests/parity_cases.py: case_deconvolve_vs_oracle, case_zero_padd_*).  Fiji pre-pads its blocks by a
+ *   kernel width (ref: tests/tiff_fixtures.hpp:225-258), which is why either choice gives the same interior.
+ *   inplace_gpu_convolution is circular (no_padd) in the reference too (ref: src/multiviewnative.cu:58-75).
+ *
  * Error behaviour differs from the reference on purpose: no
  * entry point calls exit() or throws across the ABI.  On failure a message goes
  * to stderr, the output buffers are left untouched, and lmvn_last_error()

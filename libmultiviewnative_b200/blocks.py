@@ -7,8 +7,10 @@ runs on GPU ``b mod G`` -- with NO collective on the data path.  Two drivers:
 
 * ``run_sharded``: one process per GPU (torchrun / torch.distributed), each rank
   deconvolves its shard; results are optionally gathered on rank 0 for checking.
-* ``run_threads``: one process, one host thread per GPU (the C library is
+* ``run_threads``: one process, host threads per GPU (the C library is
   re-entrant per device and ctypes releases the GIL during the call).
+* ``run_pipelined``: the block pipeline both are built on -- two calls in flight per
+  device, so that block b+1 uploads while block b iterates.
 """
 from __future__ import annotations
 
@@ -33,17 +35,39 @@ def deconvolve_block(lib, block: dict, num_iterations: int, lam: float, min_valu
     return psi
 
 
-def run_shard(lib, make_block: Callable[[int], dict], n_blocks: int, rank: int, world: int, num_iterations: int,
-              lam: float, min_value: float, device: int, keep: bool = True) -> Dict[int, Optional[np.ndarray]]:
+def run_pipelined(lib, make_block: Callable[[int], dict], indices: Sequence[int], num_iterations: int, lam: float,
+                  min_value: float, device: int, depth: int = 2, keep: bool = True) -> Dict[int, Optional[np.ndarray]]:
+    """Block pipeline on ONE device: ``depth`` calls of ``inplace_gpu_deconvolve`` in flight at a time, each from its
+    own host thread (the library is re-entrant per device; every call has its own stream and arena, and the
+    library parks up to two arenas per device between calls).  With depth = 2 the uploads, PSF spectra and the
+    download of block b+1 overlap the iteration loop of block b -- the copy engines and the SMs work at the same
+    time -- which is what the reference's interleaved strategy did with two streams inside one call
+    (ref: src/gpu_deconvolve_methods.cuh:153-158).  Results are identical to the sequential order: blocks are
+    independent.  ``make_block(b)`` is called on the worker thread, so block generation / disk reads overlap too."""
+    from concurrent.futures import ThreadPoolExecutor
+
     out: Dict[int, Optional[np.ndarray]] = {}
-    for b in shard(n_blocks, rank, world):
+    if not getattr(lib, "reentrant", True):
+        depth = 1
+
+    def work(b: int):
         res = deconvolve_block(lib, make_block(b), num_iterations, lam, min_value, device)
-        out[b] = res if keep else None
+        return b, (res if keep else None)
+
+    with ThreadPoolExecutor(max_workers=max(1, int(depth))) as pool:
+        for b, res in pool.map(work, list(indices)):
+            out[b] = res
     return out
 
 
+def run_shard(lib, make_block: Callable[[int], dict], n_blocks: int, rank: int, world: int, num_iterations: int,
+              lam: float, min_value: float, device: int, keep: bool = True, depth: int = 2) -> Dict[int, Optional[np.ndarray]]:
+    return run_pipelined(lib, make_block, shard(n_blocks, rank, world), num_iterations, lam, min_value, device,
+                         depth=depth, keep=keep)
+
+
 def run_sharded(lib, make_block: Callable[[int], dict], n_blocks: int, num_iterations: int, lam: float,
-                min_value: float, device: Optional[int] = None, gather: bool = False):
+                min_value: float, device: Optional[int] = None, gather: bool = False, depth: int = 2):
     """Every rank of the initialised torch.distributed group processes its shard.
     No data-path collective; ``gather=True`` collects the results on rank 0 (testing)."""
     import torch.distributed as dist
@@ -53,7 +77,7 @@ def run_sharded(lib, make_block: Callable[[int], dict], n_blocks: int, num_itera
     else:
         rank, world = 0, 1
     dev = rank if device is None else device
-    mine = run_shard(lib, make_block, n_blocks, rank, world, num_iterations, lam, min_value, dev, keep=gather)
+    mine = run_shard(lib, make_block, n_blocks, rank, world, num_iterations, lam, min_value, dev, keep=gather, depth=depth)
     if not gather or world == 1:
         return mine
     gathered: List[Optional[dict]] = [None] * world
@@ -67,15 +91,17 @@ def run_sharded(lib, make_block: Callable[[int], dict], n_blocks: int, num_itera
 
 
 def run_threads(lib, blocks: Sequence[dict], devices: Sequence[int], num_iterations: int, lam: float,
-                min_value: float) -> List[np.ndarray]:
-    """Single process: block b on devices[b mod G], one host thread per device."""
+                min_value: float, depth: int = 2) -> List[np.ndarray]:
+    """Single process: block b on devices[b mod G], ``depth`` host threads (calls in flight) per device."""
     results: List[Optional[np.ndarray]] = [None] * len(blocks)
     errors: List[BaseException] = []
 
     def worker(slot: int):
         try:
-            for b in shard(len(blocks), slot, len(devices)):
-                results[b] = deconvolve_block(lib, blocks[b], num_iterations, lam, min_value, devices[slot])
+            mine = run_pipelined(lib, lambda b: blocks[b], shard(len(blocks), slot, len(devices)), num_iterations, lam,
+                                 min_value, devices[slot], depth=depth)
+            for b, res in mine.items():
+                results[b] = res
         except BaseException as exc:  # surfaced to the caller below
             errors.append(exc)
 

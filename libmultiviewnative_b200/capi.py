@@ -75,7 +75,8 @@ EXTENSION_SYMBOLS = [
     "lmvn_plan_iterate", "lmvn_plan_convolve", "lmvn_plan_profile", "lmvn_plan_synchronize", "lmvn_debug_rfftn", "lmvn_debug_irfftn",
     "lmvn_dist_create", "lmvn_dist_destroy", "lmvn_dist_get_info", "lmvn_dist_export_handle", "lmvn_dist_connect_ipc",
     "lmvn_dist_connect_local", "lmvn_dist_set_view_slab", "lmvn_dist_set_psi_slab", "lmvn_dist_get_psi_slab",
-    "lmvn_dist_psf_phase", "lmvn_dist_conv_phase", "lmvn_dist_barrier", "lmvn_dist_iterate", "lmvn_dist_synchronize",
+    "lmvn_dist_psf_phase", "lmvn_dist_conv_phase", "lmvn_dist_barrier", "lmvn_dist_reset_barrier", "lmvn_dist_iterate",
+    "lmvn_dist_synchronize",
     "lmvn_dist_set_stream", "lmvn_dist_set_staged", "lmvn_dist_buffer",
 ]
 
@@ -115,6 +116,9 @@ class Library:
         self.path = path
         self.lib = C.CDLL(path)
         L = self.lib
+        L.lmvn_version.restype = C.c_char_p
+        # the host-emulator test build (tests/emu) runs one kernel at a time on fibers: not re-entrant
+        self.reentrant = b"emu" not in (L.lmvn_version() or b"").lower()
         L.lmvn_last_error.restype = C.c_char_p
         L.lmvn_version.restype = C.c_char_p
         L.lmvn_clear_error.restype = None
@@ -165,6 +169,7 @@ class Library:
         L.lmvn_dist_psf_phase.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p, c_int_p]
         L.lmvn_dist_conv_phase.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_float]
         L.lmvn_dist_barrier.argtypes = [C.c_void_p]
+        L.lmvn_dist_reset_barrier.argtypes = [C.c_void_p]
         L.lmvn_dist_iterate.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_float, c_float_p]
         L.lmvn_dist_synchronize.argtypes = [C.c_void_p]
         L.lmvn_dist_set_stream.argtypes = [C.c_void_p, C.c_void_p]

@@ -1,6 +1,7 @@
 // api.cu -- the C ABI: include/multiviewnative.h (reference drop-in) and
 // include/lmvn_b200.h (persistent handle + diagnostics).
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -73,7 +74,7 @@ int pad_mode_from_env() {
   const char* e = getenv("LMVN_PAD");
   return (e && (e[0] == 'z' || e[0] == 'Z')) ? LMVN_PAD_ZERO : LMVN_PAD_NONE;
 }
-int g_pad_mode = -1;
+std::atomic<int> g_pad_mode{-1};  // process wide (lmvn_set_padding); every call samples it once
 }  // namespace
 
 extern "C" int lmvn_set_padding(int mode) {
@@ -81,10 +82,13 @@ extern "C" int lmvn_set_padding(int mode) {
     set_last_error("unknown padding mode %d", mode);
     return -1;
   }
-  g_pad_mode = mode;
+  g_pad_mode.store(mode);
   return 0;
 }
-static int current_pad_mode() { return g_pad_mode >= 0 ? g_pad_mode : pad_mode_from_env(); }
+static int current_pad_mode() {
+  const int m = g_pad_mode.load();
+  return m >= 0 ? m : pad_mode_from_env();
+}
 
 namespace {
 thread_local int g_last_geometry = LMVN_GEOMETRY_NONE;

@@ -150,22 +150,32 @@ int threads_of(int nthreads) {
 void convolve(const Fft3& f, float* image, const std::vector<cf>& khat, std::vector<cf>& spec, int nt) {
   f.forward(image, spec, nt);
   const size_t n = f.spec_elems();
-  for (size_t i = 0; i < n; ++i) spec[i] *= khat[i];  // serial, like ref: inc/cpu_convolve.h:257-266
+  // ref: inc/cpu_convolve.h:257-266 runs this loop and the scale loop below serially; element-wise, so the threaded
+  // form gives the same bits
+#pragma omp parallel for num_threads(nt) schedule(static)
+  for (long long i = 0; i < (long long)n; ++i) spec[i] *= khat[i];
   f.backward(spec, image, nt);
   const size_t vox = size_t(f.nz) * f.ny * f.nx;
   const float scale = float(1.0 / double(vox));
-  for (size_t i = 0; i < vox; ++i) image[i] *= scale;
+#pragma omp parallel for num_threads(nt) schedule(static)
+  for (long long i = 0; i < (long long)vox; ++i) image[i] *= scale;
 }
 
 }  // namespace
 
+// the error contract of include/multiviewnative.h: message to stderr + lmvn_last_error(), outputs untouched
+namespace lmvn { void set_last_error(const char* fmt, ...); }  // csrc/engine.cu
+static void fail(const char* what) {
+  lmvn::set_last_error("%s", what);
+  std::fprintf(stderr, "[libmultiviewnative] error: %s\n", what);
+}
+
 extern "C" void inplace_cpu_convolution(imageType* im, int* imDim, imageType* kernel, int* kernelDim, int nthreads) {
-  if (!im || !imDim || !kernel || !kernelDim) return;
+  if (!im || !imDim || !kernel || !kernelDim) return fail("inplace_cpu_convolution: null argument");
+  for (int a = 0; a < 3; ++a)
+    if (imDim[a] <= 0 || kernelDim[a] <= 0) return fail("inplace_cpu_convolution: non-positive extent");
   std::vector<float> padded;
-  if (!wrap_kernel(kernel, kernelDim, imDim, padded)) {
-    std::fprintf(stderr, "[libmultiviewnative] error: kernel does not fit the image\n");
-    return;
-  }
+  if (!wrap_kernel(kernel, kernelDim, imDim, padded)) return fail("inplace_cpu_convolution: kernel does not fit the image");
   const int nt = threads_of(nthreads);
   Fft3 f(imDim[0], imDim[1], imDim[2]);
   std::vector<cf> khat, spec;
@@ -174,8 +184,21 @@ extern "C" void inplace_cpu_convolution(imageType* im, int* imDim, imageType* ke
 }
 
 extern "C" void inplace_cpu_deconvolve(imageType* psi, workspace input, int nthreads) {
-  if (!psi || !input.data_ || input.num_views_ == 0) return;
+  // same validation and reporting as the GPU entry point (gpu_deconvolve_impl, csrc/api.cu)
+  if (!psi || !input.data_ || input.num_views_ == 0) return fail("inplace_cpu_deconvolve: null psi / no views");
+  if (!input.data_[0].image_dims_) return fail("inplace_cpu_deconvolve: view 0 has no image_dims_");
   const int* d = input.data_[0].image_dims_;
+  for (int v = 0; v < input.num_views_; ++v) {
+    const view_data& vd = input.data_[v];
+    if (!vd.image_ || !vd.weights_ || !vd.kernel1_ || !vd.kernel2_ || !vd.image_dims_ || !vd.kernel1_dims_ || !vd.kernel2_dims_)
+      return fail("inplace_cpu_deconvolve: a view has a null buffer or dims pointer");
+    for (int a = 0; a < 3; ++a) {
+      if (vd.image_dims_[a] != d[a] || d[a] <= 0)
+        return fail("inplace_cpu_deconvolve: all views must share view 0's (positive) image dims");  // decision q6
+      if (vd.kernel1_dims_[a] <= 0 || vd.kernel2_dims_[a] <= 0 || vd.kernel1_dims_[a] > d[a] || vd.kernel2_dims_[a] > d[a])
+        return fail("inplace_cpu_deconvolve: a kernel does not fit the image");  // decision q11
+    }
+  }
   const int nt = threads_of(nthreads);
   Fft3 f(d[0], d[1], d[2]);
   const size_t vox = size_t(d[0]) * d[1] * d[2];
@@ -183,9 +206,9 @@ extern "C" void inplace_cpu_deconvolve(imageType* psi, workspace input, int nthr
   std::vector<float> padded;
   for (int v = 0; v < input.num_views_; ++v) {
     const view_data& vd = input.data_[v];
-    if (!wrap_kernel(vd.kernel1_, vd.kernel1_dims_, d, padded)) return;
+    if (!wrap_kernel(vd.kernel1_, vd.kernel1_dims_, d, padded)) return fail("inplace_cpu_deconvolve: kernel1 does not fit the image");
     f.forward(padded.data(), k1[v], nt);
-    if (!wrap_kernel(vd.kernel2_, vd.kernel2_dims_, d, padded)) return;
+    if (!wrap_kernel(vd.kernel2_, vd.kernel2_dims_, d, padded)) return fail("inplace_cpu_deconvolve: kernel2 does not fit the image");
     f.forward(padded.data(), k2[v], nt);
   }
   std::vector<float> integral(vox);

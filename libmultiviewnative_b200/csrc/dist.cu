@@ -57,10 +57,15 @@ int ilog2(int v) {
 size_t align_up_(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Cross-GPU barrier: every rank raises its flag in every peer's exchange region, then waits for
-// all of its own flags.  One CTA, one thread per peer.  Bounded spin: a lost peer must not hang
-// the device (the error flag is reported by the next host call).
+// all of its own flags.  One CTA, one thread per peer.  The wait is bounded by wall time (%globaltimer):
+// a lost peer must not hang the device.  On timeout the error flag is raised and STAYS raised; every later
+// barrier of the plan then returns at once, the host sees the flag at the end of the call
+// (check_device_error) and the plan refuses further work until lmvn_dist_reset_barrier has been called by
+// every rank.  timeout_ns comes from LMVN_BARRIER_TIMEOUT_S (default 600 s: ranks may legitimately be
+// seconds apart -- first-call graph instantiation, staging a pageable slab; ProcessSlabPlan.iterate
+// additionally lines the hosts up with a torch.distributed barrier before the launch).
 __global__ void k_peer_barrier(unsigned* const* peer_flags, unsigned* my_flags, int rank, int world, unsigned* epoch_counter,
-                               unsigned* err) {
+                               unsigned* err, unsigned long long timeout_ns) {
 #ifndef LMVN_EMU
   // the epoch lives on the device (every rank launches the same sequence of barriers), so that a captured
   // launch sequence can be replayed as a CUDA graph
@@ -75,18 +80,23 @@ __global__ void k_peer_barrier(unsigned* const* peer_flags, unsigned* my_flags, 
     *dst = epoch;
     __threadfence_system();
     volatile unsigned* src = my_flags + t;
-    unsigned spins = 0;
+    volatile unsigned* verr = err;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while (*src < epoch) {
+      if (*verr) break;  // an earlier barrier of this plan timed out: do not wait again
       __nanosleep(200);
-      if (++spins > (1u << 25)) {
-        *err = 1u;
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (now - t0 > timeout_ns) {
+        *verr = 1u;
         break;
       }
     }
     __threadfence_system();
   }
 #else
-  (void)peer_flags; (void)my_flags; (void)rank; (void)world; (void)epoch_counter; (void)err;
+  (void)peer_flags; (void)my_flags; (void)rank; (void)world; (void)epoch_counter; (void)err; (void)timeout_ns;
 #endif
 }
 
@@ -122,6 +132,8 @@ struct DistDeconv {
   float graph_min = 0.f;
   unsigned** d_peer_flags = nullptr;  // device array of kMaxRanks pointers
   unsigned* d_err = nullptr;
+  bool barrier_failed = false;                         // a device-side barrier timed out; reset_barrier() clears it
+  unsigned long long barrier_timeout_ns = 600ull * 1000000000ull;
   // comparator: exchanges staged through local buffers and moved by the caller (NCCL all-to-all)
   bool staged = false;
   bool own_stream = true;
@@ -241,6 +253,10 @@ struct DistDeconv {
     LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_epoch), sizeof(unsigned)));
     LMVN_CUDA_TRY(cudaMemset(d_epoch, 0, sizeof(unsigned)));
     if (const char* e = getenv("LMVN_GRAPH")) use_graph = (*e != '0');
+    if (const char* e = getenv("LMVN_BARRIER_TIMEOUT_S")) {
+      const double sec = atof(e);
+      if (sec > 0) barrier_timeout_ns = (unsigned long long)(sec * 1e9);
+    }
     unsigned char* p = arena;
     auto take = [&](size_t bytes) {
       unsigned char* r = p;
@@ -375,8 +391,22 @@ struct DistDeconv {
   int barrier() {
     if (!multi_process || world == 1) return 0;  // one process: stream order is the barrier
     LMVN_CUDA_TRY(cudaSetDevice(device));
-    LMVN_LAUNCH(k_peer_barrier, dim3(1), dim3(32), 0, stream, d_peer_flags, flags(rank), rank, world, d_epoch, d_err);
+    LMVN_LAUNCH(k_peer_barrier, dim3(1), dim3(32), 0, stream, d_peer_flags, flags(rank), rank, world, d_epoch, d_err,
+                barrier_timeout_ns);
     LMVN_CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+
+  // Collective recovery after a timed-out barrier: the caller lines every rank up on the host (no kernel of the
+  // plan in flight anywhere), every rank calls this, the caller lines them up again.  Epochs restart from zero.
+  int reset_barrier() {
+    LMVN_CUDA_TRY(cudaSetDevice(device));
+    LMVN_CUDA_TRY(cudaStreamSynchronize(stream));
+    LMVN_CUDA_TRY(cudaMemset(d_err, 0, sizeof(unsigned)));
+    LMVN_CUDA_TRY(cudaMemset(d_epoch, 0, sizeof(unsigned)));
+    LMVN_CUDA_TRY(cudaMemset(xchg + flags_off, 0, 256));
+    LMVN_CUDA_TRY(cudaDeviceSynchronize());
+    barrier_failed = false;
     return 0;
   }
 
@@ -385,7 +415,10 @@ struct DistDeconv {
     LMVN_CUDA_TRY(cudaMemcpyAsync(&e, d_err, sizeof(e), cudaMemcpyDeviceToHost, stream));
     LMVN_CUDA_TRY(cudaStreamSynchronize(stream));
     if (e) {
-      set_last_error("rank %d: cross-GPU barrier timed out (a peer did not arrive)", rank);
+      barrier_failed = true;
+      set_last_error("rank %d: cross-GPU barrier timed out (a peer did not arrive within %.0f s); the result of this "
+                     "call is invalid, call lmvn_dist_reset_barrier on every rank before using the plan again",
+                     rank, barrier_timeout_ns * 1e-9);
       return -1;
     }
     return 0;
@@ -406,6 +439,10 @@ struct DistDeconv {
       if (!view_set[v]) { set_last_error("view %d has not been set", v); return -1; }
     if (!multi_process && world > 1) {
       set_last_error("lmvn_dist_iterate needs one process per rank; in-process groups drive lmvn_dist_conv_phase");
+      return -1;
+    }
+    if (barrier_failed) {
+      set_last_error("rank %d: an earlier cross-GPU barrier timed out; call lmvn_dist_reset_barrier on every rank", rank);
       return -1;
     }
     LMVN_CUDA_TRY(cudaSetDevice(device));
@@ -651,6 +688,11 @@ extern "C" int lmvn_dist_barrier(lmvn_dist* h) {
   LMVN_DIST_GUARD(h);
   LMVN_TRY(h->d.connected());
   return h->d.barrier();
+}
+
+extern "C" int lmvn_dist_reset_barrier(lmvn_dist* h) {
+  LMVN_DIST_GUARD(h);
+  return h->d.reset_barrier();
 }
 
 extern "C" int lmvn_dist_iterate(lmvn_dist* h, int iterations, double lambda, float min_value, float* device_ms) {

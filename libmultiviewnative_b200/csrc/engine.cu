@@ -4,6 +4,7 @@
 #include "fft_generic.cuh"
 
 #include <algorithm>
+#include <atomic>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -49,17 +50,21 @@ void trace(const char* fmt, ...) {
   va_end(ap);
 }
 
-static int g_default_strategy = -1;
+static std::atomic<int> g_default_strategy{-1};  // process wide; lmvn_set_default_strategy may race with calls on other threads
 int default_strategy() {
-  if (g_default_strategy < 0) {
+  int cur = g_default_strategy.load(std::memory_order_relaxed);
+  if (cur < 0) {
     const char* e = getenv("LMVN_STRATEGY");
-    g_default_strategy = 0;
-    if (e && !strcmp(e, "generic")) g_default_strategy = 1;
-    if (e && !strcmp(e, "fused")) g_default_strategy = 2;
+    cur = 0;
+    if (e && !strcmp(e, "generic")) cur = 1;
+    if (e && !strcmp(e, "fused")) cur = 2;
+    int expected = -1;
+    g_default_strategy.compare_exchange_strong(expected, cur);
+    cur = g_default_strategy.load();
   }
-  return g_default_strategy;
+  return cur;
 }
-void set_default_strategy(int s) { g_default_strategy = s; }
+void set_default_strategy(int s) { g_default_strategy.store(s); }
 
 // ------------------------------------------------------------------------------
 // device selection (ref: inc/cuda_helpers.cuh:116-136)
@@ -139,7 +144,6 @@ struct PlanKey {
 };
 static std::mutex g_store_mutex;
 static std::map<PlanKey, std::shared_ptr<FftPlan>> g_store;
-static bool g_attr_done = false;
 
 std::shared_ptr<FftPlan> get_fft_plan(int device, int nz, int ny, int nx) {
   std::lock_guard<std::mutex> lock(g_store_mutex);
@@ -156,12 +160,10 @@ std::shared_ptr<FftPlan> get_fft_plan(int device, int nz, int ny, int nx) {
   const int n[3] = {nz, ny, nx};
   for (int a = 0; a < 3; ++a)
     if (build_axis(*fp, a, n[a]) != 0) return nullptr;
-  if (!g_attr_done) {
-    cudaFuncSetAttribute(gen::k_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxSmem));
-    cudaFuncSetAttribute(gen::k_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxSmem));
-    cudaFuncSetAttribute(gen::k_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxSmem));
-    g_attr_done = true;
-  }
+  // the attribute is per (function, device): set it for every device that gets a plan (new plans are rare)
+  cudaFuncSetAttribute(gen::k_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxSmem));
+  cudaFuncSetAttribute(gen::k_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxSmem));
+  cudaFuncSetAttribute(gen::k_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMaxSmem));
   g_store[key] = fp;
   trace("new fft plan dev=%d dims=%dx%dx%d", device, nz, ny, nx);
   return fp;
@@ -260,15 +262,20 @@ std::unique_ptr<ConvEngine> make_fused_engine(std::shared_ptr<FftPlan>) { return
 // ------------------------------------------------------------------------------
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// One parked arena per device.  Fiji calls inplace_gpu_deconvolve once per block with identical
+// Parked arenas (at most two per device).  Fiji calls inplace_gpu_deconvolve once per block with identical
 // shapes (ref: bench/bench_gpu_deconvolve.cu:48-49); returning several GiB to the driver and asking
 // for them again costs tens to hundreds of milliseconds per call (fresh pages are scrubbed).  A
-// destroyed handle parks its arena here, the next handle on that device takes it when it is large
-// enough.  lmvn_release_cached_memory() / LMVN_CACHE_ARENA=0 give the memory back.
+// destroyed handle parks its arena here, the next handle on that device takes one that is large
+// enough.  Two slots: the block pipeline (libmultiviewnative_b200/blocks.py) keeps two calls in flight per
+// device so that the uploads of block b+1 overlap the loop of block b.  What stays allocated between calls
+// is bounded: LMVN_CACHE_ARENA_MAX_MB per device (default: a quarter of the device's memory; anything
+// larger goes straight back to the driver), lmvn_release_cached_memory() / LMVN_CACHE_ARENA=0 give
+// everything back (a host application that shares the GPU with other libraries should call it when idle).
 namespace {
 struct ParkedArena { unsigned char* p = nullptr; size_t bytes = 0; };
+static const int kParkSlots = 2;
 std::mutex g_arena_mu;
-std::map<int, ParkedArena> g_parked;
+std::map<int, std::vector<ParkedArena>> g_parked;
 bool arena_cache_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -277,27 +284,48 @@ bool arena_cache_enabled() {
   }
   return v == 1;
 }
+size_t arena_cache_cap(int device) {
+  if (const char* e = getenv("LMVN_CACHE_ARENA_MAX_MB")) return size_t(std::max(0.0, atof(e)) * 1048576.0);
+  size_t free_b = 0, total_b = 0;
+  (void)device;  // the caller has made `device` current
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { (void)cudaGetLastError(); return size_t(16) << 30; }
+  return total_b / 4;
+}
 unsigned char* take_parked(int device, size_t bytes, size_t* capacity) {
   std::lock_guard<std::mutex> lk(g_arena_mu);
   auto it = g_parked.find(device);
-  if (it == g_parked.end() || !it->second.p) return nullptr;
-  if (it->second.bytes < bytes || it->second.bytes > bytes + bytes / 2 + (size_t(64) << 20)) {
-    cudaFree(it->second.p);  // too small, or wastefully large for this request
-    g_parked.erase(it);
+  if (it == g_parked.end()) return nullptr;
+  std::vector<ParkedArena>& v = it->second;
+  // best fit among the parked arenas; wastefully large ones (> 1.5 x + 64 MiB) are not used for this request
+  int best = -1;
+  for (int i = 0; i < int(v.size()); ++i)
+    if (v[i].bytes >= bytes && v[i].bytes <= bytes + bytes / 2 + (size_t(64) << 20) && (best < 0 || v[i].bytes < v[best].bytes))
+      best = i;
+  if (best < 0) {
+    // nothing fits: the request will allocate; make room by returning what is parked
+    for (auto& a : v) cudaFree(a.p);
+    v.clear();
     return nullptr;
   }
-  unsigned char* p = it->second.p;
-  *capacity = it->second.bytes;
-  g_parked.erase(it);
+  unsigned char* p = v[best].p;
+  *capacity = v[best].bytes;
+  v.erase(v.begin() + best);
   return p;
 }
 void park(int device, unsigned char* p, size_t bytes) {
   if (!arena_cache_enabled()) { cudaFree(p); return; }
+  const size_t cap = arena_cache_cap(device);
   std::lock_guard<std::mutex> lk(g_arena_mu);
-  ParkedArena& slot = g_parked[device];
-  if (slot.p) cudaFree(slot.p);
-  slot.p = p;
-  slot.bytes = bytes;
+  std::vector<ParkedArena>& v = g_parked[device];
+  size_t held = 0;
+  for (auto& a : v) held += a.bytes;
+  while (!v.empty() && (int(v.size()) >= kParkSlots || held + bytes > cap)) {  // oldest first
+    held -= v.front().bytes;
+    cudaFree(v.front().p);
+    v.erase(v.begin());
+  }
+  if (bytes > cap) { cudaFree(p); return; }
+  v.push_back(ParkedArena{p, bytes});
 }
 }  // namespace
 
@@ -308,11 +336,10 @@ void release_stagers();  // pinned staging rings (below)
 void release_cached_memory() {
   release_stagers();
   std::lock_guard<std::mutex> lk(g_arena_mu);
-  for (auto& kv : g_parked)
-    if (kv.second.p) {
-      cudaSetDevice(kv.first);
-      cudaFree(kv.second.p);
-    }
+  for (auto& kv : g_parked) {
+    cudaSetDevice(kv.first);
+    for (auto& a : kv.second) cudaFree(a.p);
+  }
   g_parked.clear();
 }
 
@@ -805,9 +832,10 @@ int Deconv::iterate(int iterations, double lambda, float min_value, float* devic
       if (!sweep_graph || graph_lambda != lambda || graph_min != min_value || graph_psi != psi) {
         if (sweep_graph) { cudaGraphExecDestroy(sweep_graph); sweep_graph = nullptr; }
         cudaGraph_t g = nullptr;
-        LMVN_CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-        const int rc = sweep(false);
-        const cudaError_t ce = cudaStreamEndCapture(stream, &g);
+        // a failing capture is treated like every other graph failure: plain launches from now on
+        const cudaError_t be = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
+        const int rc = (be == cudaSuccess) ? sweep(false) : -1;
+        const cudaError_t ce = (be == cudaSuccess) ? cudaStreamEndCapture(stream, &g) : be;
         if (rc != 0 || ce != cudaSuccess || !g) {
           if (g) cudaGraphDestroy(g);
           (void)cudaGetLastError();

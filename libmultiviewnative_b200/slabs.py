@@ -217,6 +217,18 @@ class ProcessSlabPlan(SlabPlan):
             self.psf_phase(v, which, 1)
         self._host_barrier()
 
+    def iterate(self, iterations: int, lam: float = 0.0, min_value: float = 1e-4) -> float:
+        """lmvn_dist_iterate with the hosts lined up first: the device-side barriers then only absorb launch
+        skew, not seconds of host skew (first-call graph instantiation, staging of pageable slabs)."""
+        self._host_barrier()
+        return super().iterate(iterations, lam, min_value)
+
+    def reset_barrier(self):
+        """Collective recovery after a timed-out device barrier (lmvn_dist_reset_barrier)."""
+        self._host_barrier()
+        self.L._check(self.L.lib.lmvn_dist_reset_barrier(self.handle), "lmvn_dist_reset_barrier")
+        self._host_barrier()
+
     def iterate_host_barriers(self, iterations: int, lam: float = 0.0, min_value: float = 1e-4):
         """The phase sequence of lmvn_dist_iterate with torch.distributed barriers instead of the device-side
         flag barrier: slower, but independent of peer-visible flags (and what the gloo tests on the CPU drive)."""

@@ -123,7 +123,7 @@ def deconvolve_tiled(deconvolve_block: Callable[[dict], np.ndarray], psi: np.nda
     ``deconvolve_block`` is e.g. ``lambda b: blocks.deconvolve_block(lib, b, iterations, lam, min_value, device)``.
     """
     if halo is None:
-        halo = halo_for(list(kernels1) + list(kernels2), num_kernel_widths)
+        halo = halo_for([np.shape(k) for k in list(kernels1) + list(kernels2)], num_kernel_widths)
     plan = plan_blocks(psi.shape, block_shape, halo)
     out = np.array(psi, dtype=np.float32, copy=True)
     for b in plan:

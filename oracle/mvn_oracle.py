@@ -265,8 +265,20 @@ def direct_convolve(image: np.ndarray, kernel: np.ndarray, offset) -> np.ndarray
 # torch (MKL) twin: same restatement on a second, faster FFT back-end.  Used for
 # cross-checking the oracle and as the multi-threaded timed CPU baseline.
 # --------------------------------------------------------------------------- #
+def torch_forwarded_kernels(kernels, dims, nthreads=-1):
+    """K^ of every kernel on the torch back-end (src/multiviewnative.cpp:146-174), for `khats=` below."""
+    import torch
+
+    torch.set_num_threads(_workers(nthreads))
+    return [torch.fft.rfftn(torch.from_numpy(wrap_kernel(k, tuple(dims)))) for k in kernels]
+
+
 def inplace_cpu_deconvolve_torch(psi, views, kernels1, kernels2, weights, num_iterations,
-                                 lam=0.0, min_value=1e-4, nthreads=-1):
+                                 lam=0.0, min_value=1e-4, nthreads=-1, checkpoints=None, max_units=None, khats=None):
+    """khats: optional (K^1 list, K^2 list) from torch_forwarded_kernels (kernels1/2 are then ignored).
+    checkpoints: optional dict filled with {iteration count: psi copy} for the counts it holds as keys (the
+    full-size parity test reads 1 and 10 iterations from ONE run).  max_units: stop after that many (view,
+    iteration) units (bench.py times a bounded sample of the loop through this very function)."""
     import torch
 
     n = _workers(nthreads)
@@ -276,8 +288,11 @@ def inplace_cpu_deconvolve_torch(psi, views, kernels1, kernels2, weights, num_it
     dims = tuple(psi_t.shape)
     nvox = int(np.prod(dims))
     scale = float(F32(1.0 / nvox))
-    k1 = [torch.fft.rfftn(t(wrap_kernel(k, dims))) for k in kernels1]
-    k2 = [torch.fft.rfftn(t(wrap_kernel(k, dims))) for k in kernels2]
+    if khats is None:
+        k1 = [torch.fft.rfftn(t(wrap_kernel(k, dims))) for k in kernels1]
+        k2 = [torch.fft.rfftn(t(wrap_kernel(k, dims))) for k in kernels2]
+    else:
+        k1, k2 = khats
     views_t = [t(v) for v in views]
     weights_t = [t(wt) for wt in weights]
     mv = float(F32(min_value))
@@ -288,8 +303,12 @@ def inplace_cpu_deconvolve_torch(psi, views, kernels1, kernels2, weights, num_it
         s = s * k
         return torch.fft.irfftn(s, s=dims, norm="forward") * scale
 
-    for _ in range(int(num_iterations)):
+    units = 0
+    for it in range(int(num_iterations)):
         for v in range(len(views_t)):
+            if max_units is not None and units >= max_units:
+                return psi_t.numpy()
+            units += 1
             integ = conv(psi_t, k1[v])
             integ = views_t[v] * (1.0 / integ.double()).float()
             integ = conv(integ, k2[v])
@@ -302,4 +321,6 @@ def inplace_cpu_deconvolve_torch(psi, views, kernels1, kernels2, weights, num_it
                 val = torch.where(pos, val, torch.full_like(val, mv))
             val = torch.where(torch.isfinite(val), val.clamp_min(mv), torch.full_like(val, mv))
             psi_t = weights_t[v] * (val - psi_t) + psi_t
+        if checkpoints is not None and (it + 1) in checkpoints:
+            checkpoints[it + 1] = psi_t.numpy().copy()
     return psi_t.numpy()

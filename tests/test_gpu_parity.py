@@ -210,6 +210,117 @@ def test_full_size_properties(L):
     assert pc.rel_l2(sh, np.roll(ca, (3, -5, 7), axis=(0, 1, 2))) < 2e-6
 
 
+# ---- config 3 itself against the oracle, full size ("re-checked at this size for 1 and 10 iterations") ----
+_CONFIG3 = {}
+
+
+def _config3_inputs():
+    if not _CONFIG3:
+        from libmultiviewnative_b200.synthetic import make_views_fast
+
+        _CONFIG3.update(make_views_fast((512, 512, 256), 6, 41, 20240607))
+    return _CONFIG3
+
+
+@pytest.mark.parametrize("lam", [0.006, 0.0])
+def test_config3_full_size_vs_oracle(L, lam):
+    """BASELINE config 3 as bench.py runs it -- 6 views, 512 x 512 x 256, 41^3 PSFs, the one-shot C-ABI call
+    (512-point y / z plans, the split Nyquist plane at this shape, graph replay of the sweeps) -- against the
+    oracle's torch/MKL twin on all host cores; 1 and 10 iterations are read from ONE oracle run.
+    Tolerances: the north star's (per voxel <= 1e-4 after one iteration, relative L2 <= 1e-3 after ten)."""
+    from oracle import mvn_oracle as orc
+
+    d = _config3_inputs()
+    ck = {1: None, 10: None}
+    orc.inplace_cpu_deconvolve_torch(d["psi0"], d["views"], d["kernels1"], d["kernels2"], d["weights"], 10, lam, 1e-4,
+                                     nthreads=-1, checkpoints=ck)
+    res = {}
+    for iters in (1, 10):
+        psi = d["psi0"].copy()
+        L.inplace_gpu_deconvolve(psi, d["views"], d["kernels1"], d["kernels2"], d["weights"], iters, lam, 1e-4)
+        res[iters] = (pc.max_rel(psi, ck[iters]), pc.rel_l2(psi, ck[iters]))
+    print("config3 full size lam=%g: (max rel, rel L2) %s" % (lam, res))
+    assert res[1][0] <= pc.PER_VOXEL_TOL_1_ITER, res
+    assert res[1][1] <= pc.REL_L2_TOL_10_ITER and res[10][1] <= pc.REL_L2_TOL_10_ITER, res
+
+
+@pytest.mark.parametrize("dims,ks", [((1024, 64, 64), 21), ((64, 1024, 64), 21), ((1024, 1024, 64), 15)])
+def test_deconvolve_1024_point_axes(L, dims, ks):
+    """the 1024-point plans: three-stage merged z pass (Radix<1024>) and the 32 x 32 y passes (Plan<1024, 1>)"""
+    pc.case_deconvolve_vs_oracle(L, dims, 2, ks, 0.006, iters_list=(1, 10), n_sources=100)
+
+
+def test_deconvolve_256x256x1024_wide_rows(L):
+    """nx = 1024 rows kernels (chained wide link included) at a size whose working set leaves L2"""
+    from libmultiviewnative_b200.synthetic import make_views_fast
+    from oracle import mvn_oracle as orc
+
+    dims = (256, 256, 1024)
+    d = make_views_fast(dims, 2, 31, 77)
+    ck = {1: None, 10: None}
+    orc.inplace_cpu_deconvolve_torch(d["psi0"], d["views"], d["kernels1"], d["kernels2"], d["weights"], 10, 0.006, 1e-4,
+                                     checkpoints=ck)
+    for iters in (1, 10):
+        psi = d["psi0"].copy()
+        L.inplace_gpu_deconvolve(psi, d["views"], d["kernels1"], d["kernels2"], d["weights"], iters, 0.006, 1e-4)
+        if iters == 1:
+            assert pc.max_rel(psi, ck[1]) <= pc.PER_VOXEL_TOL_1_ITER
+        assert pc.rel_l2(psi, ck[iters]) <= pc.REL_L2_TOL_10_ITER
+
+
+# ---- the callers either side of the path (SURVEY §8f-2, f-3) through the CUDA entry point -------------------
+def test_tiler_through_the_gpu_entry_point(L):
+    """block tiler with halo (ref: tests/tiff_fixtures.hpp:225-258): every block is one inplace_gpu_deconvolve
+    call; with wrap padding and a halo that covers the reach of the iterations the stitched result equals the
+    UNTILED oracle.  64^3 blocks run the power-of-two fast path."""
+    from libmultiviewnative_b200 import blocks, tiler
+    from libmultiviewnative_b200.synthetic import make_views
+    from oracle import mvn_oracle as orc
+
+    dims, ks, nv, iters, lam = (96, 80, 112), 5, 2, 1, 0.006
+    d = make_views(dims, num_views=nv, kernel_size=ks, n_sources=60, workers=4)
+    exp = orc.inplace_cpu_deconvolve(d["psi0"], d["views"], d["kernels1"], d["kernels2"], d["weights"], iters, lam, 1e-4,
+                                     nthreads=4)
+    halo = tuple(2 * iters * nv * (ks // 2) for _ in range(3))
+    run = lambda b: blocks.deconvolve_block(L, b, iters, lam, 1e-4, 0)
+    got = tiler.deconvolve_tiled(run, d["psi0"], d["views"], d["kernels1"], d["kernels2"], d["weights"], (64, 64, 64), halo,
+                                 pad_mode="wrap")
+    assert pc.max_rel(got, exp) <= pc.PER_VOXEL_TOL_1_ITER
+    # the reference fixture's rule (one kernel width of halo, reflected borders): close to the untiled result in the interior
+    got1 = tiler.deconvolve_tiled(run, d["psi0"], d["views"], d["kernels1"], d["kernels2"], d["weights"], (64, 64, 64),
+                                  num_kernel_widths=2, pad_mode="reflect")
+    inner = tuple(slice(12, n - 12) for n in dims)
+    assert pc.rel_l2(got1[inner], exp[inner]) < 5e-3
+
+
+def test_tiff_fixture_directory_through_the_gpu_entry_point(L, tmp_path):
+    """the reference's fixture layout (ref: tests/tiff_fixtures.hpp:18-27, 260-286, tests/tiff_utils.h:90-160):
+    input_view_i.tif / kernel{1,2}_view_i.tif / weights_view_i.tif are loaded from disk, run through
+    inplace_gpu_deconvolve, and compared with the psi_i.tif golden stacks (written here by the oracle -- the
+    reference's own set is not shipped)."""
+    from libmultiviewnative_b200 import tiffstack
+    from libmultiviewnative_b200.synthetic import make_views
+    from oracle import mvn_oracle as orc
+
+    d = make_views((48, 40, 64), num_views=3, kernel_size=7, n_sources=30, workers=4)
+    golden = {0: d["psi0"]}
+    for it in (1, 2, 5):
+        golden[it] = orc.inplace_cpu_deconvolve(d["psi0"], d["views"], d["kernels1"], d["kernels2"], d["weights"], it,
+                                                0.006, 1e-4, nthreads=4)
+    tiffstack.save_view_set(str(tmp_path), d["views"], d["kernels1"], d["kernels2"], d["weights"], psi=golden)
+    s = tiffstack.load_view_set(str(tmp_path), 3)
+    for it in (1, 2, 5):  # ref: tests/test_gpu_deconvolve.cpp -- GPU after 1 / 2 / 5 iterations vs psi_i
+        psi = s["psi"][0].copy()
+        L.inplace_gpu_deconvolve(psi, s["views"], s["kernels1"], s["kernels2"], s["weights"], it, 0.006, 1e-4)
+        assert pc.max_rel(psi, s["psi"][it]) <= pc.PER_VOXEL_TOL_1_ITER * it
+        out = str(tmp_path / ("gpu_psi_%d.tif" % it))
+        tiffstack.write_stack(out, psi)
+        np.testing.assert_array_equal(tiffstack.read_stack(out), psi)
+        # the reference's own criterion: sum of squared differences in the central box  (tests/test_gpu_deconvolve.cpp:51-69)
+        box = tuple(slice(int(n * 0.25), int(n * 0.75)) for n in psi.shape)
+        assert float(((psi[box] - s["psi"][it][box]).astype(np.float64) ** 2).sum()) < 1e-2
+
+
 # ---- one volume over several ranks (slab-decomposed plans), all ranks on this GPU ------------
 @pytest.mark.parametrize("dims,world", [((64, 64, 64), 2), ((128, 128, 128), 4), ((256, 256, 256), 8)])
 def test_slab_group_equals_single_plan(L, dims, world, monkeypatch):

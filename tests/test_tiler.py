@@ -55,6 +55,22 @@ def test_tiled_equals_untiled_with_sufficient_halo(iterations):
     assert pc.max_rel(got, exp) < 1e-5
 
 
+def test_default_halo_follows_the_fixture_rule():
+    """halo=None: num_kernel_widths * (extent // 2) of the largest PSF (ref: tests/tiff_fixtures.hpp:241)"""
+    dims = (24, 20, 28)
+    d = make_views(dims, num_views=1, kernel_size=5, n_sources=6, workers=1)
+    seen = []
+
+    def run(b):
+        seen.append(b["psi0"].shape)
+        return b["psi0"] + 1
+
+    got = tiler.deconvolve_tiled(run, d["psi0"], d["views"], d["kernels1"], d["kernels2"], d["weights"], (16, 16, 16),
+                                 num_kernel_widths=2, pad_mode="reflect")
+    assert len(seen) == len(tiler.plan_blocks(dims, (16, 16, 16), (4, 4, 4))) and all(s == (16, 16, 16) for s in seen)
+    np.testing.assert_array_equal(got, d["psi0"] + 1)
+
+
 def test_shards_compose():
     """block b on rank b mod G (blocks.shard): the union of the shards' stitched interiors is the full result"""
     from libmultiviewnative_b200.blocks import shard

@@ -66,11 +66,11 @@ def conv_sweep(args, lib, torch, peak, peak_src, device=0):
             e1.record()
             torch.cuda.synchronize()
             cufft_ms = e0.elapsed_time(e1) / 10.0
-            err = None
-            if np.prod(dims) <= 256 ** 3 and ks == 21:
-                exp = orc.inplace_cpu_convolution(img, k)
-                err = float(np.linalg.norm(out - exp) / np.linalg.norm(exp))
-                assert err < 1e-5, (dims, ks, err)
+            # every shape and every kernel size of the sweep is checked against the oracle (rel L2 <= 1e-5)
+            exp = orc.inplace_cpu_convolution(img, k, nthreads=-1)
+            err = float(np.linalg.norm(out.astype(np.float64) - exp) / np.linalg.norm(exp.astype(np.float64)))
+            assert err < 1e-5, (dims, ks, err)
+            del exp
             del x, kh, y
             nb = conv_bytes(dims)
             rows.append({"dims_zyx": list(dims), "kernel": ks, "strategy": int(strategy), "ms": ms, "GBps": nb / (ms * 1e-3) / 1e9,
@@ -198,3 +198,154 @@ def volume(args, lib, torch, dist, rank, world, device, barrier, max_over_ranks,
                      "peak_source": peak_src + " x n_gpus", "alg_bytes_per_view_iteration": alg,
                      "nvlink_GBps_per_gpu_out": (exch / world) * args.views * iters * args.steps / (ms * 1e-3) / 1e9 if world > 1 else 0.0},
     }
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Sub-records of the default bench.py run: BASELINE configs 4 and 5 in front of the driver (every --gpus N run
+# of the headline also measures them; N = 1 emits the single-GPU baselines).
+# ------------------------------------------------------------------------------------------------------------
+def _pin(torch, a):
+    t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    return t, t.numpy()
+
+
+def blocks_record(lib, torch, dist, rank, world, device, barrier, max_over_ranks, n_blocks=64, n1_blocks=8, depth=2,
+                  dims=(256, 256, 256), views=6, kernel=41, iterations=50):
+    """Config 4: n_blocks independent 256^3 blocks (6 views, 41^3 PSFs, 50 iterations) through inplace_gpu_deconvolve
+    with PAGEABLE host buffers (what JNA hands over), block b on GPU b mod G, no collective, two calls in flight per
+    GPU (blocks.run_pipelined).  Strong scaling.  The same-build one-GPU number it is compared with is measured in
+    the same invocation: rank 0 alone runs n1_blocks blocks before the sharded run."""
+    from libmultiviewnative_b200.blocks import run_pipelined, shard
+    from libmultiviewnative_b200.synthetic import make_views_fast
+
+    workers = max(1, (os.cpu_count() or 1) // max(1, world))
+    distinct = [make_views_fast(dims, views, kernel, 20240607 + 17 * i, workers) for i in range(2)]  # cycled (host RAM)
+    nvox = float(np.prod(dims))
+
+    def timed(indices, calls_in_flight=depth):
+        t0 = time.perf_counter()
+        run_pipelined(lib, lambda b: distinct[b % len(distinct)], indices, iterations, 0.006, 1e-4, device,
+                      depth=calls_in_flight, keep=False)
+        return time.perf_counter() - t0
+
+    timed([0, 1])  # warm-up: plan store, arenas, staging ring
+    barrier()
+    one_gpu = one_gpu_seq = None
+    if rank == 0:
+        per = nvox * views * iterations * n1_blocks / 1e9
+        one_gpu = per / timed(list(range(n1_blocks)))
+        one_gpu_seq = per / timed(list(range(n1_blocks)), 1)  # the same blocks, one call at a time (no overlap)
+    barrier()
+    mine = shard(n_blocks, rank, world)
+    t0 = time.perf_counter()
+    timed(mine)
+    barrier()
+    wall = max_over_ranks(time.perf_counter() - t0)
+    if rank != 0:
+        return None
+    value = nvox * views * iterations * n_blocks / wall / 1e9
+    return {"workload": "config 4: %d independent %dx%dx%d blocks, %d views, %d^3 PSFs, %d iterations, through "
+                        "inplace_gpu_deconvolve with pageable host buffers, block b on GPU b mod G, %d calls in flight per GPU, "
+                        "no collective" % (n_blocks, dims[0], dims[1], dims[2], views, kernel, iterations, depth),
+            "value": value, "unit": "Gvoxel*view*iter/s", "scaling": "strong", "n_gpus": world, "wall_s": wall,
+            "one_gpu_same_build": {"value": one_gpu, "blocks": n1_blocks, "one_call_at_a_time": one_gpu_seq},
+            "speedup_vs_one_gpu": value / one_gpu,
+            "h2d_bytes_per_block": int((2 * views + 1) * nvox * 4), "d2h_bytes_per_block": int(nvox * 4)}
+
+
+def volume_record(lib, torch, dist, rank, world, device, barrier, max_over_ranks, peak, dims=(1024, 1024, 1024), views=6,
+                  kernel=41, iterations=2, warmup=1, link_gbps=770.0):
+    """Config 5: ONE 1024^3 6-view volume, slab-decomposed over the G ranks (P2P-fused exchanges); G = 1: the ordinary
+    plan.  Also, for G > 1: the same-build single-GPU time of the same volume (rank 0 alone, before the slab plan is
+    created) and a 256^3 parity run of the multi-process path against the single-GPU plan."""
+    from libmultiviewnative_b200.slabs import ProcessSlabPlan, slab_of
+    from libmultiviewnative_b200.synthetic import gaussian_psf, make_views
+
+    nvox = float(np.prod(dims))
+    k = gaussian_psf(kernel, (4.0, 1.5, 1.5))
+    k2 = np.ascontiguousarray(k[::-1, ::-1, ::-1])
+    S = 4 * nvox
+    C = 8 * dims[0] * dims[1] * (dims[2] // 2 + 1)
+    alg = 7 * S + 10 * C
+
+    def single_gpu_ms():
+        rng = np.random.default_rng(5)
+        img = (rng.random(dims, dtype=np.float32) + 1.0).astype(np.float32)  # timing is data independent: one stack for all views
+        wts = np.full(dims, 1.0 / views, dtype=np.float32)
+        with lib.plan(dims, views, device) as plan:
+            for v in range(views):
+                plan.set_view(v, img, wts, k, k2)
+            plan.set_psi(img)
+            for _ in range(warmup):
+                plan.iterate(iterations, 0.006, 1e-4)
+            return plan.iterate(iterations, 0.006, 1e-4)
+
+    rec = {"workload": "config 5: ONE %dx%dx%d volume, %d views, %d^3 PSFs, %d timed iterations (%d warm-up)" % (
+        dims[0], dims[1], dims[2], views, kernel, iterations, warmup), "unit": "Gvoxel*view*iter/s", "scaling": "strong",
+        "n_gpus": world}
+    one_ms = None
+    if rank == 0:
+        one_ms = single_gpu_ms()
+        lib.release_cached_memory()
+        rec["one_gpu_same_build"] = {"value": nvox * views * iterations / (one_ms * 1e-3) / 1e9, "ms": one_ms,
+                                     "roofline_frac": alg * views * iterations / (one_ms * 1e-3) / 1e9 / peak}
+    if world == 1:
+        rec["value"] = rec["one_gpu_same_build"]["value"]
+        return rec
+    barrier()
+    # ---- parity of the multi-process path: 256^3 through the same code vs the single-GPU plan ----
+    pd = (256, 256, 256)
+    d = make_views(pd, num_views=2, kernel_size=15, n_sources=100, workers=4, seed=7)  # same on every rank
+    plan = ProcessSlabPlan(lib, pd, 2, dist, device)
+    for v in range(2):
+        plan.set_view(v, slab_of(d["views"][v], rank, world), slab_of(d["weights"][v], rank, world), d["kernels1"][v], d["kernels2"][v])
+    plan.set_psi_slab(slab_of(d["psi0"], rank, world))
+    plan.iterate(2, 0.006, 1e-4)
+    mine = torch.from_numpy(plan.get_psi_slab()).to("cuda:%d" % device)
+    parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, parts, dst=0)
+    plan.close()
+    if rank == 0:
+        got = torch.cat(parts, 0).cpu().numpy()
+        single = d["psi0"].copy()
+        lib.inplace_gpu_deconvolve(single, d["views"], d["kernels1"], d["kernels2"], d["weights"], 2, 0.006, 1e-4, device)
+        rel = float(np.max(np.abs(got - single) / np.abs(single)))
+        rec["parity_256cubed_vs_single_gpu"] = {"max_rel": rel, "bit_identical": bool(np.array_equal(got, single)),
+                                                "ok": bool(rel < 5e-6)}
+    lib.release_cached_memory()
+    barrier()
+    # ---- the timed volume ----
+    nz_l = dims[0] // world
+    slab = (nz_l, dims[1], dims[2])
+    rng = np.random.default_rng(5 + rank)
+    img = (rng.random(slab, dtype=np.float32) + 1.0).astype(np.float32)
+    wts = np.full(slab, 1.0 / views, dtype=np.float32)
+    plan = ProcessSlabPlan(lib, dims, views, dist, device)
+    for v in range(views):
+        plan.set_view(v, img, wts, k, k2)
+    plan.set_psi_slab(img)
+    exch = int(plan.info().exchange_bytes_per_view_iteration)
+    for _ in range(warmup):
+        plan.iterate(iterations, 0.006, 1e-4)
+    barrier()
+    ms = max_over_ranks(plan.iterate(iterations, 0.006, 1e-4))
+    plan.close()
+    lib.release_cached_memory()
+    if rank != 0:
+        return None
+    units = nvox * views * iterations
+    link_ms = (exch / world) * views * iterations / (link_gbps * 1e9) * 1e3   # bytes out of one GPU / measured peer rate
+    comp_ms = one_ms / world                                                  # the single-GPU time split perfectly
+    rec.update({
+        "value": units / (ms * 1e-3) / 1e9, "ms": ms, "speedup_vs_one_gpu": one_ms / ms,
+        "exchange_bytes_per_view_iteration_all_ranks": exch,
+        "nvlink_GBps_per_gpu_out": (exch / world) * views * iterations / (ms * 1e-3) / 1e9,
+        "link_ms_model": link_ms, "compute_ms_model": comp_ms,
+        # 1 = the shorter of (link time at %g GB/s, compute time = one-GPU time / G) is completely hidden behind the
+        # other; 0 = they add up
+        "overlap_fraction": max(0.0, min(1.0, (link_ms + comp_ms - ms) / max(1e-9, min(link_ms, comp_ms)))),
+        "overlap_definition": "(t_link + t_compute - t_measured) / min(t_link, t_compute), t_link = bytes out of one GPU / "
+                              "%g GB/s (measured peer copy rate, B200_PROFILING.md), t_compute = same-build one-GPU time / G" % link_gbps,
+        "roofline_frac_of_G_x_hbm": alg * views * iterations / (ms * 1e-3) / 1e9 / (peak * world),
+    })
+    return rec
