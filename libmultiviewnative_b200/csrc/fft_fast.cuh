@@ -275,11 +275,27 @@ template <int N, int MODE> struct StridedBlocks {
 
 enum Where { W_SMEM = 0, W_GLOBAL = 1, W_GLOBAL_SCALED = 2, W_SCATTER = 3 };
 
+// t[1 .. R-1] = the R - 1 twiddles of one butterfly, a table row of R complex entries (16-byte aligned: R is even).
+// Two entries per 128-bit load: these passes are bound by the number of load/store instructions the SM can issue,
+// and the twiddle fetches were a fifth of them (62 of 318 per thread and tile in the merged z pass).
+template <int R>
+__device__ __forceinline__ void load_twiddles(cplx* t, const cplx* __restrict__ row) {
+  static_assert(R % 2 == 0, "pairs");
+  const float4* r4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+  for (int q = 0; q < R / 2; ++q) {
+    const float4 f = __ldg(r4 + q);
+    t[2 * q] = cmake(f.x, f.y);
+    t[2 * q + 1] = cmake(f.z, f.w);
+  }
+}
+
 // One radix-R stage of span L on the thread's column.  Forward (INV = false) is a
 // decimation-in-frequency stage (butterfly, then twiddle w_L^{jq}); inverse is the
 // decimation-in-time mirror (conjugate twiddle, then butterfly).  `sm` and `g`
 // already point at this thread's column; rows are addressed with 32-bit offsets.
-template <int N, int R, int L, int COLS, bool INV, int SRC, int DST, int UNROLL = 8>
+// PITCH: row pitch of the shared-memory tile (the two-pass schedule pads its rows, fft_x3.cuh).
+template <int N, int R, int L, int COLS, bool INV, int SRC, int DST, int UNROLL = 8, int PITCH = COLS>
 __device__ __forceinline__ void strided_stage(cplx* __restrict__ sm, cplx* __restrict__ g, int rs,
                                               const cplx* __restrict__ tws, float scale,
                                               const Scatter* sc = nullptr, long long sc_tile = 0) {
@@ -296,9 +312,9 @@ __device__ __forceinline__ void strided_stage(cplx* __restrict__ sm, cplx* __res
     const int row0 = (bf / M) * L + j;
     cplx v[R];
     if (SRC == W_SMEM) {
-      const cplx* p = sm + row0 * COLS;
+      const cplx* p = sm + row0 * PITCH;
 #pragma unroll
-      for (int r = 0; r < R; ++r) v[r] = p[r * M * COLS];
+      for (int r = 0; r < R; ++r) v[r] = p[r * M * PITCH];
     } else {
       // one 64-bit pointer bumped by a uniform 64-bit step: two integer instructions per access
       // (index arithmetic in 32 bits costs five: zero extension, carry chain, scaled address)
@@ -312,11 +328,7 @@ __device__ __forceinline__ void strided_stage(cplx* __restrict__ sm, cplx* __res
       }
     }
     cplx t[R];  // fetched before the butterfly so that their latency hides behind it
-    if (M > 1) {
-      const cplx* tp = tws + j * R;
-#pragma unroll
-      for (int q = 1; q < R; ++q) t[q] = __ldg(tp + q);
-    }
+    if (M > 1) load_twiddles<R>(t, tws + j * R);
     if (INV && M > 1) {
 #pragma unroll
       for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], t[q]);
@@ -327,9 +339,9 @@ __device__ __forceinline__ void strided_stage(cplx* __restrict__ sm, cplx* __res
       for (int q = 1; q < R; ++q) v[q] = cmul(v[q], t[q]);
     }
     if (DST == W_SMEM) {
-      cplx* p = sm + row0 * COLS;
+      cplx* p = sm + row0 * PITCH;
 #pragma unroll
-      for (int q = 0; q < R; ++q) p[q * M * COLS] = v[q];
+      for (int q = 0; q < R; ++q) p[q * M * PITCH] = v[q];
     } else if (DST == W_SCATTER) {
       const int mask = (1 << sc->shift) - 1;
 #pragma unroll
@@ -353,7 +365,7 @@ __device__ __forceinline__ void strided_stage(cplx* __restrict__ sm, cplx* __res
 // middle of the merged z pass: last forward stage (span R), spectrum product, first inverse stage.
 // The K^ operands come straight from HBM; middle_load() is called BEFORE the barrier that precedes
 // the middle so that their latency overlaps the barrier wait and the shared-memory reads.
-template <int N, int R, int COLS>
+template <int N, int R, int COLS, int PITCH = COLS>
 struct Middle {
   static const int RG = Threads<N>::V / COLS;
   static const int PT = (N / R) / RG;  // butterflies per thread: 1 or 2 in every plan that is used
@@ -375,16 +387,16 @@ struct Middle {
     const int rg = threadIdx.x / COLS;
 #pragma unroll
     for (int i = 0; i < PT; ++i) {
-      cplx* p = sm + (rg + i * RG) * R * COLS;
+      cplx* p = sm + (rg + i * RG) * R * PITCH;
       cplx v[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) v[r] = p[r * COLS];
+      for (int r = 0; r < R; ++r) v[r] = p[r * PITCH];
       Bfly<R, false>::run(v);
 #pragma unroll
       for (int r = 0; r < R; ++r) v[r] = cmul(v[r], o.k[i][r]);
       Bfly<R, true>::run(v);
 #pragma unroll
-      for (int r = 0; r < R; ++r) p[r * COLS] = v[r];
+      for (int r = 0; r < R; ++r) p[r * PITCH] = v[r];
     }
   }
 };
@@ -532,7 +544,24 @@ struct RowArgs {
   cplx* spec_out;
   cplx* nyq_out;
   int lz, ly, lx, oz, oy, ox;
+  // plane kernels (fft_x3.cuh): spectrum row i of the tile is real-space row rr_base + i * (1 + rr_skip) of the volume
+  // (both zero everywhere else: spectrum row = real-space row)
+  long long rr_base;
+  int rr_skip;
 };
+// (compile-time switch: the rows kernels that work on global spectra have no register to spare for the mapping)
+template <int SP>
+__device__ __forceinline__ long long real_row(const RowArgs& A, long long row) {
+  return SP ? A.rr_base + row * (1 + A.rr_skip) : row;
+}
+
+// where the spectrum rows of an x pass live: SP = 0 global memory (streaming accesses), SP = 1 shared memory (the plane
+// kernels transform the rows of a tile in place)
+template <int SP> __device__ __forceinline__ cplx ld_spec(const cplx* p) { return SP ? *p : ld_stream(p); }
+template <int SP> __device__ __forceinline__ void st_spec(cplx* p, cplx v) {
+  if (SP) *p = v;
+  else st_stream(p, v);
+}
 
 // a + conj(b) and a - conj(b): one packed FFMA2 each on sm_100
 __device__ __forceinline__ cplx cadd_conj(cplx a, cplx b) {
@@ -614,11 +643,11 @@ struct RowTwShared {
 // forward transform of RPG rows whose samples are already in registers: v[a * R1 + r] = complex sample
 // lane + 16 r of row row0 + a (the distribution the loads of rows_fwd_group produce, and exactly what the
 // last butterfly of the inverse leaves behind)
-template <int M, typename TW>
+template <int M, typename TW, int SP = 0>
 __device__ __forceinline__ void rows_fwd_from_regs(const RowArgs& A, cplx* slab, long long row0, int lane,
                                                    const TW& T, cplx* v);
 
-template <int M, bool WRAPPED, typename TW>
+template <int M, bool WRAPPED, typename TW, int SP = 0>
 __device__ __forceinline__ void rows_fwd_group(const RowArgs& A, cplx* slab, long long row0, int lane,
                                                const TW& T) {
   typedef Row2Cfg<M> CF;
@@ -630,7 +659,7 @@ __device__ __forceinline__ void rows_fwd_group(const RowArgs& A, cplx* slab, lon
   for (int a = 0; a < RPG; ++a) {
     const long long row = row0 + a;
     if (!WRAPPED) {
-      const float2* in = reinterpret_cast<const float2*>(A.src.data + row * nx);
+      const float2* in = reinterpret_cast<const float2*>(A.src.data + real_row<SP>(A, row) * nx);
 #pragma unroll
       for (int r = 0; r < R1; ++r) v[a * R1 + r] = ld_stream(in + lane + 16 * r);
     } else {
@@ -652,10 +681,10 @@ __device__ __forceinline__ void rows_fwd_group(const RowArgs& A, cplx* slab, lon
       }
     }
   }
-  rows_fwd_from_regs<M>(A, slab, row0, lane, T, v);
+  rows_fwd_from_regs<M, TW, SP>(A, slab, row0, lane, T, v);
 }
 
-template <int M, typename TW>
+template <int M, typename TW, int SP>
 __device__ __forceinline__ void rows_fwd_from_regs(const RowArgs& A, cplx* slab, long long row0, int lane,
                                                    const TW& T, cplx* v) {
   typedef Row2Cfg<M> CF;
@@ -697,14 +726,15 @@ __device__ __forceinline__ void rows_fwd_from_regs(const RowArgs& A, cplx* slab,
       const int k = lane + 16 * i;
       if (k == 0) {
         const cplx z0 = zr[0];
-        st_stream(orow, cmake(z0.x + z0.y, 0.f));
-        st_stream(A.nyq ? A.nyq + (row0 + a) : orow + M, cmake(z0.x - z0.y, 0.f));
-        st_stream(orow + M / 2, cconj(zr[M / 2]));
+        const cplx zh = zr[M / 2];  // read before the stores: with SP = 1 the spectrum row IS the slab row
+        st_spec<SP>(orow, cmake(z0.x + z0.y, 0.f));
+        st_spec<SP>(A.nyq ? A.nyq + (row0 + a) : orow + M, cmake(z0.x - z0.y, 0.f));
+        st_spec<SP>(orow + M / 2, cconj(zh));
       } else {
         cplx xk, xm;
         r2c_pair(zr[k], zr[M - k], T.twp(i), xk, xm);
-        st_stream(orow + k, xk);
-        st_stream(orow + (M - k), xm);
+        st_spec<SP>(orow + k, xk);
+        st_spec<SP>(orow + (M - k), xm);
       }
     }
   }
@@ -715,7 +745,7 @@ __device__ __forceinline__ void rows_fwd_from_regs(const RowArgs& A, cplx* slab,
 // CHAIN: the real samples the epilogue produces are not (only) stored but forward transformed again and
 // written back as the row's spectrum -- the x pass of the NEXT convolution, fused: `integral` never goes to
 // HBM at all and the new psi is not read back (saves 3S of the 7S + 18C per (view, iteration)).
-template <int M, int EPI, typename TW, bool CHAIN = false, bool EMBED = false>
+template <int M, int EPI, typename TW, bool CHAIN = false, bool EMBED = false, int SP = 0>
 __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, long long row0, int lane,
                                                const TW& T) {
   typedef Row2Cfg<M> CF;
@@ -745,11 +775,12 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
 #pragma unroll
     for (int i = 0; i < PAIRS; ++i) {
       const int k = lane + 16 * i;
-      xs[a * PAIRS + i] = ld_stream(irow + k);
-      xm[a * PAIRS + i] = ld_stream((k == 0 && A.nyq) ? A.nyq + srow[a] : irow + (M - k));  // k = 0 reads X[M]
+      xs[a * PAIRS + i] = ld_spec<SP>(irow + k);
+      xm[a * PAIRS + i] = ld_spec<SP>((k == 0 && A.nyq) ? A.nyq + srow[a] : irow + (M - k));  // k = 0 reads X[M]
     }
-    if (lane == 0) xh[a] = ld_stream(irow + M / 2);
+    if (lane == 0) xh[a] = ld_spec<SP>(irow + M / 2);
   }
+  if (SP) __syncwarp();  // the spectrum rows are the slab rows: every lane has read before any lane writes
   // epilogue operands: independent of the transform, fetched now so that their latency
   // overlaps both exchanges (element n = lane + 16 r of each row = real samples 2n, 2n+1)
   float2 oa[16], ob[16];
@@ -757,7 +788,7 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
     const float* pa = (mode == gen::EPI_QUOTIENT) ? A.ep.view : A.ep.psi;
 #pragma unroll
     for (int a = 0; a < RPG; ++a) {
-      const float2* p2 = reinterpret_cast<const float2*>(pa + srow[a] * nx);
+      const float2* p2 = reinterpret_cast<const float2*>(pa + real_row<SP>(A, srow[a]) * nx);
 #pragma unroll
       for (int r = 0; r < R1; ++r) oa[a * R1 + r] = ld_stream(p2 + lane + 16 * r);
     }
@@ -787,7 +818,7 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
     // its latency still overlaps the radix-16 stage and the second exchange
 #pragma unroll
     for (int a = 0; a < RPG; ++a) {
-      const float2* p2 = reinterpret_cast<const float2*>(A.ep.weights + srow[a] * nx);
+      const float2* p2 = reinterpret_cast<const float2*>(A.ep.weights + real_row<SP>(A, srow[a]) * nx);
 #pragma unroll
       for (int r = 0; r < R1; ++r) ob[a * R1 + r] = ld_stream(p2 + lane + 16 * r);
     }
@@ -818,7 +849,7 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
       v[a * R1 + q] = x;
     }
     Bfly<R1, true>::run(v + a * R1);
-    float2* orow = reinterpret_cast<float2*>(obase + srow[a] * nx);
+    float2* orow = reinterpret_cast<float2*>(obase + real_row<SP>(A, srow[a]) * nx);
     const bool own_row = !EMBED || srow[a] == row0 + a;  // aliases recompute, only the interior row stores psi
 #pragma unroll
     for (int r = 0; r < R1; ++r) {
@@ -864,9 +895,9 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
     RowArgs B = A;  // the forward transform writes the OTHER spectrum buffer, at the row's own position
     B.spec = A.spec_out;
     B.nyq = A.nyq_out;
-    rows_fwd_from_regs<M>(B, slab, row0, lane, T, v);
+    rows_fwd_from_regs<M, TW, 0>(B, slab, row0, lane, T, v);
   } else if (CHAIN) {
-    rows_fwd_from_regs<M>(A, slab, row0, lane, T, v);
+    rows_fwd_from_regs<M, TW, SP>(A, slab, row0, lane, T, v);
   }
 }
 

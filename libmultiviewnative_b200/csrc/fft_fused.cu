@@ -19,6 +19,7 @@
 
 #include "engine.cuh"
 #include "fft_fast.cuh"
+#include "fft_x3.cuh"
 
 namespace lmvn {
 
@@ -35,8 +36,13 @@ struct FastTables {
   cplx* tw_y[2] = {nullptr, nullptr};
   cplx* tw_z[2] = {nullptr, nullptr};
   bool y_alt = false;  // ny = 1024: the y passes run the 32 x 32 plan (fast::Plan<1024, 1>), tw_y holds its tables
+  cplx* tw_p128[2] = {nullptr, nullptr};  // two-pass schedule: stage tables of the 128-point in-tile y transform
+  cplx* tw_ny_lin = nullptr;              // two-pass schedule: w_ny^m, m < ny
   ~FastTables() {
     cudaSetDevice(device);
+    for (int i = 0; i < 2; ++i)
+      if (tw_p128[i]) cudaFree(tw_p128[i]);
+    if (tw_ny_lin) cudaFree(tw_ny_lin);
     if (tw_h) cudaFree(tw_h);
     if (tw_m) cudaFree(tw_m);
     if (tw_nx) cudaFree(tw_nx);
@@ -46,6 +52,12 @@ struct FastTables {
     }
   }
 };
+
+// extents the two-pass schedule (fft_x3.cuh) takes: 128-row plane tiles of nx = 256, ny = 128 * R2 with R2 in {2, 4},
+// two-stage z plans whose tiles are at most 32 columns wide
+static bool x3_shape_ok(int nz, int ny, int nx) {
+  return nx == 256 && (ny == 256 || ny == 512) && (nz == 64 || nz == 128 || nz == 256 || nz == 512);
+}
 
 struct FastEngine : ConvEngine, FastOps {
   std::shared_ptr<FastTables> tables;
@@ -123,6 +135,10 @@ struct FastEngine : ConvEngine, FastOps {
         if (const char* e = getenv("LMVN_Y1024_WIDE")) t->y_alt = t->y_alt && (*e != '0');
         LMVN_TRY(upload_stage_tables(t->tw_y, plan->ny, t->y_alt));
         LMVN_TRY(upload_stage_tables(t->tw_z, plan->nz, false));
+        if (x3_shape_ok(plan->nz, plan->ny, plan->nx)) {
+          LMVN_TRY(upload_stage_tables(t->tw_p128, 128, false));
+          LMVN_TRY(upload_table(&t->tw_ny_lin, plan->ny, plan->ny));
+        }
         plan->fast_tables = t;
       }
       tables = std::static_pointer_cast<FastTables>(plan->fast_tables);
@@ -570,6 +586,141 @@ struct FastEngine : ConvEngine, FastOps {
   }
 };
 
+// ------------------------------------------------------------------------------------------------------------
+// Two-pass schedule (fft_x3.cuh): plane-tile pass + z-middle pass, spectrum in the A layout.  The PSF spectra are
+// produced by the five-pass kernels of the base class into the work buffer and permuted into the A layout.
+// ------------------------------------------------------------------------------------------------------------
+struct X3Engine : FastEngine {
+  int r2 = 4;
+  size_t a_elems() const { return size_t(r2) * plan->nz * x3::kTileElems; }
+  size_t khat_elems() const override { return std::max(a_elems(), FastEngine::khat_elems()); }
+  size_t work_elems() const override { return khat_elems(); }
+  int launches_per_conv() const override { return 2; }
+  bool can_chain() const override { return true; }
+  bool can_chain_embedded() const override { return false; }
+  bool can_chain_rows() const override { return false; }
+
+  int x3_prefetch = 0;  // CTAs of look-ahead of the plane pass' L2 prefetch (A/B knob LMVN_X3_PREFETCH)
+  int init_x3() {
+    r2 = plan->ny / x3::kRows;
+    x3_prefetch = 0;  // measured: -3 % (quotient) / -11 % (update) with a look-ahead of one CTA per SM (profiles/r02_x3_v2_probe*.json)
+    if (const char* e = getenv("LMVN_X3_PREFETCH")) x3_prefetch = std::max(0, atoi(e));
+    if (!tables->tw_p128[0] || !tables->tw_ny_lin) { set_last_error("two-pass schedule: tables missing"); return -1; }
+    return 0;
+  }
+
+  template <int MODE, int EPI>
+  int launch_plane(const x3::PlaneArgs& a, cudaStream_t s) {
+    auto k = x3::k_plane<MODE, EPI>;
+    LMVN_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(x3::kPlaneSmem)));
+    LMVN_LAUNCH(k, dim3(unsigned(plan->nz * r2)), dim3(x3::kPlaneThreads), x3::kPlaneSmem, s, a);
+    LMVN_CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+  int plane(int mode, cplx* a_buf, const float* in, const gen::Epilogue* ep, float* out, cudaStream_t s) {
+    x3::PlaneArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.a = a_buf;
+    a.nz = plan->nz; a.ny = plan->ny; a.r2 = r2;
+    a.tw_y = tables->tw_p128[0];
+    a.prefetch = x3_prefetch;
+    a.row.tw_m = d_tw_m; a.row.tw_nx = d_tw_nx;
+    a.row.nz = plan->nz; a.row.ny = plan->ny;
+    int epi = gen::EPI_STORE;
+    if (ep) {
+      if (ep->scale != 1.f) { set_last_error("two-pass schedule: the 1/N scale lives in the PSF spectra"); return -1; }
+      a.row.ep = *ep;
+      epi = ep->mode;
+    }
+    a.row.out = out;
+    if (in) a.row.src = gen::RealSource{in, 0, 0, 0, 0};
+    const unsigned long long Sb = S(), Cb = C();
+    if (mode == x3::PM_BEGIN) {
+      LMVN_TRY((launch_plane<x3::PM_BEGIN, gen::EPI_STORE>(a, s)));
+      mark("x3_plane_fwd", Sb + Cb, s);
+    } else if (mode == x3::PM_CHAIN) {
+      if (epi == gen::EPI_QUOTIENT) {
+        LMVN_TRY((launch_plane<x3::PM_CHAIN, gen::EPI_QUOTIENT>(a, s)));
+        mark("x3_plane_quotient", 2 * Cb + Sb, s);
+      } else if (epi == gen::EPI_UPDATE) {
+        LMVN_TRY((launch_plane<x3::PM_CHAIN, gen::EPI_UPDATE>(a, s)));
+        mark("x3_plane_update", 2 * Cb + 3 * Sb, s);
+      } else { set_last_error("two-pass schedule: chained pass needs a quotient or update epilogue"); return -1; }
+    } else {
+      switch (epi) {
+        case gen::EPI_QUOTIENT: LMVN_TRY((launch_plane<x3::PM_END, gen::EPI_QUOTIENT>(a, s))); break;
+        case gen::EPI_UPDATE: LMVN_TRY((launch_plane<x3::PM_END, gen::EPI_UPDATE>(a, s))); break;
+        default: LMVN_TRY((launch_plane<x3::PM_END, gen::EPI_STORE>(a, s))); break;
+      }
+      mark("x3_plane_inv", Cb + Sb * (epi == gen::EPI_UPDATE ? 3 : (epi == gen::EPI_QUOTIENT ? 2 : 1)), s);
+    }
+    return 0;
+  }
+
+  template <int NZ, int RR>
+  int launch_zmid(const x3::ZmidArgs& a, cudaStream_t s) {
+    constexpr int COLS = x3::ZmidCols<NZ>::V;
+    const size_t smem = size_t(NZ) * x3::ZmidPitch<NZ, RR>::V * sizeof(cplx);
+    auto k = x3::k_zmid<NZ, RR>;
+    LMVN_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const unsigned tiles = unsigned((x3::kRows + 1) * (x3::kM / (COLS / RR)));
+    LMVN_LAUNCH(k, dim3(tiles), dim3(fast::Threads<NZ>::V), smem, s, a);
+    LMVN_CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+  int zmid(cplx* a_buf, const cplx* khat, cudaStream_t s) {
+    x3::ZmidArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.a = a_buf; a.khat = khat; a.nz = plan->nz; a.r2 = r2;
+    a.tw1 = d_tw_z[0]; a.tw2 = d_tw_z[1]; a.tw_ny = tables->tw_ny_lin;
+    int rc = -1;
+    if (r2 == 4) {
+      switch (plan->nz) {
+        case 64: rc = launch_zmid<64, 4>(a, s); break;
+        case 128: rc = launch_zmid<128, 4>(a, s); break;
+        case 256: rc = launch_zmid<256, 4>(a, s); break;
+        case 512: rc = launch_zmid<512, 4>(a, s); break;
+      }
+    } else if (r2 == 2) {
+      switch (plan->nz) {
+        case 64: rc = launch_zmid<64, 2>(a, s); break;
+        case 128: rc = launch_zmid<128, 2>(a, s); break;
+        case 256: rc = launch_zmid<256, 2>(a, s); break;
+        case 512: rc = launch_zmid<512, 2>(a, s); break;
+      }
+    }
+    if (rc != 0) { if (rc == -1 && !*last_error()) set_last_error("two-pass schedule: unsupported z extent"); return -1; }
+    mark("x3_z_mul", 3 * C(), s);
+    return 0;
+  }
+
+  int chain_begin(const float* in, cplx* work, cudaStream_t s) override { return plane(x3::PM_BEGIN, work, in, nullptr, nullptr, s); }
+  int chain_middle(cplx* work, const cplx* khat, cudaStream_t s) override { return zmid(work, khat, s); }
+  int chain_link(cplx* work, const gen::Epilogue& ep, cudaStream_t s) override { return plane(x3::PM_CHAIN, work, nullptr, &ep, nullptr, s); }
+  int chain_end(cplx* work, const gen::Epilogue& ep, float* out, cudaStream_t s) override {
+    return plane(x3::PM_END, work, nullptr, &ep, out, s);
+  }
+  int convolve(const float* in, cplx* work, const cplx* khat, const gen::Epilogue& ep, float* out, cudaStream_t s) override {
+    LMVN_TRY(plane(x3::PM_BEGIN, work, in, nullptr, nullptr, s));
+    LMVN_TRY(zmid(work, khat, s));
+    return plane(x3::PM_END, work, nullptr, &ep, out, s);
+  }
+  int kernel_spectrum(const float* d_kernel, const int kd[3], cplx* khat, cplx* work, cudaStream_t s) override {
+    // five-pass kernels into the work buffer (split layout of the base class), then the permutation into the A layout
+    LMVN_TRY(FastEngine::kernel_spectrum(d_kernel, kd, work, nullptr, s));
+    x3::KhatPermArgs k;
+    k.main = work; k.nyq = nyq_of(work); k.out = khat;
+    k.nz = plan->nz; k.ny = plan->ny; k.r2 = r2;
+    switch (plan->ny) {
+      case 512: k.y_r1 = fast::Radix<512>::R1; k.y_r2 = fast::Radix<512>::R2; k.y_r3 = 1; break;
+      default: k.y_r1 = fast::Radix<256>::R1; k.y_r2 = fast::Radix<256>::R2; k.y_r3 = 1; break;
+    }
+    LMVN_LAUNCH(x3::k_khat_to_a, dim3(unsigned(num_sms * 8)), dim3(256), 0, s, k);
+    LMVN_CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+};
+
 bool axis_ok(int n) { return n == 16 || n == 32 || n == 64 || n == 128 || n == 256 || n == 512 || n == 1024; }
 bool nx_ok(int nx) { return nx == 64 || nx == 128 || nx == 256 || nx == 512 || nx == 1024; }
 
@@ -600,9 +751,22 @@ std::unique_ptr<ConvEngine> make_fused_engine(std::shared_ptr<FftPlan> plan) {
   if (!axis_ok(plan->ny) || !axis_ok(plan->nz)) return nullptr;
   const size_t rows = size_t(plan->nz) * plan->ny;
   if (rows % 128 != 0) return nullptr;
+  if (cudaSetDevice(plan->device) != cudaSuccess) return nullptr;
+  // The two-pass schedule (fft_x3.cuh) is OPT-IN (LMVN_X3=1): it moves 4S + 10C instead of 4S + 18C per (view, iteration)
+  // and is still 12 % slower than the chained five-pass loop on BASELINE config 3 (1.17 vs 1.04 ms, DESIGN.md 3.4,
+  // profiles/r02_x3_*.json): the passes are bound by the SM's load/store/shared-memory pipe, which the fusion does
+  // not relieve (it trades global for shared wavefronts one for one).
+  bool x3 = false;
+  if (const char* e = getenv("LMVN_X3")) x3 = (*e != '0') && x3_shape_ok(plan->nz, plan->ny, plan->nx);
+  if (const char* e = getenv("LMVN_CHAIN")) x3 = x3 && (*e != '0');  // LMVN_CHAIN=0: the unchained five-pass loop
+  if (x3) {
+    std::unique_ptr<X3Engine> e(new X3Engine());
+    e->plan = plan;
+    if (e->init() != 0 || e->init_x3() != 0) return nullptr;
+    return std::unique_ptr<ConvEngine>(e.release());
+  }
   std::unique_ptr<FastEngine> e(new FastEngine());
   e->plan = plan;
-  if (cudaSetDevice(plan->device) != cudaSuccess) return nullptr;
   if (e->init() != 0) return nullptr;
   return std::unique_ptr<ConvEngine>(e.release());
 }

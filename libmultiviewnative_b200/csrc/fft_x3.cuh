@@ -1,0 +1,343 @@
+// fft_x3.cuh -- the two-pass ("three HBM round trips per convolution") schedule of the power-of-two fast path.
+//
+// The five-pass schedule of fft_fast.cuh moves the spectrum between HBM and the SMs five times per convolution
+// (x | y | z * K^ * z^-1 | y^-1 | x^-1; four launches in the chained loop).  Every one of those passes already streams
+// at 5.3 - 5.9 TB/s, so the only way to go faster is to move fewer bytes.  A whole
+// x-y plane (512 x 129 complex = 516 KB for BASELINE config 3) does not fit the 227 KB of one SM, and a 4-CTA cluster
+// that does fit it leaves 16 of the 148 SMs idle and pays the x <-> y transposition through DSMEM at ~20 B/clk/SM.
+// This file splits the y axis by DIGITS instead:   ny = 128 * R2   (R2 = 4 for ny = 512, 2 for ny = 256)
+//
+//   pass A  "plane tile"  k_plane<MODE>   one CTA = the 128 rows y = R2 * i + n2 of one z plane (a 128 KB spectrum tile in
+//           shared memory):  [128-point inverse along i] -> [x inverse] -> quotient / RL update -> [x forward] ->
+//           [128-point forward along i].  Everything the chained rows kernel of fft_fast.cuh did, plus seven of the
+//           nine (eight) radix-2 levels of the y transform, without touching HBM in between.
+//   pass B  "z middle"    k_zmid          the merged z pass of fft_fast.cuh (forward z, * K^, inverse z on 64 KB tiles)
+//           with the remaining radix-R2 level of y as a register stage on the way in and out: a tile holds the R2
+//           samples (n2 = 0 .. R2-1) of its short y transforms, as pieces of KXC = 16 / R2 adjacent kx columns.
+//
+// HBM traffic per (view, iteration): (2C + S) + 3C + (2C + 3S) + 3C = 4S + 10C -- below the contract's 7S + 10C
+// (SURVEY.md section 8d), against 4S + 18C of the chained five-pass loop.
+//
+// Spectrum layout between the passes ("A layout"):  A[n2][z][p][kx], n2 < R2, p < 129, kx < 128 (complex64).
+//   p < 128: position p of the 128-point transform along i (16 x 8 decimation in frequency: p = 8 q1 + q2 holds
+//            frequency k1 = q1 + 16 q2);  p = 128: the Nyquist column kx = nx/2 of the tile, TRANSPOSED (entry kx
+//            of that row = position kx), so that the array is uniform: pass B sees 129 x 128 identical columns per (n2, z)
+//            and needs no special case, pass A reads / writes one contiguous 129 KB tile.
+//   after the forward radix-R2 level slot n2 holds ky = k1 + 128 * n2; z is in the digit-reversed order
+//   of fft_fast.cuh's merged pass.  K^ is precomputed by the five-pass kernels and permuted into this layout once
+//   per view (k_khat_to_a), so the spectrum product never needs a natural order.
+#pragma once
+#include "fft_fast.cuh"
+
+namespace lmvn {
+namespace x3 {
+
+using namespace fast;
+
+static const int kRows = 128;      // rows of a plane tile = length of the in-tile y transform
+static const int kM = 128;         // complex samples per row (nx = 256)
+static const int kPitch = 136;     // shared-memory row pitch = Row2Cfg<128>::RS: the x transforms run in place on the tile rows
+static const int kPlaneThreads = 512;
+static const int kTileElems = (kRows + 1) * kM;  // 129 x 128 complex per (n2, z) in HBM
+static const size_t kPlaneSmem = size_t(kRows) * kPitch * sizeof(cplx);
+
+enum PlaneMode { PM_CHAIN = 0, PM_BEGIN = 1, PM_END = 2 };
+
+struct PlaneArgs {
+  RowArgs row;        // spec = nullptr (set per CTA), ep, src (PM_BEGIN), out (PM_END), tw_m, tw_nx
+  cplx* a;            // A layout, transformed in place
+  int nz, ny, r2;     // r2 = ny / 128
+  const cplx* tw_y;   // [j < 8][q < 16] = w_128^{jq}: stage table of the 128-point transform (16 x 8)
+  int prefetch;       // > 0: once its own tile is on chip, a CTA pulls the tile and the operand rows of CTA
+                      // blockIdx + prefetch (the one that takes an SM next) from HBM into L2
+};
+
+// L2 prefetch of everything CTA `b` will read: its spectrum tile and its rows of the pointwise operands
+template <int MODE, int EPI>
+__device__ __forceinline__ void plane_prefetch(const PlaneArgs& P, unsigned b) {
+  if (b >= unsigned(P.nz * P.r2)) return;
+  const int n2 = b % P.r2, z = b / P.r2;
+  if (MODE != PM_BEGIN) {
+    const char* t = reinterpret_cast<const char*>(P.a + (size_t(n2) * P.nz + z) * kTileElems);
+    for (int i = threadIdx.x; i < int(kTileElems * sizeof(cplx) / 128); i += kPlaneThreads) prefetch_l2(t + size_t(i) * 128);
+  }
+  // real-space rows y = r2 * i + n2 of plane z: 2 * kM floats = 8 lines each
+  const size_t row0 = size_t(z) * P.ny + n2;
+  const float* ops[2] = {nullptr, nullptr};
+  if (MODE == PM_BEGIN) ops[0] = P.row.src.data;
+  else if (EPI == gen::EPI_QUOTIENT) ops[0] = P.row.ep.view;
+  else if (EPI == gen::EPI_UPDATE) { ops[0] = P.row.ep.psi; ops[1] = P.row.ep.weights; }
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    if (!ops[o]) continue;
+    for (int i = threadIdx.x; i < kRows * 8; i += kPlaneThreads) {
+      const size_t row = row0 + size_t(i / 8) * P.r2;
+      prefetch_l2(reinterpret_cast<const char*>(ops[o] + row * (2 * kM)) + (i % 8) * 128);
+    }
+  }
+}
+
+// one radix-R butterfly of span L of the 128-point transform along the tile rows, for one column.
+// sm: the column in shared memory (row pitch kPitch); g: the column in global memory (row stride g_rs).
+template <int R, int L, bool INV, int SRC, int DST>
+__device__ __forceinline__ void plane_bfly(cplx* sm, cplx* g, int g_rs, const cplx* __restrict__ tws, int bf) {
+  constexpr int Mq = L / R;
+  const int j = bf % Mq;
+  const int row0 = (bf / Mq) * L + j;
+  cplx v[R];
+  if (SRC == W_SMEM) {
+    const cplx* p = sm + row0 * kPitch;
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = p[r * Mq * kPitch];
+  } else {
+    const cplx* gp = g + row0 * g_rs;
+    const int step = Mq * g_rs;
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = ld_stream(gp + r * step);
+  }
+  cplx t[R];
+  if (Mq > 1) load_twiddles<R>(t, tws + j * R);
+  if (INV && Mq > 1) {
+#pragma unroll
+    for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], t[q]);
+  }
+  Bfly<R, INV>::run(v);
+  if (!INV && Mq > 1) {
+#pragma unroll
+    for (int q = 1; q < R; ++q) v[q] = cmul(v[q], t[q]);
+  }
+  if (DST == W_SMEM) {
+    cplx* p = sm + row0 * kPitch;
+#pragma unroll
+    for (int q = 0; q < R; ++q) p[q * Mq * kPitch] = v[q];
+  } else {
+    cplx* gp = g + row0 * g_rs;
+    const int step = Mq * g_rs;
+#pragma unroll
+    for (int q = 0; q < R; ++q) st_stream(gp + q * step, v[q]);
+  }
+}
+
+// one stage over the whole tile: 128 ordinary columns (thread = column tid % 128, four row groups) and the Nyquist
+// column (tile column 128 <-> row 128 of the tile in HBM, stride 1), which the first threads take on top
+template <int R, int L, bool INV, int SRC, int DST>
+__device__ __forceinline__ void plane_stage(cplx* tile, cplx* gt, const cplx* __restrict__ tws) {
+  constexpr int NB = kRows / R;                 // butterflies per column
+  constexpr int RG = kPlaneThreads / kM;        // 4 row groups
+  const int c = threadIdx.x % kM, rg = threadIdx.x / kM;
+#pragma unroll
+  for (int i = 0; i < NB / RG; ++i) plane_bfly<R, L, INV, SRC, DST>(tile + c, gt + c, kM, tws, rg + i * RG);
+  if (threadIdx.x < NB) plane_bfly<R, L, INV, SRC, DST>(tile + kM, gt + kRows * kM, 1, tws, threadIdx.x);
+}
+
+// pass A.  grid = nz * r2 CTAs (one tile each), 512 threads, kPlaneSmem bytes of dynamic shared memory.
+template <int MODE, int EPI>
+static __global__ void __launch_bounds__(kPlaneThreads, 1) k_plane(PlaneArgs P) {
+  typedef Row2Cfg<kM> CF;
+  static_assert(CF::RS == kPitch, "the x transforms run in place on the tile rows");
+  LMVN_DYN_SMEM(cplx, tile);
+  __shared__ cplx s_tw[RowTwShared<kM>::ENTRIES * 16];
+  const int n2 = blockIdx.x % P.r2;
+  const int z = blockIdx.x / P.r2;
+  cplx* gt = P.a + (size_t(n2) * P.nz + z) * kTileElems;
+  RowArgs A = P.row;
+  A.spec = tile;
+  A.nxp = kPitch;
+  A.nyq = nullptr;  // X[nx/2] of tile row i lives at tile[i][128]
+  A.rr_base = (long long)z * P.ny + n2;
+  A.rr_skip = P.r2 - 1;
+  RowTwShared<kM>::fill(s_tw, A);
+  if (MODE != PM_BEGIN) {
+    // inverse along the tile rows: radix 8 (span 8) straight from HBM, radix 16 (span 128)
+    plane_stage<8, 8, true, W_GLOBAL, W_SMEM>(tile, gt, nullptr);
+    __syncthreads();
+    if (P.prefetch > 0) plane_prefetch<MODE, EPI>(P, blockIdx.x + unsigned(P.prefetch));
+    plane_stage<16, 128, true, W_SMEM, W_SMEM>(tile, gt, P.tw_y);
+  } else if (P.prefetch > 0) {
+    plane_prefetch<MODE, EPI>(P, blockIdx.x + unsigned(P.prefetch));
+  }
+  __syncthreads();
+  {
+    RowTwShared<kM> T;
+    const int lane = threadIdx.x % 16, group = threadIdx.x / 16;
+    T.base = s_tw + lane;
+    constexpr int GROUPS = kPlaneThreads / 16;
+#pragma unroll 1
+    for (int row0 = group * CF::RPG; row0 < kRows; row0 += GROUPS * CF::RPG) {
+      cplx* slab = tile + row0 * kPitch;
+      if (MODE == PM_BEGIN) rows_fwd_group<kM, false, RowTwShared<kM>, 1>(A, slab, row0, lane, T);
+      else rows_inv_group<kM, EPI, RowTwShared<kM>, MODE == PM_CHAIN, false, 1>(A, slab, row0, lane, T);
+    }
+  }
+  if (MODE == PM_END) return;
+  __syncthreads();
+  plane_stage<16, 128, false, W_SMEM, W_SMEM>(tile, gt, P.tw_y);
+  __syncthreads();
+  plane_stage<8, 8, false, W_SMEM, W_GLOBAL>(tile, gt, nullptr);
+}
+
+// ------------------------------------------------------------------------------
+// pass B: forward z, * K^, inverse z on tiles of NZ rows x COLS columns; a column = (n2, kx), COLS = R2 * KXC.
+// The radix-R2 level of y needs the R2 samples (n2 = 0 .. R2-1) of one (z, kx) in one thread, the z stages need NZ/R
+// rows of one column in one thread, so the level is its own register stage, in place on the shared tile (128-bit
+// accesses: two adjacent kx of R2 slots), between the first z stage and the spectrum product, and mirrored after it:
+//   global -> radix R1 (z) -> tile | twiddle w_ny^{n2 k1}, radix R2 (y) | radix R2z, * K^, radix R2z^-1 (z) |
+//   radix R2^-1 (y), conjugate twiddle | radix R1^-1 (z) -> global
+// Measured alternatives, config 3, five-pass z pass = 0.165 ms:
+//   * the level across lanes with shuffles right after the loads (8 SHFL per value): 0.367 ms
+//     (profiles/r02_x3_v1_shuffle_zmid_probe.json);
+//   * the level as the FIRST stage (128-bit global loads -> radix R2 -> tile, then a radix-32 z stage fed from shared
+//     memory): 0.393 ms -- that z stage keeps 64 data + 62 twiddle registers live and spills 340 bytes per thread
+//     (gpurun_out/r02_x3_probe_2.json -> profiles/r02_x3_v2_probe.json).
+// These kernels are bound by the load/store/shuffle pipe of the SM, not by HBM.
+// ------------------------------------------------------------------------------
+struct ZmidArgs {
+  cplx* a;
+  const cplx* khat;   // A layout
+  int nz, r2;
+  const cplx* tw1;    // stage tables of the z plan (fft_fast.cuh)
+  const cplx* tw2;
+  const cplx* tw_ny;  // w_ny^m, m < ny: the twiddles between the 128-point level and the radix-R2 level of y
+};
+
+// tile width of pass B: the strided passes' width, at most 32 columns
+template <int NZ> struct ZmidCols { static const int V = Cols<NZ>::V < 32 ? Cols<NZ>::V : 32; };
+// shared-memory row pitch: COLS + KXC complex.  The 128-bit accesses of the y level are served per quarter-warp (8 lanes =
+// 8 / PAIRS consecutive rows x PAIRS column pairs per slot n2); with this pitch consecutive rows start PAIRS * 16 bytes
+// apart (mod 128), so the eight 16-byte accesses of a quarter-warp fall into distinct banks.  (COLS + 2 looked fine on
+// paper for whole warps and cost 2-way conflicts on every access of the level: 8.7 M of 25.7 M shared wavefronts of the
+// pass, profiles/r02_ncu_x3_v3.md.)
+template <int NZ, int R2> struct ZmidPitch { static const int V = ZmidCols<NZ>::V + ZmidCols<NZ>::V / R2; };
+
+// the radix-R2 level of y, in place on the shared tile: item = (z, column pair), R2 values of 16 bytes each
+template <int NZ, int R2, bool INV>
+__device__ __forceinline__ void zmid_y_level(cplx* smem, const cplx* __restrict__ tw_ny) {
+  constexpr int COLS = ZmidCols<NZ>::V, PITCH = ZmidPitch<NZ, R2>::V;
+  constexpr int KXC = COLS / R2, PAIRS = KXC / 2;
+  constexpr int THREADS = Threads<NZ>::V;
+  constexpr int ITEMS = NZ * PAIRS;
+  static_assert(KXC >= 2 && KXC % 2 == 0, "128-bit accesses");
+  static_assert(ITEMS % THREADS == 0, "whole items per thread");
+  constexpr int IPT = ITEMS / THREADS;
+  const int pair = threadIdx.x % PAIRS;
+  // (recomputed here and not passed in: nothing of this stage stays live through the z stages, which have no register to spare)
+  const int p = blockIdx.x / (kM / KXC);
+  const int kx0 = (blockIdx.x % (kM / KXC)) * KXC;
+  // position along the 128-point level: the tile row, or (Nyquist row) the column; 16 x 8 decimation in frequency:
+  // position 8 q1 + q2 holds frequency k1 = q1 + 16 q2.  Twiddle between the levels: w_ny^{n2 k1}.
+  cplx w[2][R2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int pos = (p < kRows) ? p : (kx0 + 2 * pair + e);
+    const int k1 = (pos >> 3) + ((pos & 7) << 4);
+#pragma unroll
+    for (int n = 1; n < R2; ++n) w[e][n] = __ldg(tw_ny + n * k1);
+  }
+#pragma unroll(IPT >= 2 ? 2 : 1)
+  for (int i = 0; i < IPT; ++i) {
+    const int item = threadIdx.x + i * THREADS;
+    const int z = item / PAIRS;
+    float4* sp = reinterpret_cast<float4*>(smem + z * PITCH + 2 * pair);
+    cplx v0[R2], v1[R2];
+#pragma unroll
+    for (int n = 0; n < R2; ++n) {
+      const float4 f = sp[n * (KXC / 2)];
+      v0[n] = cmake(f.x, f.y);
+      v1[n] = cmake(f.z, f.w);
+    }
+    if (!INV) {
+#pragma unroll
+      for (int n = 1; n < R2; ++n) {
+        v0[n] = cmul(v0[n], w[0][n]);
+        v1[n] = cmul(v1[n], w[1][n]);
+      }
+    }
+    Bfly<R2, INV>::run(v0);
+    Bfly<R2, INV>::run(v1);
+    if (INV) {
+#pragma unroll
+      for (int n = 1; n < R2; ++n) {
+        v0[n] = cmulc(v0[n], w[0][n]);
+        v1[n] = cmulc(v1[n], w[1][n]);
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < R2; ++n) sp[n * (KXC / 2)] = make_float4(v0[n].x, v0[n].y, v1[n].x, v1[n].y);
+  }
+}
+
+template <int NZ, int R2>
+static __global__ void __launch_bounds__(Threads<NZ>::V, StridedBlocks<NZ, SM_FWD_MUL_INV>::V) k_zmid(ZmidArgs Z) {
+  typedef Radix<NZ> RX;
+  static_assert(RX::S == 2, "two-stage z plans only");
+  constexpr int COLS = ZmidCols<NZ>::V, PITCH = ZmidPitch<NZ, R2>::V;
+  constexpr int KXC = COLS / R2;     // adjacent kx columns per n2: pieces of KXC * 8 bytes
+  constexpr int R1 = RX::R1, RR2 = RX::R2;
+  constexpr int U = LMVN_ZMUL_UNROLL;
+  LMVN_DYN_SMEM(cplx, smem);  // [NZ][PITCH]
+  constexpr int CHUNKS = kM / KXC;
+  const int c = threadIdx.x % COLS;
+  cplx* sm = smem + c;
+  const int rs = kTileElems;  // between consecutive z
+  // this thread's column (n2, kx) of tile (p, kx chunk) -- recomputed where it is needed instead of kept in registers
+  auto column = [&]() -> long long {
+    const int p = blockIdx.x / CHUNKS, kx0 = (blockIdx.x % CHUNKS) * KXC;
+    return (long long)(c / KXC) * Z.nz * kTileElems + (long long)p * kM + kx0 + (c % KXC);
+  };
+  typedef Middle<NZ, RR2, COLS, PITCH> MID;
+  typename MID::K kk;
+  // the y level and the z stages commute (different axes; the twiddle between the y levels does not depend on z), so
+  // the level sits between the first z stage and the middle: every register stage keeps the footprint it has in the
+  // five-pass kernel (a radix-32 stage fed from shared memory instead of HBM spills at 128 registers)
+  strided_stage<NZ, R1, NZ, COLS, false, W_GLOBAL, W_SMEM, U, PITCH>(sm, Z.a + column(), rs, Z.tw1, 1.f);
+  __syncthreads();
+  zmid_y_level<NZ, R2, false>(smem, Z.tw_ny);
+  MID::load(kk, Z.khat + column(), rs);  // K^ straight from HBM, issued before the barrier that precedes its use
+  __syncthreads();
+  MID::run(sm, kk);
+  __syncthreads();
+  zmid_y_level<NZ, R2, true>(smem, Z.tw_ny);
+  __syncthreads();
+  strided_stage<NZ, R1, NZ, COLS, true, W_SMEM, W_GLOBAL, U, PITCH>(sm, Z.a + column(), rs, Z.tw1, 1.f);
+}
+
+// ------------------------------------------------------------------------------
+// K^ of the five-pass layout (main[z'][y'][kx] with nx/2 columns + Nyquist plane nyq[z'][y']) -> A layout.
+// y' of the five-pass y plan: two stages R1y x R2y, position R2y * (ky % R1y) + ky / R1y.
+// ------------------------------------------------------------------------------
+struct KhatPermArgs {
+  const cplx* main;
+  const cplx* nyq;
+  cplx* out;
+  int nz, ny, r2;
+  int y_r1, y_r2, y_r3;  // radices of the five-pass y plan (r3 = 1 for two-stage plans)
+};
+
+__device__ __forceinline__ int old_y_position(int ky, int r1, int r2, int r3) {
+  // decimation in frequency: the first-stage output index is the LOW digit of the frequency and the HIGH digit of the position
+  const int q1 = ky % r1, rest = ky / r1;
+  if (r3 == 1) return q1 * r2 + rest;
+  const int q2 = rest % r2, q3 = rest / r2;
+  return (q1 * r2 + q2) * r3 + q3;
+}
+
+static __global__ void k_khat_to_a(KhatPermArgs K) {
+  // one thread per output element
+  const size_t n = size_t(K.r2) * K.nz * kTileElems;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const int kx = int(i % kM);
+    const int p = int((i / kM) % (kRows + 1));
+    const size_t zn = i / kTileElems;
+    const int z = int(zn % K.nz);
+    const int n2 = int(zn / K.nz);
+    const int k2 = n2;  // slot n2 of pass B's y level holds ky = k1 + 128 n2
+    const int pos = (p < kRows) ? p : kx;
+    const int ky = ((pos >> 3) + ((pos & 7) << 4)) + kRows * k2;
+    const int yo = old_y_position(ky, K.y_r1, K.y_r2, K.y_r3);
+    const size_t row = size_t(z) * K.ny + yo;
+    K.out[i] = (p < kRows) ? K.main[row * kM + kx] : K.nyq[row];
+  }
+}
+
+}  // namespace x3
+}  // namespace lmvn

@@ -204,3 +204,24 @@ def test_embedded_chained_equals_unchained(L, monkeypatch):
         assert L.last_geometry() == pc.GEOMETRY_EMBEDDED
         outs[chain] = psi
     np.testing.assert_array_equal(outs["1"], outs["0"])
+
+
+# ---- two-pass schedule (csrc/fft_x3.cuh): plane-tile pass + z-middle pass with the cross-lane y level --------------
+@pytest.mark.parametrize("dims", [(64, 256, 256)])
+def test_two_pass_schedule_deconvolve(L, dims, monkeypatch):
+    """smallest shape the two-pass schedule takes (ny = 128 * 2): one view, two iterations = plane pass in its three
+    modes (begin, chained quotient / update links, end), the z-middle pass and the K^ permutation, against the
+    oracle; then the same call on the default five-pass schedule (LMVN_X3=0) must agree to round-off."""
+    from libmultiviewnative_b200.synthetic import make_views
+    from oracle import mvn_oracle as orc
+
+    d = make_views(dims, num_views=1, kernel_size=9, n_sources=40, workers=4)
+    exp = orc.inplace_cpu_deconvolve(d["psi0"], d["views"], d["kernels1"], d["kernels2"], d["weights"], 2, 0.006, 1e-4, nthreads=4)
+    monkeypatch.setenv("LMVN_X3", "1")  # opt-in schedule, read when a plan is created
+    psi = d["psi0"].copy()
+    L.inplace_gpu_deconvolve(psi, d["views"], d["kernels1"], d["kernels2"], d["weights"], 2, 0.006, 1e-4)
+    assert pc.max_rel(psi, exp) <= pc.PER_VOXEL_TOL_1_ITER
+    monkeypatch.setenv("LMVN_X3", "0")
+    old = d["psi0"].copy()
+    L.inplace_gpu_deconvolve(old, d["views"], d["kernels1"], d["kernels2"], d["weights"], 2, 0.006, 1e-4)
+    assert 0 < pc.max_rel(psi, old) < 5e-6  # different factorisations: close, not identical (identical = the knob did nothing)

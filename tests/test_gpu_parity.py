@@ -268,6 +268,37 @@ def test_deconvolve_256x256x1024_wide_rows(L):
         assert pc.rel_l2(psi, ck[iters]) <= pc.REL_L2_TOL_10_ITER
 
 
+# ---- the opt-in two-pass schedule (csrc/fft_x3.cuh, LMVN_X3=1) ---------------------------------------------------
+@pytest.mark.parametrize("dims,lam", [((128, 256, 256), 0.006), ((64, 512, 256), 0.0), ((256, 256, 256), 0.006)])
+def test_two_pass_schedule_vs_oracle(L, dims, lam, monkeypatch):
+    monkeypatch.setenv("LMVN_X3", "1")  # read when a plan is created
+    pc.case_deconvolve_vs_oracle(L, dims, 2, 31, lam, iters_list=(1, 10), n_sources=300)
+
+
+def test_two_pass_schedule_config3_full_size(L, monkeypatch):
+    """config 3 itself on the two-pass schedule against the default five-pass schedule (which the test above compares
+    with the oracle at this size): one and three iterations, and the single convolution entry point"""
+    d = _config3_inputs()
+    res = {}
+    for x3 in ("0", "1"):
+        monkeypatch.setenv("LMVN_X3", x3)
+        out = []
+        for iters in (1, 3):
+            psi = d["psi0"].copy()
+            L.inplace_gpu_deconvolve(psi, d["views"], d["kernels1"], d["kernels2"], d["weights"], iters, 0.006, 1e-4)
+            out.append(psi)
+        with L.plan((512, 512, 256), 1, 0) as p:
+            p.set_view(0, d["views"][0], d["weights"][0], d["kernels1"][0], d["kernels2"][0])
+            p.set_psi(d["views"][1])
+            p.convolve(0, 1, 1)
+            out.append(p.get_psi())
+            info = p.info()
+        res[x3] = out
+        assert int(info.launches_per_view_iteration) == (4 if x3 == "1" else 8)
+    for a, b in zip(res["1"], res["0"]):
+        assert 0 < pc.max_rel(a, b) < 2e-5
+
+
 # ---- the callers either side of the path (SURVEY §8f-2, f-3) through the CUDA entry point -------------------
 def test_tiler_through_the_gpu_entry_point(L):
     """block tiler with halo (ref: tests/tiff_fixtures.hpp:225-258): every block is one inplace_gpu_deconvolve
