@@ -49,10 +49,21 @@ def run_pipelined(lib, make_block: Callable[[int], dict], indices: Sequence[int]
     out: Dict[int, Optional[np.ndarray]] = {}
     if not getattr(lib, "reentrant", True):
         depth = 1
+    local = threading.local()  # keep=False: one psi buffer per worker thread, reused (a fresh 64 MiB array per block costs
+                               # ~16 ms of copying plus the page faults of first-touched memory inside the call)
 
     def work(b: int):
-        res = deconvolve_block(lib, make_block(b), num_iterations, lam, min_value, device)
-        return b, (res if keep else None)
+        block = make_block(b)
+        if keep:
+            return b, deconvolve_block(lib, block, num_iterations, lam, min_value, device)
+        psi0 = np.asarray(block["psi0"], dtype=np.float32)
+        buf = getattr(local, "psi", None)
+        if buf is None or buf.shape != psi0.shape:
+            buf = local.psi = np.empty_like(psi0)
+        np.copyto(buf, psi0)
+        lib.inplace_gpu_deconvolve(buf, block["views"], block["kernels1"], block["kernels2"], block["weights"],
+                                   num_iterations, lam, min_value, device)
+        return b, None
 
     with ThreadPoolExecutor(max_workers=max(1, int(depth))) as pool:
         for b, res in pool.map(work, list(indices)):

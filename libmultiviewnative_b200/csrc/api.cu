@@ -2,6 +2,7 @@
 // include/lmvn_b200.h (persistent handle + diagnostics).
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -362,9 +363,12 @@ extern "C" void inplace_gpu_convolution(imageType* im, int* imDim, imageType* ke
 // ---------------------------------------------------------------------------------
 extern "C" void convolution3DfftCUDAInPlace(imageType* im, int* imDim, imageType* kernel, int* kernelDim,
                                             int devCUDA) {
-  // Same circular convolution as inplace_gpu_convolution.  (The reference copies the
-  // unpitched image into the in-place cuFFT buffer, :225, which only preserves sums;
-  // its tests check sums only, tests/test_gpu_convolve.cpp:12-191.)
+  // Same circular convolution as inplace_gpu_convolution.  The reference's version is not reproducible bit for bit
+  // because it reads uninitialised device memory: it cudaMalloc's imSize + 2 d0 d1 floats (ref: src/multiviewnative.cu:
+  // 210-216), copies the imSize UNPITCHED image floats in (:225) and runs the in-place R2C, which reads rows at pitch
+  // d2 + 2 -- i.e. a sheared image whose last rows come from the never-written tail of the allocation.  Only sums are
+  // (approximately) preserved, and sums are all its tests check (ref: tests/test_gpu_convolve.cpp:12-191); those tests pass
+  // against this entry point (tests/parity_cases.py case_conv_fixture(entry="convolution3DfftCUDAInPlace")).
   (void)gpu_convolution_impl(im, imDim, kernel, kernelDim, devCUDA);
 }
 
@@ -404,10 +408,20 @@ extern "C" void iterate_fft_plain(imageType* _input, imageType* _kernel, imageTy
 }
 extern "C" void iterate_fft_tikhonov(imageType* _input, imageType* _kernel, imageType* _output, int* _input_dims,
                                      int* _kernel_dims, size_t, float _minValue, double _lambda, int _device) {
-  // The reference ignores _minValue/_lambda here and hard-codes 1e-4 / 0.2 with an
-  // older update rule (ref: src/multiviewnative.cu:582-583); this build honours the
-  // arguments and uses the regularised update of the main path.
-  (void)legacy_iterate_impl(_input, _kernel, _output, _input_dims, _kernel_dims, _minValue, _lambda, _device);
+  // Like the reference, this entry point IGNORES _minValue and _lambda: it hard-codes minValue = 1e-4 and lambda = 0.2
+  // (ref: src/multiviewnative.cu:582-583 `device_finalValues_tikhonov<<<...>>>(d_initial_, d_image_, d_weights_, .0001f,
+  // .2f, inputSize)`).  Its older update rule, new = w (max(min, v) - v) + v with v = (sqrt(1 + 2 lambda psi integral) - 1)
+  // / lambda (ref: inc/cuda_kernels.cuh:161-194), blends towards the VALUE instead of towards the last psi; with the
+  // weights of 1 this entry point hard-codes (:527) both rules give max(min, v), so the main path's update is exact here.
+  // (The reference additionally passes `&weights_[0]` / `&kernel2_[0]` of POINTERS to vectors (:548, :573), i.e. it
+  // uploads the vector objects' own bytes instead of their data -- undefined behaviour that is not reproduced; the
+  // intended values 1 and 0.1 are used.)  LMVN_LEGACY_HONOUR_ARGS=1 makes the entry point use its arguments instead.
+  (void)_minValue; (void)_lambda;
+  float min_value = 1e-4f;
+  double lambda = 0.2;
+  if (const char* e = getenv("LMVN_LEGACY_HONOUR_ARGS"))
+    if (*e == '1') { min_value = _minValue; lambda = _lambda; }
+  (void)legacy_iterate_impl(_input, _kernel, _output, _input_dims, _kernel_dims, min_value, lambda, _device);
 }
 
 // ---------------------------------------------------------------------------------

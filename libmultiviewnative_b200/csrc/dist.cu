@@ -48,6 +48,9 @@ namespace lmvn {
 namespace {
 
 const int kMaxRanks = 8;
+const int kMaxGroups = 8;                                  // column groups of the pipelined loop
+const int kChannels = 1 + 2 * kMaxGroups;                  // barrier channels: whole phase, per group x {y scatter, z scatter}
+const size_t kFlagBytes = sizeof(unsigned) * kChannels * kMaxRanks;
 
 int ilog2(int v) {
   int l = 0;
@@ -64,22 +67,24 @@ size_t align_up_(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // every rank.  timeout_ns comes from LMVN_BARRIER_TIMEOUT_S (default 600 s: ranks may legitimately be
 // seconds apart -- first-call graph instantiation, staging a pageable slab; ProcessSlabPlan.iterate
 // additionally lines the hosts up with a torch.distributed barrier before the launch).
+// channel: independent barrier sequences (own flags, own epoch) -- the pipelined loop runs one per column group and
+// exchange direction, on different streams.
 __global__ void k_peer_barrier(unsigned* const* peer_flags, unsigned* my_flags, int rank, int world, unsigned* epoch_counter,
-                               unsigned* err, unsigned long long timeout_ns) {
+                               unsigned* err, unsigned long long timeout_ns, int channel) {
 #ifndef LMVN_EMU
   // the epoch lives on the device (every rank launches the same sequence of barriers), so that a captured
   // launch sequence can be replayed as a CUDA graph
   __shared__ unsigned s_epoch;
-  if (threadIdx.x == 0) s_epoch = ++(*epoch_counter);
+  if (threadIdx.x == 0) s_epoch = ++epoch_counter[channel];
   __syncthreads();
   const unsigned epoch = s_epoch;
   const int t = threadIdx.x;
   if (t < world) {
     __threadfence_system();
-    volatile unsigned* dst = peer_flags[t] + rank;
+    volatile unsigned* dst = peer_flags[t] + channel * kMaxRanks + rank;
     *dst = epoch;
     __threadfence_system();
-    volatile unsigned* src = my_flags + t;
+    volatile unsigned* src = my_flags + channel * kMaxRanks + t;
     volatile unsigned* verr = err;
     unsigned long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -96,7 +101,7 @@ __global__ void k_peer_barrier(unsigned* const* peer_flags, unsigned* my_flags, 
     __threadfence_system();
   }
 #else
-  (void)peer_flags; (void)my_flags; (void)rank; (void)world; (void)epoch_counter; (void)err; (void)timeout_ns;
+  (void)peer_flags; (void)my_flags; (void)rank; (void)world; (void)epoch_counter; (void)err; (void)timeout_ns; (void)channel;
 #endif
 }
 
@@ -130,6 +135,16 @@ struct DistDeconv {
   bool use_graph = true;
   double graph_lambda = 0.0;
   float graph_min = 0.f;
+  // pipelined loop: the kx columns are cut into `groups` windows; the z pass of window g (and the y-inverse pass behind it)
+  // runs on its own streams while window g+1 is still being scattered, per-window barriers instead of whole-phase ones
+  // OPT-IN (LMVN_DIST_GROUPS > 1): measured on 8 x B200, 1024^3 (profiles/r02_slab_phase_timing_8gpu.log): 6.12 ms per
+  // (view, iteration) unpipelined, 6.23 with 2 windows, 6.39 with 4 -- the scatter kernels fill every CTA slot of the
+  // device while they wait on their peer stores (y scatter 1.1 ms, z scatter 1.2 ms for 470 MB out of each GPU = ~400 GB/s),
+  // so the passes of the other windows queue behind them instead of running beside them, and only 0.65 ms of the 3.2 ms
+  // of a convolution is local work that could hide.  The limiter is the rate of the scattered peer stores, not the order.
+  int groups = 1;
+  cudaStream_t s_z = nullptr, s_yi = nullptr;
+  cudaEvent_t ev_y[kMaxGroups] = {nullptr}, ev_z[kMaxGroups] = {nullptr}, ev_yi[kMaxGroups] = {nullptr}, ev_rows = nullptr;
   unsigned** d_peer_flags = nullptr;  // device array of kMaxRanks pointers
   unsigned* d_err = nullptr;
   bool barrier_failed = false;                         // a device-side barrier timed out; reset_barrier() clears it
@@ -181,6 +196,14 @@ struct DistDeconv {
 #endif
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    for (int g = 0; g < kMaxGroups; ++g) {
+      if (ev_y[g]) cudaEventDestroy(ev_y[g]);
+      if (ev_z[g]) cudaEventDestroy(ev_z[g]);
+      if (ev_yi[g]) cudaEventDestroy(ev_yi[g]);
+    }
+    if (ev_rows) cudaEventDestroy(ev_rows);
+    if (s_z) { cudaStreamSynchronize(s_z); cudaStreamDestroy(s_z); }
+    if (s_yi) { cudaStreamSynchronize(s_yi); cudaStreamDestroy(s_yi); }
     if (stream && own_stream) cudaStreamDestroy(stream);
     if (stage_send) cudaFree(stage_send);
     if (stage_recv) cudaFree(stage_recv);
@@ -232,7 +255,7 @@ struct DistDeconv {
     slab_off = 0;
     pencil_off = align_up_(slab_spec() * sizeof(cplx), 256);
     flags_off = pencil_off + align_up_(pencil_spec() * sizeof(cplx), 256);
-    xchg_bytes = flags_off + 256;
+    xchg_bytes = flags_off + kFlagBytes;
     size_t free_b = 0, total_b = 0;
     LMVN_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     if (arena_bytes + xchg_bytes > free_b) {
@@ -246,12 +269,12 @@ struct DistDeconv {
 #else
     LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&xchg), xchg_bytes));
 #endif
-    LMVN_CUDA_TRY(cudaMemset(xchg + flags_off, 0, 256));
+    LMVN_CUDA_TRY(cudaMemset(xchg + flags_off, 0, kFlagBytes));
     LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_peer_flags), sizeof(unsigned*) * kMaxRanks));
     LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_err), sizeof(unsigned)));
     LMVN_CUDA_TRY(cudaMemset(d_err, 0, sizeof(unsigned)));
-    LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_epoch), sizeof(unsigned)));
-    LMVN_CUDA_TRY(cudaMemset(d_epoch, 0, sizeof(unsigned)));
+    LMVN_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_epoch), sizeof(unsigned) * kChannels));
+    LMVN_CUDA_TRY(cudaMemset(d_epoch, 0, sizeof(unsigned) * kChannels));
     if (const char* e = getenv("LMVN_GRAPH")) use_graph = (*e != '0');
     if (const char* e = getenv("LMVN_BARRIER_TIMEOUT_S")) {
       const double sec = atof(e);
@@ -280,7 +303,30 @@ struct DistDeconv {
     LMVN_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     LMVN_CUDA_TRY(cudaEventCreate(&ev0));
     LMVN_CUDA_TRY(cudaEventCreate(&ev1));
+    LMVN_CUDA_TRY(cudaStreamCreateWithFlags(&s_z, cudaStreamNonBlocking));
+    LMVN_CUDA_TRY(cudaStreamCreateWithFlags(&s_yi, cudaStreamNonBlocking));
+    for (int g = 0; g < kMaxGroups; ++g) {
+      LMVN_CUDA_TRY(cudaEventCreateWithFlags(&ev_y[g], cudaEventDisableTiming));
+      LMVN_CUDA_TRY(cudaEventCreateWithFlags(&ev_z[g], cudaEventDisableTiming));
+      LMVN_CUDA_TRY(cudaEventCreateWithFlags(&ev_yi[g], cudaEventDisableTiming));
+    }
+    LMVN_CUDA_TRY(cudaEventCreateWithFlags(&ev_rows, cudaEventDisableTiming));
+    if (const char* e = getenv("LMVN_DIST_GROUPS")) groups = std::max(1, std::min(kMaxGroups, atoi(e)));
     return 0;
+  }
+
+  // column windows of the pipelined loop: tile aligned for both the y and the z passes, at most `groups` of them
+  int window_count() const {
+    const int tile = std::max(ops->strided_tile_cols(ny), ops->strided_tile_cols(nz));
+    const int tiles = (nx / 2 + 1 + tile - 1) / tile;
+    return std::max(1, std::min(groups, tiles));
+  }
+  void window(int g, int ng, int* col0, int* ncols) const {
+    const int tile = std::max(ops->strided_tile_cols(ny), ops->strided_tile_cols(nz));
+    const int tiles = (nx / 2 + 1 + tile - 1) / tile;
+    const int t0 = int((long long)tiles * g / ng), t1 = int((long long)tiles * (g + 1) / ng);
+    *col0 = t0 * tile;
+    *ncols = std::min((t1 - t0) * tile, nx / 2 + 1 - *col0);
   }
 
   int connected() const {
@@ -388,11 +434,11 @@ struct DistDeconv {
     return 0;
   }
 
-  int barrier() {
+  int barrier(int channel = 0, cudaStream_t s = nullptr) {
     if (!multi_process || world == 1) return 0;  // one process: stream order is the barrier
     LMVN_CUDA_TRY(cudaSetDevice(device));
-    LMVN_LAUNCH(k_peer_barrier, dim3(1), dim3(32), 0, stream, d_peer_flags, flags(rank), rank, world, d_epoch, d_err,
-                barrier_timeout_ns);
+    LMVN_LAUNCH(k_peer_barrier, dim3(1), dim3(32), 0, s ? s : stream, d_peer_flags, flags(rank), rank, world, d_epoch, d_err,
+                barrier_timeout_ns, channel);
     LMVN_CUDA_TRY(cudaGetLastError());
     return 0;
   }
@@ -403,8 +449,8 @@ struct DistDeconv {
     LMVN_CUDA_TRY(cudaSetDevice(device));
     LMVN_CUDA_TRY(cudaStreamSynchronize(stream));
     LMVN_CUDA_TRY(cudaMemset(d_err, 0, sizeof(unsigned)));
-    LMVN_CUDA_TRY(cudaMemset(d_epoch, 0, sizeof(unsigned)));
-    LMVN_CUDA_TRY(cudaMemset(xchg + flags_off, 0, 256));
+    LMVN_CUDA_TRY(cudaMemset(d_epoch, 0, sizeof(unsigned) * kChannels));
+    LMVN_CUDA_TRY(cudaMemset(xchg + flags_off, 0, kFlagBytes));
     LMVN_CUDA_TRY(cudaDeviceSynchronize());
     barrier_failed = false;
     return 0;
@@ -452,15 +498,53 @@ struct DistDeconv {
     if (ops->can_chain_rows() && !staged && iterations > 0) {
       // chained loop (see Deconv::iterate): the x-inverse pass also runs the x-forward pass of the next
       // convolution, in place on the slab's spectrum rows
+      const int ng = window_count();
+      // Pipelined exchange (ng > 1).  Per convolution, on three streams:
+      //   stream  (link)   y forward + scatter of window 0, 1, .. back to back; joins; chained rows pass
+      //   s_z     (link)   per window: wait for its scatter, barrier [all ranks scattered it], z fwd * K^ * z inv + scatter
+      //                    back, barrier [all ranks scattered it back]
+      //   s_yi    (local)  per window: y inverse
+      // so the z pass of window g (HBM bound: data + K^) and the y-inverse pass of window g-1 (local) run while window
+      // g+1 is still crossing NVLink, instead of scatter | barrier | z pass | barrier | y inverse with the links idle
+      // during every local phase.  Same kernels on the same data: bit-identical to the unpipelined loop.
+      auto pipelined_conv = [&](int v, int which) -> int {
+        const cplx* kh = (which == 1) ? khat1[v] : khat2[v];
+        for (int g = 0; g < ng; ++g) {
+          int c0, nc;
+          window(g, ng, &c0, &nc);
+          StridedGeom yg = y_geom(fast::SM_FWD_SCATTER);
+          yg.col0 = c0; yg.ncols = nc;
+          LMVN_TRY(ops->strided_geom(yg, stream));
+          LMVN_CUDA_TRY(cudaEventRecord(ev_y[g], stream));
+          LMVN_CUDA_TRY(cudaStreamWaitEvent(s_z, ev_y[g], 0));
+          LMVN_TRY(barrier(1 + g, s_z));
+          StridedGeom zg = z_geom(fast::SM_FWD_MUL_INV_SCATTER, kh, 1.f);
+          zg.col0 = c0; zg.ncols = nc;
+          LMVN_TRY(ops->strided_geom(zg, s_z));
+          LMVN_TRY(barrier(1 + kMaxGroups + g, s_z));
+          LMVN_CUDA_TRY(cudaEventRecord(ev_z[g], s_z));
+          LMVN_CUDA_TRY(cudaStreamWaitEvent(s_yi, ev_z[g], 0));
+          StridedGeom ig = y_geom(fast::SM_INV);
+          ig.col0 = c0; ig.ncols = nc;
+          LMVN_TRY(ops->strided_geom(ig, s_yi));
+          LMVN_CUDA_TRY(cudaEventRecord(ev_yi[g], s_yi));
+        }
+        for (int g = 0; g < ng; ++g) LMVN_CUDA_TRY(cudaStreamWaitEvent(stream, ev_yi[g], 0));
+        return 0;
+      };
       auto sweep = [&](bool ends_call) -> int {  // one iteration = one sweep over all views
         for (int v = 0; v < num_views; ++v)
           for (int which = 1; which <= 2; ++which) {
             const bool last = (ends_call && v == num_views - 1 && which == 2);
+            if (ng > 1 && multi_process) {
+              LMVN_TRY(pipelined_conv(v, which));
+            } else {
             LMVN_TRY(ops->strided_geom(y_geom(fast::SM_FWD_SCATTER), stream));
             LMVN_TRY(barrier());
             LMVN_TRY(conv_phase(v, which, 1, up));
             LMVN_TRY(barrier());
             LMVN_TRY(ops->strided_geom(y_geom(fast::SM_INV), stream));
+            }
             gen::Epilogue e = (which == 1) ? gen::Epilogue{gen::EPI_QUOTIENT, 1.f, image[v], nullptr, nullptr, up}
                                            : gen::Epilogue{gen::EPI_UPDATE, 1.f, nullptr, psi, weights[v], up};
             if (last) LMVN_TRY(ops->rows_inv_planes(slab_work(rank), psi, e, nz_l, stream));

@@ -545,7 +545,10 @@ struct HostStager {
     const long long pieces = (long long)((bytes + piece - 1) / piece);
     int threads = 1;
 #ifdef _OPENMP
-    threads = std::max(1, std::min(8, omp_get_max_threads()));
+    // the machine's cores, not omp_get_max_threads(): launchers such as torchrun export OMP_NUM_THREADS=1, and a
+    // single-threaded copy into the pinned ring runs at a quarter of the PCIe rate
+    threads = std::max(1, std::min(8, omp_get_num_procs()));
+    if (const char* e = getenv("LMVN_STAGING_THREADS")) threads = std::max(1, atoi(e));
 #endif
 #pragma omp parallel for num_threads(threads) schedule(static)
     for (long long i = 0; i < pieces; ++i) {

@@ -105,6 +105,10 @@ struct StridedGeom {
   Scatter sc{};                // SM_*_SCATTER
   cplx* nyq = nullptr;         // split layout: Nyquist plane of `data` (nullptr: the column is inside the rows)
   const cplx* nyq_khat = nullptr;
+  // column window (whole-row layouts only): the pass covers kx columns [col0, col0 + ncols) -- col0 a multiple of the
+  // tile width.  ncols = 0: all columns.  The slab-decomposed plans pipeline their exchanges over such windows.
+  int col0 = 0, ncols = 0;
+  bool khat_half = false;      // merged z pass: khat / nyq_khat hold __half2 elements + un-scale factor (opt-in)
 };
 struct FastOps {
   virtual ~FastOps() {}
@@ -114,6 +118,7 @@ struct FastOps {
                               cudaStream_t s) = 0;
   virtual int rows_inv_planes(const cplx* spec, float* out, const gen::Epilogue& ep, int nz_local, cudaStream_t s) = 0;
   virtual int strided_geom(const StridedGeom& g, cudaStream_t s) = 0;
+  virtual int strided_tile_cols(int n) const = 0;  // tile width (kx columns) of the strided passes along an axis of length n
   // chained x passes (x inverse + pointwise + x forward in place on nz_local planes of `spec`); false: not available
   virtual bool can_chain_rows() const = 0;
   virtual int rows_inv_fwd_planes(cplx* spec, const gen::Epilogue& ep, int nz_local, cudaStream_t s) = 0;

@@ -25,6 +25,9 @@
 #include "fft_types.cuh"
 #include "lmvn_common.cuh"
 #include "pointwise.cuh"
+#ifndef LMVN_EMU
+#include <cuda_fp16.h>
+#endif
 
 namespace lmvn {
 namespace fast {
@@ -206,6 +209,9 @@ struct StridedArgs {
   float scale;            // SM_FWD_SCALE
   int prefetch;           // > 0: every CTA first pulls the tile of block (id + prefetch) into L2
   int prefetch_khat;      // SM_FWD_MUL_INV: pull the CTA's own K^ tile into L2 at kernel entry
+  // opt-in half-precision PSF spectra (KH = 1 kernels): khat / nyq_khat point at __half2 elements (same indexing),
+  // stored as K^ * (1 / *khat_unscale); the product uses K^ = half value * *khat_unscale
+  const float* khat_unscale;
   Scatter sc;             // SM_*_SCATTER
   // Split layout (single-device engine): the half spectrum is stored as nx/2 columns per row -- a whole number of
   // tiles, rows of whole 128-byte lines, no pitch padding -- plus the Nyquist column kx = nx/2 as a compact plane
@@ -365,15 +371,30 @@ __device__ __forceinline__ void strided_stage(cplx* __restrict__ sm, cplx* __res
 // middle of the merged z pass: last forward stage (span R), spectrum product, first inverse stage.
 // The K^ operands come straight from HBM; middle_load() is called BEFORE the barrier that precedes
 // the middle so that their latency overlaps the barrier wait and the shared-memory reads.
-template <int N, int R, int COLS, int PITCH = COLS>
+template <int N, int R, int COLS, int PITCH = COLS, int KH = 0>
 struct Middle {
   static const int RG = Threads<N>::V / COLS;
   static const int PT = (N / R) / RG;  // butterflies per thread: 1 or 2 in every plan that is used
   struct K { cplx k[PT][R]; };
-  static __device__ __forceinline__ void load(K& o, const cplx* __restrict__ gk, int rs) {
+  // KH = 1: gk points at __half2 elements (4 bytes per complex value): half the K^ bytes of the pass
+  static __device__ __forceinline__ void load(K& o, const cplx* __restrict__ gk, int rs, float unscale = 1.f) {
     const int rg = threadIdx.x / COLS;
 #pragma unroll
     for (int i = 0; i < PT; ++i) {
+#if !defined(LMVN_EMU)
+      if (KH) {
+        const __half2* hp = reinterpret_cast<const __half2*>(gk) + (long long)((rg + i * RG) * R) * rs;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const unsigned raw = __ldcg(reinterpret_cast<const unsigned*>(hp));
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&raw));
+          o.k[i][r] = cmake(f.x * unscale, f.y * unscale);
+          hp += rs;
+          LMVN_KEEP_PTR(hp);
+        }
+        continue;
+      }
+#endif
       const cplx* gp = gk + (long long)((rg + i * RG) * R) * rs;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -404,7 +425,7 @@ struct Middle {
 // One tile of a strided pass.  `sm`, `g`, `gk` already point at this thread's column; threads of
 // the padding columns of a ragged last tile pass live = false: they skip the stages (every stage
 // touches the thread's own column only) but still take part in the barriers.
-template <int N, int MODE_, int U, int ALT = 0>
+template <int N, int MODE_, int U, int ALT = 0, int KH = 0>
 __device__ __forceinline__ void strided_tile(const StridedArgs& A, cplx* sm, cplx* g, const cplx* gk, bool live,
                                              long long sc_tile, int rs) {
   typedef Plan<N, ALT> RX;
@@ -439,19 +460,19 @@ __device__ __forceinline__ void strided_tile(const StridedArgs& A, cplx* sm, cpl
   } else {  // SM_FWD_MUL_INV
     if (live) strided_stage<N, R1, N, COLS, false, W_GLOBAL, W_SMEM, U>(sm, g, rs, A.tw1, 1.f);
     if (RX::S == 3) {
-      typedef Middle<N, R3, COLS> MID;
+      typedef Middle<N, R3, COLS, COLS, KH> MID;
       typename MID::K kk;
       __syncthreads();
       if (live) strided_stage<N, R2, L2, COLS, false, W_SMEM, W_SMEM, U>(sm, g, rs, A.tw2, 1.f);
-      if (live) MID::load(kk, gk, rs);
+      if (live) MID::load(kk, gk, rs, KH ? __ldg(A.khat_unscale) : 1.f);
       __syncthreads();
       if (live) MID::run(sm, kk);
       __syncthreads();
       if (live) strided_stage<N, R2, L2, COLS, true, W_SMEM, W_SMEM, U>(sm, g, rs, A.tw2, 1.f);
     } else {
-      typedef Middle<N, R2, COLS> MID;
+      typedef Middle<N, R2, COLS, COLS, KH> MID;
       typename MID::K kk;
-      if (live) MID::load(kk, gk, rs);
+      if (live) MID::load(kk, gk, rs, KH ? __ldg(A.khat_unscale) : 1.f);
       __syncthreads();
       if (live) MID::run(sm, kk);
     }
@@ -460,9 +481,10 @@ __device__ __forceinline__ void strided_tile(const StridedArgs& A, cplx* sm, cpl
   }
 }
 
-template <int N, int MODE, int ALT = 0>
+template <int N, int MODE, int ALT = 0, int KH = 0>
 static __global__ void __launch_bounds__(Threads<N>::V, StridedBlocks<N, MODE>::V * (kStridedThreads / Threads<N>::V))
     k_strided(StridedArgs A) {
+  static_assert(KH == 0 || MODE == SM_FWD_MUL_INV, "half-precision K^ is an option of the merged z pass");
   static_assert(ALT == 0 || (MODE != SM_FWD_MUL_INV && MODE != SM_FWD_MUL_INV_SCATTER), "the merged pass keeps the default plan");
   constexpr int COLS = Cols<N>::V;
   LMVN_DYN_SMEM(cplx, smem);  // [N][COLS]
@@ -478,7 +500,9 @@ static __global__ void __launch_bounds__(Threads<N>::V, StridedBlocks<N, MODE>::
       // Nyquist plane: this thread's column is slow index s (the plane is small and L2 resident)
       const unsigned s = blockIdx.x * COLS + c;
       const long long nb = (long long)s * A.nyq_cs;
-      strided_tile<N, MODE, U, ALT>(A, smem + c, A.nyq + nb, A.nyq_khat + nb, s < A.slow, 0, A.nyq_rs);
+      // (KH: the K^ pointers count __half2 elements -- same element offsets, half the bytes)
+      const cplx* nk = KH ? reinterpret_cast<const cplx*>(reinterpret_cast<const unsigned*>(A.nyq_khat) + nb) : A.nyq_khat + nb;
+      strided_tile<N, MODE, U, ALT, KH>(A, smem + c, A.nyq + nb, nk, s < A.slow, 0, A.nyq_rs);
       return;
     }
     tiles_x = unsigned(A.tiles_x);
@@ -507,8 +531,36 @@ static __global__ void __launch_bounds__(Threads<N>::V, StridedBlocks<N, MODE>::
     }
   }
   const long long sc_tile = A.sc.offset + (long long)by * A.sc.tile_stride + col;
-  strided_tile<N, MODE, U, ALT>(A, smem + c, A.data + base, A.khat + base, col < A.ncols, sc_tile, A.row_stride);
+  const cplx* gk = KH ? reinterpret_cast<const cplx*>(reinterpret_cast<const unsigned*>(A.khat) + base) : A.khat + base;
+  strided_tile<N, MODE, U, ALT, KH>(A, smem + c, A.data + base, gk, col < A.ncols, sc_tile, A.row_stride);
 }
+
+// ------------------------------------------------------------------------------
+// opt-in half-precision PSF spectra: K^ (float2) -> __half2 scaled by 1 / max |component|
+// ------------------------------------------------------------------------------
+#ifndef LMVN_EMU
+static __global__ void k_khat_absmax(const cplx* __restrict__ k, size_t n, unsigned* out_bits) {
+  float m = 0.f;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const cplx v = k[i];
+    m = fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));  // non-negative floats order like their bits
+}
+// dst[i] = half2(src[i] / max); *unscale = max (stored behind the half data, read by the z pass)
+static __global__ void k_khat_to_half(const cplx* __restrict__ src, size_t n, const unsigned* max_bits, __half2* dst,
+                                      float* unscale) {
+  const float mx = fmaxf(__uint_as_float(*max_bits), 1e-38f);
+  const float inv = 1.f / mx;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *unscale = mx;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const cplx v = src[i];
+    dst[i] = __floats2half2_rn(v.x * inv, v.y * inv);
+  }
+}
+#endif
 
 // ------------------------------------------------------------------------------
 // x passes: one real row of nx = 2M samples <-> M+1 complex bins; every global access

@@ -76,6 +76,10 @@ struct FastEngine : ConvEngine, FastOps {
   cplx* d_tw_nx = nullptr;
   cplx* d_tw_h = nullptr;
   bool y_alt = false;
+  // opt-in (LMVN_KHAT_FP16=1, single-device five-pass engine only; OUTSIDE the parity gate): the PSF spectra are stored as
+  // __half2 scaled by 1 / max|component| -- the merged z pass then reads 2.5 C instead of 3 C.  Layout of a K^ buffer:
+  // khat_elems() half2 values (same indexing as the float layout), then one float: the un-scale factor.
+  bool khat_half = false;
   cplx* d_tw_y[2] = {nullptr, nullptr};  // per-stage tables of the y / z passes
   cplx* d_tw_z[2] = {nullptr, nullptr};
 
@@ -358,7 +362,23 @@ struct FastEngine : ConvEngine, FastOps {
     return 0;
   }
   template <int N>
+  int launch_strided_khalf(const fast::StridedArgs& a, dim3 grid, cudaStream_t s) {
+#ifndef LMVN_EMU
+    constexpr int COLS = fast::Cols<N>::V;
+    const size_t smem = size_t(N) * COLS * sizeof(cplx);
+    auto kfn = fast::k_strided<N, fast::SM_FWD_MUL_INV, 0, 1>;
+    if (smem > 48 * 1024) LMVN_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    LMVN_LAUNCH(kfn, grid, dim3(fast::Threads<N>::V), smem, s, a);
+    return 0;
+#else
+    (void)a; (void)grid; (void)s;
+    set_last_error("half-precision PSF spectra are not available in the emulated build");
+    return -1;
+#endif
+  }
+  template <int N>
   int launch_strided_mode(const fast::StridedArgs& a, int mode, dim3 grid, cudaStream_t s) {
+    if (a.khat_unscale && mode == fast::SM_FWD_MUL_INV) return launch_strided_khalf<N>(a, grid, s);
     switch (mode) {
       case fast::SM_FWD: return launch_strided<N, fast::SM_FWD>(a, grid, s);
       case fast::SM_INV: return launch_strided<N, fast::SM_INV>(a, grid, s);
@@ -396,7 +416,10 @@ struct FastEngine : ConvEngine, FastOps {
     if (split) {
       g.nyq = nyq_of(data) + ((axis == 1 && nzs >= 0) ? size_t(z0) * p.ny : 0);
       g.nyq_khat = khat ? nyq_of(khat) : nullptr;
+      if (khat && khat_half && mode == fast::SM_FWD_MUL_INV)  // half2 elements: same element offset, half the bytes
+        g.nyq_khat = reinterpret_cast<const cplx*>(reinterpret_cast<const unsigned*>(khat) + main_elems());
     }
+    g.khat_half = khat && khat_half && mode == fast::SM_FWD_MUL_INV;
     if (axis == 1 && nzs >= 0) data += size_t(z0) * p.ny * nxp;  // y pass on a slab of planes
     g.data = data;
     g.khat = khat;
@@ -411,16 +434,38 @@ struct FastEngine : ConvEngine, FastOps {
     return strided_geom(g, s);
   }
 
+  int strided_tile_cols(int n) const override {
+    switch (n) {
+      case 1024: return fast::Cols<1024>::V;
+      case 512: return fast::Cols<512>::V;
+      case 256: return fast::Cols<256>::V;
+      case 128: return fast::Cols<128>::V;
+      default: return fast::Cols<64>::V;
+    }
+  }
+
   int strided_geom(const StridedGeom& g, cudaStream_t s) override {
     fast::StridedArgs a;
     std::memset(&a, 0, sizeof(a));
     a.data = g.data;
     a.khat = g.khat;
     a.ncols = g.nyq ? M : nxc;
+    int win_cols = nxc;  // columns the grid covers
+    if (g.ncols > 0) {
+      if (g.nyq || g.col0 % strided_tile_cols(g.n) != 0 || g.col0 < 0 || g.col0 >= nxc) {
+        set_last_error("strided pass: invalid column window");
+        return -1;
+      }
+      win_cols = std::min(g.ncols, nxc - g.col0);
+      a.data = g.data + g.col0;
+      if (g.khat) a.khat = g.khat + g.col0;
+      a.ncols = win_cols;
+    }
     a.scale = g.scale;
     a.row_stride = g.row_stride;
     a.tile_stride = g.tile_stride;
     a.sc = g.sc;
+    if (g.ncols > 0) a.sc.offset += g.col0;
     a.nyq_groups = -1;
     a.slow = g.slow;
     if (g.nyq) {
@@ -436,6 +481,10 @@ struct FastEngine : ConvEngine, FastOps {
                  : (g.tw_axis == 1 && mode == fast::SM_INV) ? y_inv_prefetch
                  : (mode == fast::SM_FWD_MUL_INV) ? z_prefetch : 0;
     a.prefetch_khat = khat_prefetch;
+    if (g.khat_half) {
+      a.khat_unscale = reinterpret_cast<const float*>(reinterpret_cast<const unsigned*>(g.khat) + khat_elems());
+      a.prefetch_khat = 0;
+    }
     if (g.tw_axis == 1) { a.tw1 = d_tw_y[0]; a.tw2 = d_tw_y[1]; }
     else { a.tw1 = d_tw_z[0]; a.tw2 = d_tw_z[1]; }
     if (g.n != (g.tw_axis == 1 ? plan->ny : plan->nz)) {
@@ -446,7 +495,7 @@ struct FastEngine : ConvEngine, FastOps {
     int rc;
 #define LMVN_STRIDED_CASE(NN)                                                                   \
   case NN: {                                                                                    \
-    dim3 grid(unsigned(ceil_div(size_t(nxc), size_t(fast::Cols<NN>::V))), slow);                \
+    dim3 grid(unsigned(ceil_div(size_t(win_cols), size_t(fast::Cols<NN>::V))), slow);           \
     if (g.nyq) {                                                                                \
       a.tiles_x = int(ceil_div(size_t(M), size_t(fast::Cols<NN>::V)));                          \
       a.nyq_groups = int(ceil_div(size_t(slow), size_t(fast::Cols<NN>::V)));                    \
@@ -565,12 +614,26 @@ struct FastEngine : ConvEngine, FastOps {
     return rows_inv_fwd(in, ep, s, -1, out, logical, offset, psi_out);
   }
 
-  int kernel_spectrum(const float* d_kernel, const int kd[3], cplx* khat, cplx*, cudaStream_t s) override {
+  int kernel_spectrum(const float* d_kernel, const int kd[3], cplx* khat, cplx* work, cudaStream_t s) override {
     gen::RealSource src{d_kernel, 1, kd[0], kd[1], kd[2]};
-    LMVN_TRY(rows_fwd(src, khat, s));
-    LMVN_TRY(strided(khat, nullptr, 1, fast::SM_FWD, 1.f, s));
+    cplx* dst = khat_half ? work : khat;
+    if (!dst) { set_last_error("kernel spectrum: work buffer missing"); return -1; }
+    LMVN_TRY(rows_fwd(src, dst, s));
+    LMVN_TRY(strided(dst, nullptr, 1, fast::SM_FWD, 1.f, s));
     const float inv_n = float(1.0 / double(plan->voxels()));  // decision q10: 1/N folded into K^
-    LMVN_TRY(strided(khat, nullptr, 0, fast::SM_FWD_SCALE, inv_n, s));
+    LMVN_TRY(strided(dst, nullptr, 0, fast::SM_FWD_SCALE, inv_n, s));
+#ifndef LMVN_EMU
+    if (khat_half) {
+      // float2 -> half2 scaled by 1 / max|component| (K^ carries the 1/N factor: far below the half range unscaled)
+      unsigned* max_bits = reinterpret_cast<unsigned*>(khat) + khat_elems() + 1;  // scratch word behind the un-scale factor
+      float* unscale = reinterpret_cast<float*>(reinterpret_cast<unsigned*>(khat) + khat_elems());
+      LMVN_CUDA_TRY(cudaMemsetAsync(max_bits, 0, sizeof(unsigned), s));
+      LMVN_LAUNCH(fast::k_khat_absmax, dim3(unsigned(num_sms * 8)), dim3(256), 0, s, work, khat_elems(), max_bits);
+      LMVN_LAUNCH(fast::k_khat_to_half, dim3(unsigned(num_sms * 8)), dim3(256), 0, s, work, khat_elems(), max_bits,
+                  reinterpret_cast<__half2*>(khat), unscale);
+      LMVN_CUDA_TRY(cudaGetLastError());
+    }
+#endif
     return 0;
   }
 
@@ -602,6 +665,7 @@ struct X3Engine : FastEngine {
 
   int x3_prefetch = 0;  // CTAs of look-ahead of the plane pass' L2 prefetch (A/B knob LMVN_X3_PREFETCH)
   int init_x3() {
+    khat_half = false;
     r2 = plan->ny / x3::kRows;
     x3_prefetch = 0;  // measured: -3 % (quotient) / -11 % (update) with a look-ahead of one CTA per SM (profiles/r02_x3_v2_probe*.json)
     if (const char* e = getenv("LMVN_X3_PREFETCH")) x3_prefetch = std::max(0, atoi(e));
@@ -768,6 +832,9 @@ std::unique_ptr<ConvEngine> make_fused_engine(std::shared_ptr<FftPlan> plan) {
   std::unique_ptr<FastEngine> e(new FastEngine());
   e->plan = plan;
   if (e->init() != 0) return nullptr;
+#ifndef LMVN_EMU
+  if (const char* h = getenv("LMVN_KHAT_FP16")) e->khat_half = (*h == '1');
+#endif
   return std::unique_ptr<ConvEngine>(e.release());
 }
 

@@ -209,9 +209,14 @@ def case_legacy_iterate(L):
     k2 = np.full(k1.shape, 0.1, F32)
     exp = orc.inplace_cpu_deconvolve(inp, [inp], [k1], [k2], [np.ones_like(inp)], 1, 0.0, 1e-4)
     assert max_rel(out, exp) <= 1e-4
-    out = L.iterate_fft_tikhonov(inp, k1, 1e-4, 0.006)
-    exp = orc.inplace_cpu_deconvolve(inp, [inp], [k1], [k2], [np.ones_like(inp)], 1, 0.006, 1e-4)
+    # like the reference, iterate_fft_tikhonov ignores its minValue / lambda arguments and uses 1e-4 / 0.2
+    # (ref: src/multiviewnative.cu:582-583); with the hard-coded unit weights its older update rule equals the main one
+    out = L.iterate_fft_tikhonov(inp, k1, 0.5, 0.006)
+    exp = orc.inplace_cpu_deconvolve(inp, [inp], [k1], [k2], [np.ones_like(inp)], 1, 0.2, 1e-4)
     assert max_rel(out, exp) <= 1e-4
+    t = inp.astype(np.float64) * orc.inplace_cpu_convolution(orc.compute_quotient(inp, orc.inplace_cpu_convolution(inp, k1)), k2)
+    old_rule = np.maximum((np.sqrt(1.0 + 2.0 * 0.2 * t) - 1.0) / 0.2, 1e-4)  # ref: inc/cuda_kernels.cuh:161-194 with w = 1
+    assert max_rel(out, old_rule) <= 1e-4
     im = inp.copy()
     L.convolution3DfftCUDAInPlace(im, k1)
     assert rel_l2(im, orc.inplace_cpu_convolution(inp, k1)) <= 1e-5

@@ -299,6 +299,32 @@ def test_two_pass_schedule_config3_full_size(L, monkeypatch):
         assert 0 < pc.max_rel(a, b) < 2e-5
 
 
+# ---- opt-in half-precision PSF spectra (LMVN_KHAT_FP16=1; SURVEY §8f-4, outside the parity gate) -------------------
+def test_half_precision_psf_spectra_opt_in(L, monkeypatch):
+    """K^ stored as __half2 scaled to its largest component: the merged z pass reads 2.5 C instead of 3 C.  Not within
+    the 1e-4 parity tolerance by construction (11-bit mantissas) -- the test bounds and prints the error against the
+    float32 spectra and checks that the default is untouched."""
+    from libmultiviewnative_b200.synthetic import make_views
+
+    dims = (128, 128, 128)
+    d = make_views(dims, num_views=3, kernel_size=31, n_sources=200, workers=4)
+    res = {}
+    for half in ("0", "1"):
+        monkeypatch.setenv("LMVN_KHAT_FP16", half)
+        out = []
+        for iters in (1, 10):
+            psi = d["psi0"].copy()
+            L.inplace_gpu_deconvolve(psi, d["views"], d["kernels1"], d["kernels2"], d["weights"], iters, 0.006, 1e-4)
+            out.append(psi)
+        res[half] = out
+    e1 = (pc.max_rel(res["1"][0], res["0"][0]), pc.rel_l2(res["1"][0], res["0"][0]))
+    e10 = (pc.max_rel(res["1"][1], res["0"][1]), pc.rel_l2(res["1"][1], res["0"][1]))
+    print("fp16 K^ vs f32 K^: 1 iteration (max rel, rel L2) = %s, 10 iterations = %s" % (e1, e10))
+    assert 0 < e1[1] < 1e-3 and e10[1] < 5e-3
+    monkeypatch.setenv("LMVN_KHAT_FP16", "0")
+    pc.case_deconvolve_vs_oracle(L, dims, 3, 31, 0.006, iters_list=(1,), n_sources=200)
+
+
 # ---- the callers either side of the path (SURVEY §8f-2, f-3) through the CUDA entry point -------------------
 def test_tiler_through_the_gpu_entry_point(L):
     """block tiler with halo (ref: tests/tiff_fixtures.hpp:225-258): every block is one inplace_gpu_deconvolve

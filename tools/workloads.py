@@ -230,11 +230,27 @@ def blocks_record(lib, torch, dist, rank, world, device, barrier, max_over_ranks
 
     timed([0, 1])  # warm-up: plan store, arenas, staging ring
     barrier()
-    one_gpu = one_gpu_seq = None
+    one_gpu = one_gpu_seq = one_gpu_pinned = None
     if rank == 0:
         per = nvox * views * iterations * n1_blocks / 1e9
         one_gpu = per / timed(list(range(n1_blocks)))
         one_gpu_seq = per / timed(list(range(n1_blocks)), 1)  # the same blocks, one call at a time (no overlap)
+        # the same blocks from page-locked buffers (a caller that can allocate its stacks with cudaHostAlloc)
+        keep, pinned = [], []
+        for b in distinct:
+            q = dict(b)
+            for key in ("views", "weights"):
+                q[key] = []
+                for a in b[key]:
+                    t, arr = _pin(torch, a)
+                    keep.append(t)
+                    q[key].append(arr)
+            pinned.append(q)
+        t0 = time.perf_counter()
+        run_pipelined(lib, lambda b: pinned[b % len(pinned)], list(range(n1_blocks)), iterations, 0.006, 1e-4, device,
+                      depth=depth, keep=False)
+        one_gpu_pinned = per / (time.perf_counter() - t0)
+        del keep, pinned
     barrier()
     mine = shard(n_blocks, rank, world)
     t0 = time.perf_counter()
@@ -248,7 +264,8 @@ def blocks_record(lib, torch, dist, rank, world, device, barrier, max_over_ranks
                         "inplace_gpu_deconvolve with pageable host buffers, block b on GPU b mod G, %d calls in flight per GPU, "
                         "no collective" % (n_blocks, dims[0], dims[1], dims[2], views, kernel, iterations, depth),
             "value": value, "unit": "Gvoxel*view*iter/s", "scaling": "strong", "n_gpus": world, "wall_s": wall,
-            "one_gpu_same_build": {"value": one_gpu, "blocks": n1_blocks, "one_call_at_a_time": one_gpu_seq},
+            "one_gpu_same_build": {"value": one_gpu, "blocks": n1_blocks, "one_call_at_a_time": one_gpu_seq,
+                                   "pinned_host_buffers": one_gpu_pinned},
             "speedup_vs_one_gpu": value / one_gpu,
             "h2d_bytes_per_block": int((2 * views + 1) * nvox * 4), "d2h_bytes_per_block": int(nvox * 4)}
 
