@@ -16,9 +16,17 @@ namespace lmvn {
 
 // view / blurred: view * (1 / blurred) like the reference (ref: inc/cpu_kernels.h:19-26, which rounds a
 // double reciprocal to float).
+// Host emulation of the device's MUFU arithmetic (tests/emu): flush-to-zero on inputs and results like the .ftz forms
+// below, so that the emulated parity cases exercise the SAME special-value behaviour as the device (a subnormal blurred
+// value gives an infinite quotient on both; the reference gives a finite 8.5e37 .. 3.4e38 there, an infinity below 2.9e-39);
+// the values themselves differ from MUFU's by <= 1-2 ulp.
+#ifdef LMVN_EMU
+static inline float emu_ftz(float x) { return (std::fabs(x) < 1.17549435e-38f) ? std::copysign(0.0f, x) : x; }
+#endif
+
 __device__ __forceinline__ float quotient(float view, float blurred) {
 #ifdef LMVN_EMU
-  return __fmul_rn(view, __frcp_rn(blurred));
+  return __fmul_rn(view, emu_ftz(1.0f / emu_ftz(blurred)));
 #else
   // MUFU reciprocal (<= 1 ulp, IEEE special values for 0 / Inf / NaN): two instructions per voxel instead of
   // the range-checked IEEE sequence with its slow-path branch
@@ -40,7 +48,7 @@ __device__ __forceinline__ float quotient(float view, float blurred, int zero_vi
 // orders of magnitude inside the parity tolerance (measured: tests/test_gpu_parity.py prints ~1e-6).
 __device__ __forceinline__ float rcp_fast(float d) {
 #ifdef LMVN_EMU
-  return 1.0f / d;
+  return emu_ftz(1.0f / emu_ftz(d));
 #else
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
@@ -49,7 +57,7 @@ __device__ __forceinline__ float rcp_fast(float d) {
 }
 __device__ __forceinline__ float sqrt_fast(float x) {
 #ifdef LMVN_EMU
-  return std::sqrt(x);
+  return emu_ftz(std::sqrt(emu_ftz(x)));
 #else
   float r;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

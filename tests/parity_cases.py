@@ -133,6 +133,16 @@ def case_pointwise(L):
     psi = np.array([1.0, 1.0, 3e38, 2.0], F32)
     L.compute_final_values(psi, np.array([np.nan, -np.inf, 3e38, 0.0], F32), np.ones(4, F32), 1e-3, 0.006)
     assert np.isfinite(psi).all() and np.allclose(psi[[0, 1, 3]], 1e-3, atol=1e-6)
+    # special values of the quotient, identical on the device (MUFU .ftz forms) and in the emulated build, which
+    # flushes subnormals the same way: 1/0 = inf like the reference; a SUBNORMAL blurred value is flushed to zero (the
+    # reference's double reciprocal still gives a finite 8.5e37 .. 3.4e38 above 2.9e-39: documented deviation)
+    out = np.array([0.0, -0.0, 1e-39, 1.17549435e-38, np.inf, np.nan], F32)
+    L.compute_quotient(np.ones(6, F32), out)
+    with np.errstate(divide="ignore"):
+        ref = orc.compute_quotient(np.ones(6, F32), np.array([0.0, -0.0, 1e-39, 1.17549435e-38, np.inf, np.nan], F32))
+    assert out[0] == np.inf and out[1] == -np.inf and out[2] == np.inf and out[4] == 0.0 and np.isnan(out[5])
+    np.testing.assert_allclose(out[3], ref[3], rtol=3e-7)
+    assert ref[0] == np.inf and ref[4] == 0.0 and np.isnan(ref[5])
 
 
 # ---- deconvolution (config-1 protocol, reduced size for CPU-side runs) ----
