@@ -600,6 +600,10 @@ struct RowArgs {
   // (both zero everywhere else: spectrum row = real-space row)
   long long rr_base;
   int rr_skip;
+  // plane kernels: first pointwise operand (view for the quotient, psi for the update) of tile row i staged in shared
+  // memory at op_smem + i * nx floats for i < op_smem_rows (bulk async copies, fft_x3.cuh); nullptr: read from global memory
+  const float* op_smem;
+  int op_smem_rows;  // tile rows [0, op_smem_rows) are staged
 };
 // (compile-time switch: the rows kernels that work on global spectra have no register to spare for the mapping)
 template <int SP>
@@ -840,9 +844,15 @@ __device__ __forceinline__ void rows_inv_group(const RowArgs& A, cplx* slab, lon
     const float* pa = (mode == gen::EPI_QUOTIENT) ? A.ep.view : A.ep.psi;
 #pragma unroll
     for (int a = 0; a < RPG; ++a) {
-      const float2* p2 = reinterpret_cast<const float2*>(pa + real_row<SP>(A, srow[a]) * nx);
+      if (SP && A.op_smem && srow[a] < A.op_smem_rows) {
+        const float2* p2 = reinterpret_cast<const float2*>(A.op_smem + srow[a] * nx);
 #pragma unroll
-      for (int r = 0; r < R1; ++r) oa[a * R1 + r] = ld_stream(p2 + lane + 16 * r);
+        for (int r = 0; r < R1; ++r) oa[a * R1 + r] = p2[lane + 16 * r];
+      } else {
+        const float2* p2 = reinterpret_cast<const float2*>(pa + real_row<SP>(A, srow[a]) * nx);
+#pragma unroll
+        for (int r = 0; r < R1; ++r) oa[a * R1 + r] = ld_stream(p2 + lane + 16 * r);
+      }
     }
   }
   // ---- inverse split into the slab, natural order ----

@@ -663,10 +663,16 @@ struct X3Engine : FastEngine {
   bool can_chain_embedded() const override { return false; }
   bool can_chain_rows() const override { return false; }
 
+  // operand rows of the chained plane pass by bulk async copies (TMA engine + mbarrier): OPT-IN, LMVN_X3_TMA=1.  Measured
+  // (profiles/r02_x3_v5_tma_probe.json): quotient link 0.285 -> 0.354 ms, update link 0.332 -> 0.410 ms -- the 64 KB staging
+  // buffer next to the 136 KB tile leaves ~20 KB of the SM's 228 KB for L1 (twiddle tables, operand lines of the second
+  // row iteration), and the copy adds a shared-memory write + read per operand byte to kernels that are bound by that pipe.
+  int x3_stage_ops = 0;
   int x3_prefetch = 0;  // CTAs of look-ahead of the plane pass' L2 prefetch (A/B knob LMVN_X3_PREFETCH)
   int init_x3() {
     khat_half = false;
     r2 = plan->ny / x3::kRows;
+    if (const char* e = getenv("LMVN_X3_TMA")) x3_stage_ops = (*e != '0');
     x3_prefetch = 0;  // measured: -3 % (quotient) / -11 % (update) with a look-ahead of one CTA per SM (profiles/r02_x3_v2_probe*.json)
     if (const char* e = getenv("LMVN_X3_PREFETCH")) x3_prefetch = std::max(0, atoi(e));
     if (!tables->tw_p128[0] || !tables->tw_ny_lin) { set_last_error("two-pass schedule: tables missing"); return -1; }
@@ -676,8 +682,9 @@ struct X3Engine : FastEngine {
   template <int MODE, int EPI>
   int launch_plane(const x3::PlaneArgs& a, cudaStream_t s) {
     auto k = x3::k_plane<MODE, EPI>;
-    LMVN_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(x3::kPlaneSmem)));
-    LMVN_LAUNCH(k, dim3(unsigned(plan->nz * r2)), dim3(x3::kPlaneThreads), x3::kPlaneSmem, s, a);
+    const size_t smem = (MODE == x3::PM_CHAIN && a.stage_ops) ? x3::kPlaneSmemStaged : x3::kPlaneSmem;
+    LMVN_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(x3::kPlaneSmemStaged)));
+    LMVN_LAUNCH(k, dim3(unsigned(plan->nz * r2)), dim3(x3::kPlaneThreads), smem, s, a);
     LMVN_CUDA_TRY(cudaGetLastError());
     return 0;
   }
@@ -688,6 +695,7 @@ struct X3Engine : FastEngine {
     a.nz = plan->nz; a.ny = plan->ny; a.r2 = r2;
     a.tw_y = tables->tw_p128[0];
     a.prefetch = x3_prefetch;
+    a.stage_ops = x3_stage_ops;
     a.row.tw_m = d_tw_m; a.row.tw_nx = d_tw_nx;
     a.row.nz = plan->nz; a.row.ny = plan->ny;
     int epi = gen::EPI_STORE;

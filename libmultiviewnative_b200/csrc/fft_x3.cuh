@@ -40,6 +40,42 @@ static const int kPitch = 136;     // shared-memory row pitch = Row2Cfg<128>::RS
 static const int kPlaneThreads = 512;
 static const int kTileElems = (kRows + 1) * kM;  // 129 x 128 complex per (n2, z) in HBM
 static const size_t kPlaneSmem = size_t(kRows) * kPitch * sizeof(cplx);
+// staged operand rows (TMA variant of the chained plane pass): the rows of the FIRST of the two row-loop iterations
+// (64 rows x nx floats = 64 KB; all 128 would not fit next to the 136 KB tile) behind the tile, + the mbarrier.  The
+// rows of the second iteration are pulled into L2 at the same time and read with ordinary loads.
+static const int kStagedRows = kRows / 2;
+static const size_t kPlaneOpBytes = size_t(kStagedRows) * 2 * kM * sizeof(float);
+static const size_t kPlaneSmemStaged = kPlaneSmem + kPlaneOpBytes + 16;
+
+// ---- bulk asynchronous copies (TMA engine, SASS: UBLKCP) completing on an mbarrier --------------------------------
+#if !defined(LMVN_EMU)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return unsigned(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_global, unsigned bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_global), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LMVN_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LMVN_MBAR_DONE;\n"
+      "bra LMVN_MBAR_WAIT;\n"
+      "LMVN_MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+#endif
 
 enum PlaneMode { PM_CHAIN = 0, PM_BEGIN = 1, PM_END = 2 };
 
@@ -50,6 +86,8 @@ struct PlaneArgs {
   const cplx* tw_y;   // [j < 8][q < 16] = w_128^{jq}: stage table of the 128-point transform (16 x 8)
   int prefetch;       // > 0: once its own tile is on chip, a CTA pulls the tile and the operand rows of CTA
                       // blockIdx + prefetch (the one that takes an SM next) from HBM into L2
+  int stage_ops;      // chained pass: the rows of the first pointwise operand (view / psi) come in by bulk async copies
+                      // (TMA engine, mbarrier completion) issued at kernel entry, and are read from shared memory
 };
 
 // L2 prefetch of everything CTA `b` will read: its spectrum tile and its rows of the pointwise operands
@@ -147,6 +185,31 @@ static __global__ void __launch_bounds__(kPlaneThreads, 1) k_plane(PlaneArgs P) 
   A.rr_base = (long long)z * P.ny + n2;
   A.rr_skip = P.r2 - 1;
   RowTwShared<kM>::fill(s_tw, A);
+  // TMA-staged operand rows: 128 bulk copies of one row (nx floats = 1 KB) each, issued before the tile is even loaded,
+  // completing on one mbarrier while the y stages run; the rows phase reads them from shared memory
+  float* opbuf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tile) + kPlaneSmem);
+  void* opbar = reinterpret_cast<unsigned char*>(opbuf) + kPlaneOpBytes;
+  const bool staged = (MODE == PM_CHAIN) && P.stage_ops;
+  if (staged) {
+    const float* src = (EPI == gen::EPI_QUOTIENT) ? A.ep.view : A.ep.psi;
+#ifndef LMVN_EMU
+    if (threadIdx.x == 0) mbar_init(opbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) mbar_expect_tx(opbar, unsigned(kPlaneOpBytes));
+    if (threadIdx.x < kStagedRows)
+      bulk_g2s(opbuf + threadIdx.x * (2 * kM), src + (A.rr_base + (long long)threadIdx.x * P.r2) * (2 * kM), 2 * kM * sizeof(float), opbar);
+    else if (threadIdx.x < kRows) {
+      const char* row = reinterpret_cast<const char*>(src + (A.rr_base + (long long)threadIdx.x * P.r2) * (2 * kM));
+#pragma unroll
+      for (int l = 0; l < 8; ++l) prefetch_l2(row + l * 128);
+    }
+#else
+    for (int i = threadIdx.x; i < kStagedRows * 2 * kM; i += kPlaneThreads)
+      opbuf[i] = src[(A.rr_base + (long long)(i / (2 * kM)) * P.r2) * (2 * kM) + i % (2 * kM)];
+#endif
+    A.op_smem = opbuf;
+    A.op_smem_rows = kStagedRows;
+  }
   if (MODE != PM_BEGIN) {
     // inverse along the tile rows: radix 8 (span 8) straight from HBM, radix 16 (span 128)
     plane_stage<8, 8, true, W_GLOBAL, W_SMEM>(tile, gt, nullptr);
@@ -157,6 +220,9 @@ static __global__ void __launch_bounds__(kPlaneThreads, 1) k_plane(PlaneArgs P) 
     plane_prefetch<MODE, EPI>(P, blockIdx.x + unsigned(P.prefetch));
   }
   __syncthreads();
+#ifndef LMVN_EMU
+  if (staged) mbar_wait(opbar, 0);
+#endif
   {
     RowTwShared<kM> T;
     const int lane = threadIdx.x % 16, group = threadIdx.x / 16;
