@@ -673,6 +673,7 @@ struct X3Engine : FastEngine {
     khat_half = false;
     r2 = plan->ny / x3::kRows;
     if (const char* e = getenv("LMVN_X3_TMA")) x3_stage_ops = (*e != '0');
+    if (const char* e = getenv("LMVN_X3_ZMID")) zmid_version = atoi(e);
     x3_prefetch = 0;  // measured: -3 % (quotient) / -11 % (update) with a look-ahead of one CTA per SM (profiles/r02_x3_v2_probe*.json)
     if (const char* e = getenv("LMVN_X3_PREFETCH")) x3_prefetch = std::max(0, atoi(e));
     if (!tables->tw_p128[0] || !tables->tw_ny_lin) { set_last_error("two-pass schedule: tables missing"); return -1; }
@@ -740,13 +741,27 @@ struct X3Engine : FastEngine {
     LMVN_CUDA_TRY(cudaGetLastError());
     return 0;
   }
+  template <int NZ, int RR>
+  int launch_zmid5(const x3::ZmidArgs& a, cudaStream_t s) {
+    const size_t smem = size_t(NZ) * (16 + 16 / RR) * sizeof(cplx);
+    auto k = x3::k_zmid5<NZ, RR>;
+    LMVN_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const unsigned tiles = unsigned((x3::kRows + 1) * (x3::kM / (16 / RR)));
+    LMVN_LAUNCH(k, dim3(tiles), dim3(256), smem, s, a);
+    LMVN_CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+  int zmid_version = 5;  // LMVN_X3_ZMID=4: the four-barrier form (k_zmid) also for 16-column tiles (A/B)
   int zmid(cplx* a_buf, const cplx* khat, cudaStream_t s) {
     x3::ZmidArgs a;
     std::memset(&a, 0, sizeof(a));
     a.a = a_buf; a.khat = khat; a.nz = plan->nz; a.r2 = r2;
     a.tw1 = d_tw_z[0]; a.tw2 = d_tw_z[1]; a.tw_ny = tables->tw_ny_lin;
     int rc = -1;
-    if (r2 == 4) {
+    if (zmid_version == 5 && (plan->nz == 256 || plan->nz == 512)) {
+      if (r2 == 4) rc = (plan->nz == 512) ? launch_zmid5<512, 4>(a, s) : launch_zmid5<256, 4>(a, s);
+      else rc = (plan->nz == 512) ? launch_zmid5<512, 2>(a, s) : launch_zmid5<256, 2>(a, s);
+    } else if (r2 == 4) {
       switch (plan->nz) {
         case 64: rc = launch_zmid<64, 4>(a, s); break;
         case 128: rc = launch_zmid<128, 4>(a, s); break;

@@ -156,15 +156,76 @@ __device__ __forceinline__ void plane_bfly(cplx* sm, cplx* g, int g_rs, const cp
   }
 }
 
-// one stage over the whole tile: 128 ordinary columns (thread = column tid % 128, four row groups) and the Nyquist
-// column (tile column 128 <-> row 128 of the tile in HBM, stride 1), which the first threads take on top
+// the same butterfly on TWO adjacent columns at once: every access is 128 bits wide (half the load/store instructions
+// of the stage, the twiddles are shared).  sm / g point at the even column of the pair (16-byte aligned).
+template <int R, int L, bool INV, int SRC, int DST>
+__device__ __forceinline__ void plane_bfly2(cplx* sm, cplx* g, int g_rs, const cplx* __restrict__ tws, int bf) {
+  constexpr int Mq = L / R;
+  const int j = bf % Mq;
+  const int row0 = (bf / Mq) * L + j;
+  cplx v0[R], v1[R];
+  if (SRC == W_SMEM) {
+    const float4* p = reinterpret_cast<const float4*>(sm + row0 * kPitch);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float4 f = p[r * Mq * (kPitch / 2)];
+      v0[r] = cmake(f.x, f.y);
+      v1[r] = cmake(f.z, f.w);
+    }
+  } else {
+    const float4* gp = reinterpret_cast<const float4*>(g + row0 * g_rs);
+    const int step = Mq * g_rs / 2;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float4 f = ld_stream4(gp + r * step);
+      v0[r] = cmake(f.x, f.y);
+      v1[r] = cmake(f.z, f.w);
+    }
+  }
+  cplx t[R];
+  if (Mq > 1) load_twiddles<R>(t, tws + j * R);
+  if (INV && Mq > 1) {
+#pragma unroll
+    for (int q = 1; q < R; ++q) { v0[q] = cmulc(v0[q], t[q]); v1[q] = cmulc(v1[q], t[q]); }
+  }
+  Bfly<R, INV>::run(v0);
+  Bfly<R, INV>::run(v1);
+  if (!INV && Mq > 1) {
+#pragma unroll
+    for (int q = 1; q < R; ++q) { v0[q] = cmul(v0[q], t[q]); v1[q] = cmul(v1[q], t[q]); }
+  }
+  if (DST == W_SMEM) {
+    float4* p = reinterpret_cast<float4*>(sm + row0 * kPitch);
+#pragma unroll
+    for (int q = 0; q < R; ++q) p[q * Mq * (kPitch / 2)] = make_float4(v0[q].x, v0[q].y, v1[q].x, v1[q].y);
+  } else {
+    float4* gp = reinterpret_cast<float4*>(g + row0 * g_rs);
+    const int step = Mq * g_rs / 2;
+#pragma unroll
+    for (int q = 0; q < R; ++q) st_stream4(gp + q * step, make_float4(v0[q].x, v0[q].y, v1[q].x, v1[q].y));
+  }
+}
+
+// one stage over the whole tile: 64 pairs of ordinary columns (thread = pair tid % 64, eight row groups; 128-bit
+// accesses) and the Nyquist column (tile column 128 <-> row 128 of the tile in HBM, stride 1), which the first threads
+// take on top.  Default: one column per thread, 64-bit accesses; LMVN_X3_WIDE_Y (build knob): column pairs, 128-bit
+// accesses -- half the load/store instructions of the y stages, measured neutral (quotient link 0.285 -> 0.281 ms,
+// update link 0.332 -> 0.349 ms, profiles/r02_x3_v6_probe.json): the pass is not bound by instruction issue.
 template <int R, int L, bool INV, int SRC, int DST>
 __device__ __forceinline__ void plane_stage(cplx* tile, cplx* gt, const cplx* __restrict__ tws) {
   constexpr int NB = kRows / R;                 // butterflies per column
+#ifndef LMVN_X3_WIDE_Y
   constexpr int RG = kPlaneThreads / kM;        // 4 row groups
   const int c = threadIdx.x % kM, rg = threadIdx.x / kM;
 #pragma unroll
   for (int i = 0; i < NB / RG; ++i) plane_bfly<R, L, INV, SRC, DST>(tile + c, gt + c, kM, tws, rg + i * RG);
+#else
+  constexpr int RG = kPlaneThreads / (kM / 2);  // 8 row groups
+  static_assert(NB % RG == 0, "whole butterflies per thread");
+  const int cp = threadIdx.x % (kM / 2), rg = threadIdx.x / (kM / 2);
+#pragma unroll
+  for (int i = 0; i < NB / RG; ++i) plane_bfly2<R, L, INV, SRC, DST>(tile + 2 * cp, gt + 2 * cp, kM, tws, rg + i * RG);
+#endif
   if (threadIdx.x < NB) plane_bfly<R, L, INV, SRC, DST>(tile + kM, gt + kRows * kM, 1, tws, threadIdx.x);
 }
 
@@ -365,6 +426,181 @@ static __global__ void __launch_bounds__(Threads<NZ>::V, StridedBlocks<NZ, SM_FW
   zmid_y_level<NZ, R2, true>(smem, Z.tw_ny);
   __syncthreads();
   strided_stage<NZ, R1, NZ, COLS, true, W_SMEM, W_GLOBAL, U, PITCH>(sm, Z.a + column(), rs, Z.tw1, 1.f);
+}
+
+// ------------------------------------------------------------------------------
+// pass B, version 5 (16-column tiles: nz = 256, 512): the same stages as k_zmid, but the y level is WARP LOCAL.
+// After the first z stage a half-warp (16 lanes = the 16 columns of one row group rg) has written exactly the rows
+// rg + 16 q of all 16 columns; the y level needs, per row, the R2 slots of a column pair -- all inside that half-warp's
+// rows.  Likewise after the middle stage (rows (rg + 16 i) 16 + r).  So the level runs right behind each of the two
+// stages after a __syncwarp(), and the pass is back to the TWO block-wide barriers of the five-pass z pass (k_zmid has
+// four: 27 % + 9 % of its stall samples sat in the two short phases the extra barriers fence off, profiles/r02_ncu_x3_v3.md).
+// Measured: 0.289 ms against 0.290 ms of k_zmid (profiles/r02_x3_v6_probe.json) -- the barriers were not the limiter either.
+// What is: the 32-byte pieces.  A warp-wide 64-bit access of this pass touches EIGHT 128-byte lines (4 slots x 2 rows) where
+// the five-pass z pass touches two, and the L1/LSU pipe handles one line per cycle whatever part of it is used: 768
+// instead of 192 wavefronts per warp and tile for the tile load, the K^ load and the tile store, ~1300 against ~450 in
+// total -- and 0.29 against 0.16 ms.  Wider pieces need wider tiles (KXC = 16: 256 KB of shared memory) or fewer slots
+// (R2 = 2 for ny = 512: 256-row plane tiles, 272 KB).  The plane tile and the z tile cannot both fit an SM.
+// The rows rg + 16 q of a half-warp all start at the same bank (16 rows x pitch x 8 bytes is a multiple of 128 for every
+// pitch), so the tile is swizzled: the 16-byte unit u of row z is stored at unit u ^ (((z >> 4) & (8/PAIRS - 1)) * PAIRS).
+// A quarter-warp of the level (8/PAIRS rows x PAIRS units per slot) then hits eight distinct units; the 64-bit accesses of
+// the z stages (one whole row per half-warp) are conflict free under any permutation of a row's units.
+// ------------------------------------------------------------------------------
+struct FwdTag { static const bool value = false; };
+struct InvTag { static const bool value = true; };
+
+template <int NZ, int R2>
+static __global__ void __launch_bounds__(256, 2) k_zmid5(ZmidArgs Z) {
+  typedef Radix<NZ> RX;
+  static_assert(RX::S == 2 && Cols<NZ>::V == 16 && NZ / RX::R1 == 16, "16-column tiles, 16 row groups");
+  constexpr int COLS = 16, KXC = COLS / R2, PAIRS = KXC / 2, PITCH = COLS + KXC;
+  constexpr int R1 = RX::R1, RM = RX::R2;       // z plan: R1 x RM (32 x 16, 16 x 16)
+  constexpr int PT = (NZ / RM) / 16;            // middle butterflies per thread
+  constexpr int SWZ_MASK = 8 / PAIRS - 1;
+  LMVN_DYN_SMEM(cplx, smem);                    // [NZ][PITCH], swizzled
+  constexpr int CHUNKS = kM / KXC;
+  const int c = threadIdx.x % COLS, rg = threadIdx.x / COLS;
+  const int rs = kTileElems;
+  auto column = [&]() -> long long {
+    const int p = blockIdx.x / CHUNKS, kx0 = (blockIdx.x % CHUNKS) * KXC;
+    return (long long)(c / KXC) * Z.nz * kTileElems + (long long)p * kM + kx0 + (c % KXC);
+  };
+  // this lane's twiddles of the y level (one per slot and element of its column pair)
+  auto y_twiddles = [&](cplx (&w)[2][R2], int pair) {
+    const int p = blockIdx.x / CHUNKS, kx0 = (blockIdx.x % CHUNKS) * KXC;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int pos = (p < kRows) ? p : (kx0 + 2 * pair + e);
+      const int k1 = (pos >> 3) + ((pos & 7) << 4);
+#pragma unroll
+      for (int n = 1; n < R2; ++n) w[e][n] = __ldg(Z.tw_ny + n * k1);
+    }
+  };
+  // the y level on one (row, column pair) item
+  auto y_item = [&](int row, int pair, int swz, const cplx (&w)[2][R2], auto inv_tag) {
+    constexpr bool INV = decltype(inv_tag)::value;
+    float4* rowp = reinterpret_cast<float4*>(smem + row * PITCH);
+    cplx v0[R2], v1[R2];
+#pragma unroll
+    for (int n = 0; n < R2; ++n) {
+      const float4 f = rowp[(n * PAIRS + pair) ^ swz];
+      v0[n] = cmake(f.x, f.y);
+      v1[n] = cmake(f.z, f.w);
+    }
+    if (!INV) {
+#pragma unroll
+      for (int n = 1; n < R2; ++n) { v0[n] = cmul(v0[n], w[0][n]); v1[n] = cmul(v1[n], w[1][n]); }
+    }
+    Bfly<R2, INV>::run(v0);
+    Bfly<R2, INV>::run(v1);
+    if (INV) {
+#pragma unroll
+      for (int n = 1; n < R2; ++n) { v0[n] = cmulc(v0[n], w[0][n]); v1[n] = cmulc(v1[n], w[1][n]); }
+    }
+#pragma unroll
+    for (int n = 0; n < R2; ++n) rowp[(n * PAIRS + pair) ^ swz] = make_float4(v0[n].x, v0[n].y, v1[n].x, v1[n].y);
+  };
+
+  // ---- z stage 1: radix R1 over rows rg + 16 r, straight from HBM ----
+  {
+    cplx v[R1];
+    const cplx* gp = Z.a + column() + (long long)rg * rs;
+    const int step = 16 * rs;
+#pragma unroll
+    for (int r = 0; r < R1; ++r) {
+      v[r] = ld_stream(gp);
+      gp += step;
+      LMVN_KEEP_PTR(gp);
+    }
+    cplx t[R1];
+    load_twiddles<R1>(t, Z.tw1 + rg * R1);
+    Bfly<R1, false>::run(v);
+#pragma unroll
+    for (int q = 1; q < R1; ++q) v[q] = cmul(v[q], t[q]);
+#pragma unroll
+    for (int q = 0; q < R1; ++q)
+      smem[(rg + 16 * q) * PITCH + ((((c >> 1) ^ ((q & SWZ_MASK) * PAIRS)) << 1) | (c & 1))] = v[q];
+  }
+  __syncwarp();
+  // ---- y level forward on the rows this half-warp has just written ----
+  {
+    constexpr int IPT = R1 * PAIRS / 16;
+    const int pair = c % PAIRS;
+    cplx w[2][R2];
+    y_twiddles(w, pair);
+#pragma unroll(IPT >= 2 ? 2 : 1)
+    for (int i = 0; i < IPT; ++i) {
+      const int q = (c + 16 * i) / PAIRS;
+      y_item(rg + 16 * q, pair, (q & SWZ_MASK) * PAIRS, w, FwdTag());
+    }
+  }
+  // ---- middle: radix RM, * K^, radix RM^-1 on RM consecutive rows ----
+  cplx kk[PT][RM];
+  {
+    const cplx* gk = Z.khat + column();
+#pragma unroll
+    for (int i = 0; i < PT; ++i) {
+      const cplx* gp = gk + (long long)((rg + 16 * i) * RM) * rs;
+#pragma unroll
+      for (int r = 0; r < RM; ++r) {
+        kk[i][r] = ld_stream(gp);
+        gp += rs;
+        LMVN_KEEP_PTR(gp);
+      }
+    }
+  }
+  __syncthreads();
+  const int swz_m = (rg & SWZ_MASK) * PAIRS;  // rows (rg + 16 i) RM + r: (row >> 4) = rg + 16 i
+  {
+    const int cphys = (((c >> 1) ^ swz_m) << 1) | (c & 1);
+#pragma unroll
+    for (int i = 0; i < PT; ++i) {
+      cplx* p = smem + (rg + 16 * i) * RM * PITCH + cphys;
+      cplx v[RM];
+#pragma unroll
+      for (int r = 0; r < RM; ++r) v[r] = p[r * PITCH];
+      Bfly<RM, false>::run(v);
+#pragma unroll
+      for (int r = 0; r < RM; ++r) v[r] = cmul(v[r], kk[i][r]);
+      Bfly<RM, true>::run(v);
+#pragma unroll
+      for (int r = 0; r < RM; ++r) p[r * PITCH] = v[r];
+    }
+  }
+  __syncwarp();
+  // ---- y level inverse on the rows this half-warp has just written ----
+  {
+    constexpr int IPT = PT * RM * PAIRS / 16;
+    const int pair = c % PAIRS;
+    cplx w[2][R2];
+    y_twiddles(w, pair);
+#pragma unroll(IPT >= 2 ? 2 : 1)
+    for (int j = 0; j < IPT; ++j) {
+      const int rr = (c + 16 * j) / PAIRS;  // 0 .. PT * RM - 1
+      y_item((rg + 16 * (rr / RM)) * RM + (rr % RM), pair, swz_m, w, InvTag());
+    }
+  }
+  __syncthreads();
+  // ---- z stage 1 inverse: rows rg + 16 q -> HBM ----
+  {
+    cplx v[R1];
+#pragma unroll
+    for (int q = 0; q < R1; ++q)
+      v[q] = smem[(rg + 16 * q) * PITCH + ((((c >> 1) ^ ((q & SWZ_MASK) * PAIRS)) << 1) | (c & 1))];
+    cplx t[R1];
+    load_twiddles<R1>(t, Z.tw1 + rg * R1);
+#pragma unroll
+    for (int q = 1; q < R1; ++q) v[q] = cmulc(v[q], t[q]);
+    Bfly<R1, true>::run(v);
+    cplx* gp = Z.a + column() + (long long)rg * rs;
+    const int step = 16 * rs;
+#pragma unroll
+    for (int r = 0; r < R1; ++r) {
+      st_stream(gp, v[r]);
+      gp += step;
+      LMVN_KEEP_PTR(gp);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------
