@@ -9,6 +9,8 @@
 #include <omp.h>
 #endif
 #include <chrono>
+#include <condition_variable>
+#include <thread>
 #include <cmath>
 #include <cstdlib>
 
@@ -498,6 +500,105 @@ int Deconv::wrap_exterior(float* vol) {
 // ---------------------------------------------------------------------------------
 namespace {
 #ifndef LMVN_EMU
+// Host threads that move pageable caller memory into / out of the pinned staging ring.  A persistent pool that SLEEPS
+// between copies: an OpenMP team per copy spin-waits after every parallel region, and with one process per GPU that
+// meant 8 ranks x 8 spinning threads on a 32-core host (8 x B200 box: the staged upload of config 3 took 1.3 s per call
+// instead of 0.4 s, profiles/r02_bench_8gpu_before_copy_pool.json).  Size: LMVN_STAGING_THREADS, else the machine's hardware
+// threads divided by the number of visible GPUs (every GPU usually has its own process doing the same), 1 .. 8.
+class CopyPool {
+ public:
+  explicit CopyPool(int n) {
+    for (int i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  void copy(void* dst, const void* src, size_t bytes) {
+    static const size_t kPiece = size_t(1) << 20;
+    const size_t pieces = (bytes + kPiece - 1) / kPiece;
+    if (workers_.empty() || pieces < 2) { std::memcpy(dst, src, bytes); return; }
+    std::unique_lock<std::mutex> job(job_mu_);  // one copy at a time through the pool
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      done_cv_.wait(lk, [this] { return active_ == 0; });  // no straggler of the previous job is still looking at its fields
+      dst_ = static_cast<unsigned char*>(dst);
+      src_ = static_cast<const unsigned char*>(src);
+      bytes_ = bytes;
+      pieces_ = pieces;
+      next_.store(0);
+      left_ = pieces;
+      ++generation_;
+    }
+    cv_.notify_all();
+    work(kPiece);  // the calling thread copies too
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [this] { return left_ == 0 && active_ == 0; });
+  }
+
+ private:
+  void work(size_t piece) {
+    size_t mine = 0;
+    for (;;) {
+      const size_t i = next_.fetch_add(1);
+      if (i >= pieces_) break;
+      const size_t off = i * piece;
+      std::memcpy(dst_ + off, src_ + off, std::min(piece, bytes_ - off));
+      ++mine;
+    }
+    if (mine) {
+      std::lock_guard<std::mutex> lk(mu_);
+      left_ -= mine;
+      if (left_ == 0) done_cv_.notify_all();
+    }
+  }
+  void run() {
+    unsigned long long seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+        if (stop_) return;
+        seen = generation_;
+        ++active_;  // the job's fields stay as they are while any worker is inside work()
+      }
+      work(size_t(1) << 20);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--active_ == 0) done_cv_.notify_all();
+      }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_, job_mu_;
+  std::condition_variable cv_, done_cv_;
+  unsigned char* dst_ = nullptr;
+  const unsigned char* src_ = nullptr;
+  size_t bytes_ = 0, pieces_ = 0, left_ = 0;
+  int active_ = 0;
+  std::atomic<size_t> next_{0};
+  unsigned long long generation_ = 0;
+  bool stop_ = false;
+};
+CopyPool& copy_pool() {
+  static CopyPool* pool = [] {
+    int threads = 0;
+    if (const char* e = getenv("LMVN_STAGING_THREADS")) threads = atoi(e);
+    if (threads <= 0) {
+      int gpus = 1;
+      if (cudaGetDeviceCount(&gpus) != cudaSuccess || gpus < 1) { (void)cudaGetLastError(); gpus = 1; }
+      const int hw = int(std::thread::hardware_concurrency());
+      threads = std::max(1, std::min(8, (hw > 0 ? hw : 8) / gpus));
+    }
+    return new CopyPool(threads - 1);  // + the calling thread; lives as long as the process
+  }();
+  return *pool;
+}
+
 struct HostStager {
   static const size_t kChunk = size_t(16) << 20;
   static const int kSlots = 3;
@@ -540,23 +641,7 @@ struct HostStager {
     ready = true;
     return 0;
   }
-  static void parallel_copy(void* dst, const void* src, size_t bytes) {
-    const size_t piece = size_t(1) << 20;
-    const long long pieces = (long long)((bytes + piece - 1) / piece);
-    int threads = 1;
-#ifdef _OPENMP
-    // the machine's cores, not omp_get_max_threads(): launchers such as torchrun export OMP_NUM_THREADS=1, and a
-    // single-threaded copy into the pinned ring runs at a quarter of the PCIe rate
-    threads = std::max(1, std::min(8, omp_get_num_procs()));
-    if (const char* e = getenv("LMVN_STAGING_THREADS")) threads = std::max(1, atoi(e));
-#endif
-#pragma omp parallel for num_threads(threads) schedule(static)
-    for (long long i = 0; i < pieces; ++i) {
-      const size_t off = size_t(i) * piece;
-      std::memcpy(static_cast<unsigned char*>(dst) + off, static_cast<const unsigned char*>(src) + off,
-                  std::min(piece, bytes - off));
-    }
-  }
+  static void parallel_copy(void* dst, const void* src, size_t bytes) { copy_pool().copy(dst, src, bytes); }
   // host -> device, stream ordered on s; returns when src_h has been read completely (like a pageable cudaMemcpyAsync)
   int upload(void* dst_d, const void* src_h, size_t bytes, cudaStream_t s) {
     std::lock_guard<std::mutex> lk(mu);
