@@ -533,6 +533,7 @@ class CopyPool {
       next_.store(0);
       left_ = pieces;
       ++generation_;
+      hint_.store(generation_, std::memory_order_release);
     }
     cv_.notify_all();
     work(kPiece);  // the calling thread copies too
@@ -559,6 +560,15 @@ class CopyPool {
   void run() {
     unsigned long long seen = 0;
     for (;;) {
+      // a stack is uploaded as a train of 16 MiB chunks a few hundred microseconds apart: poll for the next chunk for
+      // a short while before going to sleep (a futex wake-up per worker and chunk cost ~15 % of the upload rate)
+      const auto t0 = std::chrono::steady_clock::now();
+      while (hint_.load(std::memory_order_acquire) == seen &&
+             std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(300)) {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+      }
       {
         std::unique_lock<std::mutex> lk(mu_);
         cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
@@ -581,6 +591,7 @@ class CopyPool {
   size_t bytes_ = 0, pieces_ = 0, left_ = 0;
   int active_ = 0;
   std::atomic<size_t> next_{0};
+  std::atomic<unsigned long long> hint_{0};  // copy of generation_ the workers may poll without the lock
   unsigned long long generation_ = 0;
   bool stop_ = false;
 };
@@ -641,7 +652,39 @@ struct HostStager {
     ready = true;
     return 0;
   }
-  static void parallel_copy(void* dst, const void* src, size_t bytes) { copy_pool().copy(dst, src, bytes); }
+  // LMVN_STAGING_IMPL = pool | omp.  Default: the sleeping pool when the box has several GPUs (one process per GPU doing
+  // the same: spinning OpenMP teams oversubscribe the host), an OpenMP team otherwise (lowest wake-up latency).
+  static bool use_pool() {
+    static int v = -1;
+    if (v < 0) {
+      const char* e = getenv("LMVN_STAGING_IMPL");
+      if (e && e[0] == 'o') v = 0;
+      else if (e && e[0] == 'p') v = 1;
+      else {
+        int gpus = 1;
+        if (cudaGetDeviceCount(&gpus) != cudaSuccess) { (void)cudaGetLastError(); gpus = 1; }
+        v = gpus > 1 ? 1 : 0;
+      }
+    }
+    return v == 1;
+  }
+  static void parallel_copy(void* dst, const void* src, size_t bytes) {
+    if (use_pool()) { copy_pool().copy(dst, src, bytes); return; }
+    const size_t piece = size_t(1) << 20;
+    const long long pieces = (long long)((bytes + piece - 1) / piece);
+    int threads = 1;
+#ifdef _OPENMP
+    // the machine's cores, not omp_get_max_threads(): launchers such as torchrun export OMP_NUM_THREADS=1
+    threads = std::max(1, std::min(8, omp_get_num_procs()));
+    if (const char* e = getenv("LMVN_STAGING_THREADS")) threads = std::max(1, atoi(e));
+#endif
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (long long i = 0; i < pieces; ++i) {
+      const size_t off = size_t(i) * piece;
+      std::memcpy(static_cast<unsigned char*>(dst) + off, static_cast<const unsigned char*>(src) + off,
+                  std::min(piece, bytes - off));
+    }
+  }
   // host -> device, stream ordered on s; returns when src_h has been read completely (like a pageable cudaMemcpyAsync)
   int upload(void* dst_d, const void* src_h, size_t bytes, cudaStream_t s) {
     std::lock_guard<std::mutex> lk(mu);
