@@ -228,6 +228,23 @@ def blocks_record(lib, torch, dist, rank, world, device, barrier, max_over_ranks
                       depth=calls_in_flight, keep=False)
         return time.perf_counter() - t0
 
+    # the same blocks in page-locked buffers (a caller that can allocate its stacks with cudaHostAlloc)
+    keep, pinned = [], []
+    for blk in distinct:
+        q = dict(blk)
+        for key in ("views", "weights"):
+            q[key] = []
+            for a in blk[key]:
+                t, arr = _pin(torch, a)
+                keep.append(t)
+                q[key].append(arr)
+        pinned.append(q)
+
+    def timed_pinned(indices):
+        t0 = time.perf_counter()
+        run_pipelined(lib, lambda b: pinned[b % len(pinned)], indices, iterations, 0.006, 1e-4, device, depth=depth, keep=False)
+        return time.perf_counter() - t0
+
     timed([0, 1])  # warm-up: plan store, arenas, staging ring
     barrier()
     one_gpu = one_gpu_seq = one_gpu_pinned = None
@@ -235,31 +252,23 @@ def blocks_record(lib, torch, dist, rank, world, device, barrier, max_over_ranks
         per = nvox * views * iterations * n1_blocks / 1e9
         one_gpu = per / timed(list(range(n1_blocks)))
         one_gpu_seq = per / timed(list(range(n1_blocks)), 1)  # the same blocks, one call at a time (no overlap)
-        # the same blocks from page-locked buffers (a caller that can allocate its stacks with cudaHostAlloc)
-        keep, pinned = [], []
-        for b in distinct:
-            q = dict(b)
-            for key in ("views", "weights"):
-                q[key] = []
-                for a in b[key]:
-                    t, arr = _pin(torch, a)
-                    keep.append(t)
-                    q[key].append(arr)
-            pinned.append(q)
-        t0 = time.perf_counter()
-        run_pipelined(lib, lambda b: pinned[b % len(pinned)], list(range(n1_blocks)), iterations, 0.006, 1e-4, device,
-                      depth=depth, keep=False)
-        one_gpu_pinned = per / (time.perf_counter() - t0)
-        del keep, pinned
+        one_gpu_pinned = per / timed_pinned(list(range(n1_blocks)))
     barrier()
     mine = shard(n_blocks, rank, world)
     t0 = time.perf_counter()
     timed(mine)
     barrier()
     wall = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    t0 = time.perf_counter()
+    timed_pinned(mine)
+    barrier()
+    wall_pinned = max_over_ranks(time.perf_counter() - t0)
+    del keep, pinned
     if rank != 0:
         return None
     value = nvox * views * iterations * n_blocks / wall / 1e9
+    value_pinned = nvox * views * iterations * n_blocks / wall_pinned / 1e9
     return {"workload": "config 4: %d independent %dx%dx%d blocks, %d views, %d^3 PSFs, %d iterations, through "
                         "inplace_gpu_deconvolve with pageable host buffers, block b on GPU b mod G, %d calls in flight per GPU, "
                         "no collective" % (n_blocks, dims[0], dims[1], dims[2], views, kernel, iterations, depth),
@@ -267,6 +276,10 @@ def blocks_record(lib, torch, dist, rank, world, device, barrier, max_over_ranks
             "one_gpu_same_build": {"value": one_gpu, "blocks": n1_blocks, "one_call_at_a_time": one_gpu_seq,
                                    "pinned_host_buffers": one_gpu_pinned},
             "speedup_vs_one_gpu": value / one_gpu,
+            # the same batch from page-locked host buffers: no host-side staging copy (8 ranks share the host's cores
+            # and memory bandwidth for that copy; on the 32-core 8 x B200 box it is the limit of the pageable batch)
+            "pinned_host_buffers": {"value": value_pinned, "wall_s": wall_pinned,
+                                    "speedup_vs_one_gpu_pinned": value_pinned / one_gpu_pinned},
             "h2d_bytes_per_block": int((2 * views + 1) * nvox * 4), "d2h_bytes_per_block": int(nvox * 4)}
 
 
