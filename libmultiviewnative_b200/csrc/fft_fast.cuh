@@ -263,6 +263,19 @@ template <int N> struct Threads { static const int V = kStridedThreads; };
 #ifdef LMVN_STRIDED_HALF
 template <> struct Threads<512> { static const int V = 128; };
 #endif
+// Tile shape per (length, mode).  The merged 1024-point z pass works on FULL-LINE tiles -- 16 columns, 128 KB of shared
+// memory, 512 threads, one CTA per SM: every global access of a half-warp is a whole 128-byte line, where the 8-column
+// tiles of the other 1024-point passes use half of every L1 wavefront.  Measured (profiles/r02_1024_wide_tiles.log): z pass
+// 4.44 -> 3.27 ms at 1024^3 (-26 %), 1.10 -> 0.79 ms at 1024 x 1024 x 256; the y passes get slower on such tiles (y inverse
+// +17 %: with two stages they live on the overlap of two co-resident CTAs), so they keep theirs.  LMVN_1024_NARROW_Z: A/B.
+template <int N, int MODE> struct TileCols { static const int V = Cols<N>::V; };
+template <int N, int MODE> struct TileThreads { static const int V = Threads<N>::V; };
+#ifndef LMVN_1024_NARROW_Z
+template <> struct TileCols<1024, 2> { static const int V = 16; };     // SM_FWD_MUL_INV
+template <> struct TileThreads<1024, 2> { static const int V = 512; };
+template <> struct TileCols<1024, 5> { static const int V = 16; };     // SM_FWD_MUL_INV_SCATTER
+template <> struct TileThreads<1024, 5> { static const int V = 512; };
+#endif
 #ifndef LMVN_ZMUL_BLOCKS
 #define LMVN_ZMUL_BLOCKS 2
 #endif
@@ -301,12 +314,13 @@ __device__ __forceinline__ void load_twiddles(cplx* t, const cplx* __restrict__ 
 // decimation-in-time mirror (conjugate twiddle, then butterfly).  `sm` and `g`
 // already point at this thread's column; rows are addressed with 32-bit offsets.
 // PITCH: row pitch of the shared-memory tile (the two-pass schedule pads its rows, fft_x3.cuh).
-template <int N, int R, int L, int COLS, bool INV, int SRC, int DST, int UNROLL = 8, int PITCH = COLS>
+template <int N, int R, int L, int COLS, bool INV, int SRC, int DST, int UNROLL = 8, int PITCH = COLS,
+          int THREADS = Threads<N>::V>
 __device__ __forceinline__ void strided_stage(cplx* __restrict__ sm, cplx* __restrict__ g, int rs,
                                               const cplx* __restrict__ tws, float scale,
                                               const Scatter* sc = nullptr, long long sc_tile = 0) {
   constexpr int M = L / R;
-  constexpr int RG = Threads<N>::V / COLS;   // row groups per block
+  constexpr int RG = THREADS / COLS;   // row groups per block
   constexpr int PER_THREAD = (N / R) / RG;
   static_assert(PER_THREAD >= 1, "tile too small for the block");
   const int rg = threadIdx.x / COLS;
@@ -371,9 +385,9 @@ __device__ __forceinline__ void strided_stage(cplx* __restrict__ sm, cplx* __res
 // middle of the merged z pass: last forward stage (span R), spectrum product, first inverse stage.
 // The K^ operands come straight from HBM; middle_load() is called BEFORE the barrier that precedes
 // the middle so that their latency overlaps the barrier wait and the shared-memory reads.
-template <int N, int R, int COLS, int PITCH = COLS, int KH = 0>
+template <int N, int R, int COLS, int PITCH = COLS, int KH = 0, int THREADS = Threads<N>::V>
 struct Middle {
-  static const int RG = Threads<N>::V / COLS;
+  static const int RG = THREADS / COLS;
   static const int PT = (N / R) / RG;  // butterflies per thread: 1 or 2 in every plan that is used
   struct K { cplx k[PT][R]; };
   // KH = 1: gk points at __half2 elements (4 bytes per complex value): half the K^ bytes of the pass
@@ -429,7 +443,7 @@ template <int N, int MODE_, int U, int ALT = 0, int KH = 0>
 __device__ __forceinline__ void strided_tile(const StridedArgs& A, cplx* sm, cplx* g, const cplx* gk, bool live,
                                              long long sc_tile, int rs) {
   typedef Plan<N, ALT> RX;
-  constexpr int COLS = Cols<N>::V;
+  constexpr int COLS = TileCols<N, MODE_>::V, TH = TileThreads<N, MODE_>::V;
   constexpr int R1 = RX::R1, R2 = RX::R2;
   constexpr int R3 = (RX::R3 > 1 ? RX::R3 : 2);  // placeholder radix for the dead 3-stage code of 2-stage sizes
   constexpr int L2 = N / R1, L3 = (RX::S == 3 ? N / (R1 * R2) : 2);
@@ -438,55 +452,59 @@ __device__ __forceinline__ void strided_tile(const StridedArgs& A, cplx* sm, cpl
   constexpr int DSTG = SCAT ? W_SCATTER : ((MODE == SM_FWD_SCALE) ? W_GLOBAL_SCALED : W_GLOBAL);
   const Scatter* sc = &A.sc;
   if (MODE == SM_FWD || MODE == SM_FWD_SCALE) {
-    if (live) strided_stage<N, R1, N, COLS, false, W_GLOBAL, W_SMEM, U>(sm, g, rs, A.tw1, 1.f);
+    if (live) strided_stage<N, R1, N, COLS, false, W_GLOBAL, W_SMEM, U, COLS, TH>(sm, g, rs, A.tw1, 1.f);
     __syncthreads();
     if (RX::S == 3) {
-      if (live) strided_stage<N, R2, L2, COLS, false, W_SMEM, W_SMEM, U>(sm, g, rs, A.tw2, 1.f);
+      if (live) strided_stage<N, R2, L2, COLS, false, W_SMEM, W_SMEM, U, COLS, TH>(sm, g, rs, A.tw2, 1.f);
       __syncthreads();
-      if (live) strided_stage<N, R3, L3, COLS, false, W_SMEM, DSTG, U>(sm, g, rs, nullptr, A.scale, sc, sc_tile);
+      if (live) strided_stage<N, R3, L3, COLS, false, W_SMEM, DSTG, U, COLS, TH>(sm, g, rs, nullptr, A.scale, sc, sc_tile);
     } else {
-      if (live) strided_stage<N, R2, L2, COLS, false, W_SMEM, DSTG, U>(sm, g, rs, A.tw2, A.scale, sc, sc_tile);
+      if (live) strided_stage<N, R2, L2, COLS, false, W_SMEM, DSTG, U, COLS, TH>(sm, g, rs, A.tw2, A.scale, sc, sc_tile);
     }
   } else if (MODE == SM_INV) {
     if (RX::S == 3) {
-      if (live) strided_stage<N, R3, L3, COLS, true, W_GLOBAL, W_SMEM, U>(sm, g, rs, nullptr, 1.f);
+      if (live) strided_stage<N, R3, L3, COLS, true, W_GLOBAL, W_SMEM, U, COLS, TH>(sm, g, rs, nullptr, 1.f);
       __syncthreads();
-      if (live) strided_stage<N, R2, L2, COLS, true, W_SMEM, W_SMEM, U>(sm, g, rs, A.tw2, 1.f);
+      if (live) strided_stage<N, R2, L2, COLS, true, W_SMEM, W_SMEM, U, COLS, TH>(sm, g, rs, A.tw2, 1.f);
     } else {
-      if (live) strided_stage<N, R2, L2, COLS, true, W_GLOBAL, W_SMEM, U>(sm, g, rs, A.tw2, 1.f);
+      if (live) strided_stage<N, R2, L2, COLS, true, W_GLOBAL, W_SMEM, U, COLS, TH>(sm, g, rs, A.tw2, 1.f);
     }
     __syncthreads();
-    if (live) strided_stage<N, R1, N, COLS, true, W_SMEM, W_GLOBAL, U>(sm, g, rs, A.tw1, 1.f);
+    if (live) strided_stage<N, R1, N, COLS, true, W_SMEM, W_GLOBAL, U, COLS, TH>(sm, g, rs, A.tw1, 1.f);
   } else {  // SM_FWD_MUL_INV
-    if (live) strided_stage<N, R1, N, COLS, false, W_GLOBAL, W_SMEM, U>(sm, g, rs, A.tw1, 1.f);
+    if (live) strided_stage<N, R1, N, COLS, false, W_GLOBAL, W_SMEM, U, COLS, TH>(sm, g, rs, A.tw1, 1.f);
     if (RX::S == 3) {
-      typedef Middle<N, R3, COLS, COLS, KH> MID;
+      typedef Middle<N, R3, COLS, COLS, KH, TH> MID;
       typename MID::K kk;
       __syncthreads();
-      if (live) strided_stage<N, R2, L2, COLS, false, W_SMEM, W_SMEM, U>(sm, g, rs, A.tw2, 1.f);
+      if (live) strided_stage<N, R2, L2, COLS, false, W_SMEM, W_SMEM, U, COLS, TH>(sm, g, rs, A.tw2, 1.f);
       if (live) MID::load(kk, gk, rs, KH ? __ldg(A.khat_unscale) : 1.f);
       __syncthreads();
       if (live) MID::run(sm, kk);
       __syncthreads();
-      if (live) strided_stage<N, R2, L2, COLS, true, W_SMEM, W_SMEM, U>(sm, g, rs, A.tw2, 1.f);
+      if (live) strided_stage<N, R2, L2, COLS, true, W_SMEM, W_SMEM, U, COLS, TH>(sm, g, rs, A.tw2, 1.f);
     } else {
-      typedef Middle<N, R2, COLS, COLS, KH> MID;
+      typedef Middle<N, R2, COLS, COLS, KH, TH> MID;
       typename MID::K kk;
       if (live) MID::load(kk, gk, rs, KH ? __ldg(A.khat_unscale) : 1.f);
       __syncthreads();
       if (live) MID::run(sm, kk);
     }
     __syncthreads();
-    if (live) strided_stage<N, R1, N, COLS, true, W_SMEM, DSTG, U>(sm, g, rs, A.tw1, 1.f, sc, sc_tile);
+    if (live) strided_stage<N, R1, N, COLS, true, W_SMEM, DSTG, U, COLS, TH>(sm, g, rs, A.tw1, 1.f, sc, sc_tile);
   }
 }
 
+template <int N, int MODE> struct StridedMinBlocks {
+  static const int W = StridedBlocks<N, MODE>::V * kStridedThreads / TileThreads<N, MODE>::V;
+  static const int V = W < 1 ? 1 : W;
+};
 template <int N, int MODE, int ALT = 0, int KH = 0>
-static __global__ void __launch_bounds__(Threads<N>::V, StridedBlocks<N, MODE>::V * (kStridedThreads / Threads<N>::V))
+static __global__ void __launch_bounds__(TileThreads<N, MODE>::V, StridedMinBlocks<N, MODE>::V)
     k_strided(StridedArgs A) {
   static_assert(KH == 0 || MODE == SM_FWD_MUL_INV, "half-precision K^ is an option of the merged z pass");
   static_assert(ALT == 0 || (MODE != SM_FWD_MUL_INV && MODE != SM_FWD_MUL_INV_SCATTER), "the merged pass keeps the default plan");
-  constexpr int COLS = Cols<N>::V;
+  constexpr int COLS = TileCols<N, MODE>::V, TH = TileThreads<N, MODE>::V;
   LMVN_DYN_SMEM(cplx, smem);  // [N][COLS]
   const int c = threadIdx.x % COLS;
   constexpr bool ZMUL = (MODE == SM_FWD_MUL_INV || MODE == SM_FWD_MUL_INV_SCATTER);
@@ -516,7 +534,7 @@ static __global__ void __launch_bounds__(Threads<N>::V, StridedBlocks<N, MODE>::
   if (ZMUL && A.prefetch_khat) {
     // K^ is first needed two stages from now: start its trip from HBM to L2 right away
     const long long tb = (long long)by * A.tile_stride + bx * COLS;
-    for (int i = threadIdx.x; i < N * LINES; i += Threads<N>::V)
+    for (int i = threadIdx.x; i < N * LINES; i += TH)
       prefetch_l2(A.khat + tb + (long long)(i / LINES) * A.row_stride + (i % LINES) * 16);
   }
   if (A.prefetch > 0) {
@@ -524,7 +542,7 @@ static __global__ void __launch_bounds__(Threads<N>::V, StridedBlocks<N, MODE>::
     const long long id = tile_id + A.prefetch;
     if (id < n_tiles) {
       const long long fb = (id / tiles_x) * A.tile_stride + (id % tiles_x) * COLS;
-      for (int i = threadIdx.x; i < N * LINES; i += Threads<N>::V) {
+      for (int i = threadIdx.x; i < N * LINES; i += TH) {
         const long long off = fb + (long long)(i / LINES) * A.row_stride + (i % LINES) * 16;
         prefetch_l2(A.data + off);
       }

@@ -352,23 +352,23 @@ struct FastEngine : ConvEngine, FastOps {
 
   template <int N, int MODE, int ALT = 0>
   int launch_strided(const fast::StridedArgs& a, dim3 grid, cudaStream_t s) {
-    constexpr int COLS = fast::Cols<N>::V;
+    constexpr int COLS = fast::TileCols<N, MODE>::V;
     const size_t smem = size_t(N) * COLS * sizeof(cplx);
     auto kfn = fast::k_strided<N, MODE, ALT>;
     if (smem > 48 * 1024) {  // per device, cheap: set every time
       LMVN_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     }
-    LMVN_LAUNCH(kfn, grid, dim3(fast::Threads<N>::V), smem, s, a);
+    LMVN_LAUNCH(kfn, grid, dim3(fast::TileThreads<N, MODE>::V), smem, s, a);
     return 0;
   }
   template <int N>
   int launch_strided_khalf(const fast::StridedArgs& a, dim3 grid, cudaStream_t s) {
 #ifndef LMVN_EMU
-    constexpr int COLS = fast::Cols<N>::V;
+    constexpr int COLS = fast::TileCols<N, fast::SM_FWD_MUL_INV>::V;
     const size_t smem = size_t(N) * COLS * sizeof(cplx);
     auto kfn = fast::k_strided<N, fast::SM_FWD_MUL_INV, 0, 1>;
     if (smem > 48 * 1024) LMVN_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    LMVN_LAUNCH(kfn, grid, dim3(fast::Threads<N>::V), smem, s, a);
+    LMVN_LAUNCH(kfn, grid, dim3(fast::TileThreads<N, fast::SM_FWD_MUL_INV>::V), smem, s, a);
     return 0;
 #else
     (void)a; (void)grid; (void)s;
@@ -434,9 +434,9 @@ struct FastEngine : ConvEngine, FastOps {
     return strided_geom(g, s);
   }
 
-  int strided_tile_cols(int n) const override {
+  int strided_tile_cols(int n) const override {  // the widest tile any pass of an axis of this length uses
     switch (n) {
-      case 1024: return fast::Cols<1024>::V;
+      case 1024: return std::max(fast::Cols<1024>::V, fast::TileCols<1024, fast::SM_FWD_MUL_INV>::V);
       case 512: return fast::Cols<512>::V;
       case 256: return fast::Cols<256>::V;
       case 128: return fast::Cols<128>::V;
@@ -495,10 +495,12 @@ struct FastEngine : ConvEngine, FastOps {
     int rc;
 #define LMVN_STRIDED_CASE(NN)                                                                   \
   case NN: {                                                                                    \
-    dim3 grid(unsigned(ceil_div(size_t(win_cols), size_t(fast::Cols<NN>::V))), slow);           \
+    const bool wide = (mode == fast::SM_FWD_MUL_INV || mode == fast::SM_FWD_MUL_INV_SCATTER);   \
+    const size_t tcols = wide ? size_t(fast::TileCols<NN, fast::SM_FWD_MUL_INV>::V) : size_t(fast::Cols<NN>::V); \
+    dim3 grid(unsigned(ceil_div(size_t(win_cols), tcols)), slow);                               \
     if (g.nyq) {                                                                                \
-      a.tiles_x = int(ceil_div(size_t(M), size_t(fast::Cols<NN>::V)));                          \
-      a.nyq_groups = int(ceil_div(size_t(slow), size_t(fast::Cols<NN>::V)));                    \
+      a.tiles_x = int(ceil_div(size_t(M), tcols));                                              \
+      a.nyq_groups = int(ceil_div(size_t(slow), tcols));                                        \
       grid = dim3(unsigned(a.nyq_groups) + unsigned(a.tiles_x) * slow);                         \
     }                                                                                           \
     rc = launch_strided_axis<NN>(a, mode, grid, s, y_alt && g.tw_axis == 1);                    \
