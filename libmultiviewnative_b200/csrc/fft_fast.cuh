@@ -275,6 +275,10 @@ template <> struct TileCols<1024, 2> { static const int V = 16; };     // SM_FWD
 template <> struct TileThreads<1024, 2> { static const int V = 512; };
 template <> struct TileCols<1024, 5> { static const int V = 16; };     // SM_FWD_MUL_INV_SCATTER
 template <> struct TileThreads<1024, 5> { static const int V = 512; };
+// the scattering y pass of the slab-decomposed plans: its stores are 128-byte segments of peer memory instead of 64-byte ones
+// (link bound; the forward y pass runs equally fast on either tile shape)
+template <> struct TileCols<1024, 4> { static const int V = 16; };     // SM_FWD_SCATTER
+template <> struct TileThreads<1024, 4> { static const int V = 512; };
 #endif
 #ifndef LMVN_ZMUL_BLOCKS
 #define LMVN_ZMUL_BLOCKS 2

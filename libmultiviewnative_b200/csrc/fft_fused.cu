@@ -495,7 +495,8 @@ struct FastEngine : ConvEngine, FastOps {
     int rc;
 #define LMVN_STRIDED_CASE(NN)                                                                   \
   case NN: {                                                                                    \
-    const bool wide = (mode == fast::SM_FWD_MUL_INV || mode == fast::SM_FWD_MUL_INV_SCATTER);   \
+    const bool wide = (mode == fast::SM_FWD_MUL_INV || mode == fast::SM_FWD_MUL_INV_SCATTER ||  \
+                       mode == fast::SM_FWD_SCATTER);                                           \
     const size_t tcols = wide ? size_t(fast::TileCols<NN, fast::SM_FWD_MUL_INV>::V) : size_t(fast::Cols<NN>::V); \
     dim3 grid(unsigned(ceil_div(size_t(win_cols), tcols)), slow);                               \
     if (g.nyq) {                                                                                \

@@ -48,16 +48,22 @@ def main():
     plan.enable_nccl_comparator()
     plan.set_psi_slab(slab_of(d["psi0"], rank, world))
     plan.iterate_nccl(iters, 0.006, 1e-4)
-    nccl_same = bool(np.array_equal(plan.get_psi_slab(), mine.cpu().numpy()))
+    nccl_psi, fused_psi = plan.get_psi_slab(), mine.cpu().numpy()
+    nccl_same = bool(np.array_equal(nccl_psi, fused_psi))
+    # (the comparator drives the UNCHAINED phases; where the chained kernels of this shape contract their FMAs differently
+    # the two agree to a few ulp instead of bit for bit)
+    nccl_rel = torch.tensor([float(np.max(np.abs(nccl_psi - fused_psi) / np.abs(fused_psi)))], device="cuda")
+    dist.all_reduce(nccl_rel, op=dist.ReduceOp.MAX)
     plan.iterate_nccl(2, 0.006, 1e-4)
     tn = torch.tensor([plan.iterate_nccl(10, 0.006, 1e-4)], device="cuda")
     dist.all_reduce(tn, op=dist.ReduceOp.MAX)
     flags = torch.tensor([1.0 if nccl_same else 0.0], device="cuda")
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("slab_mp_check NCCL comparator: identical to the P2P-fused path on every rank = %s; %.3f ms/(view,iter) vs "
-              "%.3f ms fused (fused is %.2fx faster)" % (bool(flags.item() > 0), tn.item() / (10 * nv), t.item() / (10 * nv),
-                                                        tn.item() / t.item()), flush=True)
+        print("slab_mp_check NCCL comparator: identical to the P2P-fused path on every rank = %s (max rel %.2g); %.3f ms/(view,iter) vs "
+              "%.3f ms fused (fused is %.2fx faster)" % (bool(flags.item() > 0), nccl_rel.item(), tn.item() / (10 * nv),
+                                                        t.item() / (10 * nv), tn.item() / t.item()), flush=True)
+        assert nccl_rel.item() < 5e-6
         got = torch.cat(parts, 0).cpu().numpy()
         single = d["psi0"].copy()
         lib.inplace_gpu_deconvolve(single, d["views"], d["kernels1"], d["kernels2"], d["weights"], iters, 0.006, 1e-4, local)
