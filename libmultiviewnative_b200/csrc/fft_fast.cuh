@@ -1370,8 +1370,11 @@ static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_inv_wide(RowArgs
 // 128 threads per CTA, three CTAs per SM: 170 registers per thread -- the chained form keeps 32 results of the
 // inverse live through the epilogue and spills at 128
 static const int kChainWideThreads = 128;
+#ifndef LMVN_CHAIN_WIDE_BLOCKS
+#define LMVN_CHAIN_WIDE_BLOCKS 3
+#endif
 template <int EPI>
-static __global__ void __launch_bounds__(kChainWideThreads, 3) k_rows_inv_fwd_wide(RowArgs A) {
+static __global__ void __launch_bounds__(kChainWideThreads, LMVN_CHAIN_WIDE_BLOCKS) k_rows_inv_fwd_wide(RowArgs A) {
   LMVN_DYN_SMEM(cplx, sm);
   constexpr int GROUPS = kChainWideThreads / 16;
   const int lane = threadIdx.x % 16;
