@@ -11,12 +11,19 @@
 //           shared memory):  [128-point inverse along i] -> [x inverse] -> quotient / RL update -> [x forward] ->
 //           [128-point forward along i].  Everything the chained rows kernel of fft_fast.cuh did, plus seven of the
 //           nine (eight) radix-2 levels of the y transform, without touching HBM in between.
-//   pass B  "z middle"    k_zmid          the merged z pass of fft_fast.cuh (forward z, * K^, inverse z on 64 KB tiles)
-//           with the remaining radix-R2 level of y as a register stage on the way in and out: a tile holds the R2
-//           samples (n2 = 0 .. R2-1) of its short y transforms, as pieces of KXC = 16 / R2 adjacent kx columns.
+//   pass B  "z middle"    k_zmid5 / k_zmid   the merged z pass of fft_fast.cuh (forward z, * K^, inverse z on 64 KB tiles)
+//           with the remaining radix-R2 level of y as a register stage behind the first z stage and, mirrored, behind
+//           the middle stage: a tile holds the R2 samples (n2 = 0 .. R2-1) of its short y transforms, as pieces of
+//           KXC = 16 / R2 adjacent kx columns.
 //
 // HBM traffic per (view, iteration): (2C + S) + 3C + (2C + 3S) + 3C = 4S + 10C -- below the contract's 7S + 10C
 // (SURVEY.md section 8d), against 4S + 18C of the chained five-pass loop.
+//
+// STATUS: parity-green (emulator, GPU vs oracle, full config-3 size) and OPT-IN (LMVN_X3=1): measured 1.18 ms per
+// (view, iteration) on config 3 against 1.03 ms of the five-pass loop.  The plane pass wins what it should (0.28 / 0.35 ms
+// against 0.35 / 0.45 ms for y inverse + link + y forward), the z middle loses more (0.29 against 0.16 ms): its rows are
+// 32-byte pieces, and the L1/LSU pipe spends a whole wavefront on each.  DESIGN.md section 3.4 has the numbers, the ncu
+// evidence and the variants that were tried (shuffles, TMA-staged operands, L2 look-ahead, 128-bit y stages).
 //
 // Spectrum layout between the passes ("A layout"):  A[n2][z][p][kx], n2 < R2, p < 129, kx < 128 (complex64).
 //   p < 128: position p of the 128-point transform along i (16 x 8 decimation in frequency: p = 8 q1 + q2 holds
