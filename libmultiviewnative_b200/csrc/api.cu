@@ -188,7 +188,7 @@ extern "C" int lmvn_plan_get_info(const lmvn_plan* plan, lmvn_plan_info* info) {
   info->num_views = d.num_views;
   info->device = d.device;
   info->strategy = d.engine->strategy();
-  info->launches_per_view_iteration = 2 * d.engine->launches_per_conv();
+  info->launches_per_view_iteration = d.engine->launches_per_view_iteration();
   info->arena_bytes = d.arena_bytes;
   info->real_bytes = fp.voxels() * sizeof(float);
   info->spectrum_bytes = fp.spec_elems() * sizeof(cplx);

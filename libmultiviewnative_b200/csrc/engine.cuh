@@ -64,6 +64,7 @@ struct ConvEngine {
   virtual size_t khat_elems() const = 0;  // complex elements of one precomputed PSF spectrum
   virtual size_t work_elems() const = 0;  // complex elements of the spectrum work buffer
   virtual int launches_per_conv() const = 0;
+  virtual int launches_per_view_iteration() const { return 2 * launches_per_conv(); }
   // K^ = rfftn(wrap(kernel)) / N in this engine's layout.  d_kernel: device, unpadded.
   virtual int kernel_spectrum(const float* d_kernel, const int kd[3], cplx* khat, cplx* work,
                               cudaStream_t s) = 0;

@@ -91,6 +91,10 @@ struct FastEngine : ConvEngine, FastOps {
   const cplx* nyq_of(const cplx* spec) const { return split ? spec + main_elems() : nullptr; }
   size_t work_elems() const override { return khat_elems(); }
   int launches_per_conv() const override { return can_chain() ? 4 : 5; }
+  // nx = 1024: the update link is two launches (rows_inv_fwd below)
+  int launches_per_view_iteration() const override {
+    return 2 * launches_per_conv() + ((can_chain() && M == 512 && !chain_wide_update) ? 1 : 0);
+  }
   unsigned long long S() const { return plan->voxels() * sizeof(float); }
   unsigned long long C() const { return plan->spec_elems() * sizeof(cplx); }
 
@@ -123,6 +127,7 @@ struct FastEngine : ConvEngine, FastOps {
     if (const char* e = getenv("LMVN_PREFETCH_ROWS")) rows_prefetch = atoi(e);
     if (const char* e = getenv("LMVN_CHAIN")) chain_ok = (*e != '0');
     if (const char* e = getenv("LMVN_CHAIN_WIDE")) chain_wide = (*e != '0');
+    if (const char* e = getenv("LMVN_CHAIN_WIDE_UPDATE")) chain_wide_update = (*e == '1');
     if (const char* e = getenv("LMVN_ROWS_CTAS")) rows_ctas_per_sm = update_ctas_per_sm = std::max(1, atoi(e));
     {
       std::lock_guard<std::mutex> lk(plan->fast_mu);
@@ -547,6 +552,14 @@ struct FastEngine : ConvEngine, FastOps {
       set_last_error("chained rows pass: quotient or update epilogue with unit scale expected");
       return -1;
     }
+    if (M == 512 && ep.mode == gen::EPI_UPDATE && !spec_out && !chain_wide_update) {
+      // nx = 1024: the chained update link keeps 32 results of the inverse live through a three-operand epilogue (170
+      // registers, 12 warps per SM) and is SLOWER than the two passes it replaces: 6.38 ms against 4.08 + 1.44 ms at 1024^3
+      // (profiles/r02_1024_wide_tiles.log).  The quotient link stays chained (3.08 against 2.81 + 1.48 ms).
+      LMVN_TRY(rows_inv(spec, ep.psi, ep, s, 0, nzs));
+      gen::RealSource src{ep.psi, 0, 0, 0, 0};
+      return rows_fwd(src, spec, s, 0, nzs);
+    }
     fast::RowArgs a;
     std::memset(&a, 0, sizeof(a));
     a.spec = spec;
@@ -597,6 +610,7 @@ struct FastEngine : ConvEngine, FastOps {
   // nx = 1024: the chained kernel runs 128-thread CTAs (170 registers per thread: it keeps 32 results live through
   // the epilogue); +3 % over the two separate passes (LMVN_CHAIN_WIDE=0 for A/B)
   bool chain_wide = true;
+  bool chain_wide_update = false;  // LMVN_CHAIN_WIDE_UPDATE=1: chain the update link at nx = 1024 too (A/B)
   bool can_chain() const override { return chain_ok && (M <= 256 || chain_wide); }
   int chain_begin(const float* in, cplx* work, cudaStream_t s) override {
     gen::RealSource src{in, 0, 0, 0, 0};
