@@ -318,8 +318,12 @@ __device__ __forceinline__ void load_twiddles(cplx* t, const cplx* __restrict__ 
 // decimation-in-time mirror (conjugate twiddle, then butterfly).  `sm` and `g`
 // already point at this thread's column; rows are addressed with 32-bit offsets.
 // PITCH: row pitch of the shared-memory tile (the two-pass schedule pads its rows, fft_x3.cuh).
+// HV: the tile belongs to a group of THREADS threads of a larger CTA (fft_tma.cuh: two 256-thread halves, each on its own tile)
+template <int THREADS, bool HV>
+__device__ __forceinline__ int tile_tid() { return HV ? int(threadIdx.x % THREADS) : int(threadIdx.x); }
+
 template <int N, int R, int L, int COLS, bool INV, int SRC, int DST, int UNROLL = 8, int PITCH = COLS,
-          int THREADS = Threads<N>::V>
+          int THREADS = Threads<N>::V, bool HV = false>
 __device__ __forceinline__ void strided_stage(cplx* __restrict__ sm, cplx* __restrict__ g, int rs,
                                               const cplx* __restrict__ tws, float scale,
                                               const Scatter* sc = nullptr, long long sc_tile = 0) {
@@ -327,7 +331,7 @@ __device__ __forceinline__ void strided_stage(cplx* __restrict__ sm, cplx* __res
   constexpr int RG = THREADS / COLS;   // row groups per block
   constexpr int PER_THREAD = (N / R) / RG;
   static_assert(PER_THREAD >= 1, "tile too small for the block");
-  const int rg = threadIdx.x / COLS;
+  const int rg = tile_tid<THREADS, HV>() / COLS;
   // UNROLL bounds how many butterflies the compiler may interleave (register pressure)
 #pragma unroll(UNROLL)
   for (int i = 0; i < PER_THREAD; ++i) {
@@ -389,14 +393,14 @@ __device__ __forceinline__ void strided_stage(cplx* __restrict__ sm, cplx* __res
 // middle of the merged z pass: last forward stage (span R), spectrum product, first inverse stage.
 // The K^ operands come straight from HBM; middle_load() is called BEFORE the barrier that precedes
 // the middle so that their latency overlaps the barrier wait and the shared-memory reads.
-template <int N, int R, int COLS, int PITCH = COLS, int KH = 0, int THREADS = Threads<N>::V>
+template <int N, int R, int COLS, int PITCH = COLS, int KH = 0, int THREADS = Threads<N>::V, bool HV = false>
 struct Middle {
   static const int RG = THREADS / COLS;
   static const int PT = (N / R) / RG;  // butterflies per thread: 1 or 2 in every plan that is used
   struct K { cplx k[PT][R]; };
   // KH = 1: gk points at __half2 elements (4 bytes per complex value): half the K^ bytes of the pass
   static __device__ __forceinline__ void load(K& o, const cplx* __restrict__ gk, int rs, float unscale = 1.f) {
-    const int rg = threadIdx.x / COLS;
+    const int rg = tile_tid<THREADS, HV>() / COLS;
 #pragma unroll
     for (int i = 0; i < PT; ++i) {
 #if !defined(LMVN_EMU)
@@ -423,7 +427,7 @@ struct Middle {
     }
   }
   static __device__ __forceinline__ void run(cplx* __restrict__ sm, const K& o) {
-    const int rg = threadIdx.x / COLS;
+    const int rg = tile_tid<THREADS, HV>() / COLS;
 #pragma unroll
     for (int i = 0; i < PT; ++i) {
       cplx* p = sm + (rg + i * RG) * R * PITCH;
@@ -440,12 +444,27 @@ struct Middle {
   }
 };
 
+// barrier of the threads that share a tile: the whole CTA, or (HV) the 256-thread half `bar` - 1 of a two-tile CTA
+template <bool HV, int THREADS>
+__device__ __forceinline__ void tile_sync(int bar) {
+#if !defined(LMVN_EMU)
+  if (HV) {
+    asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(THREADS) : "memory");
+    return;
+  }
+#endif
+  (void)bar;
+  __syncthreads();
+}
+
 // One tile of a strided pass.  `sm`, `g`, `gk` already point at this thread's column; threads of
 // the padding columns of a ragged last tile pass live = false: they skip the stages (every stage
 // touches the thread's own column only) but still take part in the barriers.
-template <int N, int MODE_, int U, int ALT = 0, int KH = 0>
+// SRC1 = W_SMEM: the tile has already been brought into `sm` (bulk tensor copy, fft_tma.cuh) and the first stage works in
+// place on it; HV / bar: see tile_sync.
+template <int N, int MODE_, int U, int ALT = 0, int KH = 0, int SRC1 = W_GLOBAL, bool HV = false>
 __device__ __forceinline__ void strided_tile(const StridedArgs& A, cplx* sm, cplx* g, const cplx* gk, bool live,
-                                             long long sc_tile, int rs) {
+                                             long long sc_tile, int rs, int bar = 0) {
   typedef Plan<N, ALT> RX;
   constexpr int COLS = TileCols<N, MODE_>::V, TH = TileThreads<N, MODE_>::V;
   constexpr int R1 = RX::R1, R2 = RX::R2;
@@ -456,46 +475,46 @@ __device__ __forceinline__ void strided_tile(const StridedArgs& A, cplx* sm, cpl
   constexpr int DSTG = SCAT ? W_SCATTER : ((MODE == SM_FWD_SCALE) ? W_GLOBAL_SCALED : W_GLOBAL);
   const Scatter* sc = &A.sc;
   if (MODE == SM_FWD || MODE == SM_FWD_SCALE) {
-    if (live) strided_stage<N, R1, N, COLS, false, W_GLOBAL, W_SMEM, U, COLS, TH>(sm, g, rs, A.tw1, 1.f);
-    __syncthreads();
+    if (live) strided_stage<N, R1, N, COLS, false, SRC1, W_SMEM, U, COLS, TH, HV>(sm, g, rs, A.tw1, 1.f);
+    tile_sync<HV, TH>(bar);
     if (RX::S == 3) {
-      if (live) strided_stage<N, R2, L2, COLS, false, W_SMEM, W_SMEM, U, COLS, TH>(sm, g, rs, A.tw2, 1.f);
-      __syncthreads();
-      if (live) strided_stage<N, R3, L3, COLS, false, W_SMEM, DSTG, U, COLS, TH>(sm, g, rs, nullptr, A.scale, sc, sc_tile);
+      if (live) strided_stage<N, R2, L2, COLS, false, W_SMEM, W_SMEM, U, COLS, TH, HV>(sm, g, rs, A.tw2, 1.f);
+      tile_sync<HV, TH>(bar);
+      if (live) strided_stage<N, R3, L3, COLS, false, W_SMEM, DSTG, U, COLS, TH, HV>(sm, g, rs, nullptr, A.scale, sc, sc_tile);
     } else {
-      if (live) strided_stage<N, R2, L2, COLS, false, W_SMEM, DSTG, U, COLS, TH>(sm, g, rs, A.tw2, A.scale, sc, sc_tile);
+      if (live) strided_stage<N, R2, L2, COLS, false, W_SMEM, DSTG, U, COLS, TH, HV>(sm, g, rs, A.tw2, A.scale, sc, sc_tile);
     }
   } else if (MODE == SM_INV) {
     if (RX::S == 3) {
-      if (live) strided_stage<N, R3, L3, COLS, true, W_GLOBAL, W_SMEM, U, COLS, TH>(sm, g, rs, nullptr, 1.f);
-      __syncthreads();
-      if (live) strided_stage<N, R2, L2, COLS, true, W_SMEM, W_SMEM, U, COLS, TH>(sm, g, rs, A.tw2, 1.f);
+      if (live) strided_stage<N, R3, L3, COLS, true, SRC1, W_SMEM, U, COLS, TH, HV>(sm, g, rs, nullptr, 1.f);
+      tile_sync<HV, TH>(bar);
+      if (live) strided_stage<N, R2, L2, COLS, true, W_SMEM, W_SMEM, U, COLS, TH, HV>(sm, g, rs, A.tw2, 1.f);
     } else {
-      if (live) strided_stage<N, R2, L2, COLS, true, W_GLOBAL, W_SMEM, U, COLS, TH>(sm, g, rs, A.tw2, 1.f);
+      if (live) strided_stage<N, R2, L2, COLS, true, SRC1, W_SMEM, U, COLS, TH, HV>(sm, g, rs, A.tw2, 1.f);
     }
-    __syncthreads();
-    if (live) strided_stage<N, R1, N, COLS, true, W_SMEM, W_GLOBAL, U, COLS, TH>(sm, g, rs, A.tw1, 1.f);
+    tile_sync<HV, TH>(bar);
+    if (live) strided_stage<N, R1, N, COLS, true, W_SMEM, W_GLOBAL, U, COLS, TH, HV>(sm, g, rs, A.tw1, 1.f);
   } else {  // SM_FWD_MUL_INV
-    if (live) strided_stage<N, R1, N, COLS, false, W_GLOBAL, W_SMEM, U, COLS, TH>(sm, g, rs, A.tw1, 1.f);
+    if (live) strided_stage<N, R1, N, COLS, false, SRC1, W_SMEM, U, COLS, TH, HV>(sm, g, rs, A.tw1, 1.f);
     if (RX::S == 3) {
-      typedef Middle<N, R3, COLS, COLS, KH, TH> MID;
+      typedef Middle<N, R3, COLS, COLS, KH, TH, HV> MID;
       typename MID::K kk;
-      __syncthreads();
-      if (live) strided_stage<N, R2, L2, COLS, false, W_SMEM, W_SMEM, U, COLS, TH>(sm, g, rs, A.tw2, 1.f);
+      tile_sync<HV, TH>(bar);
+      if (live) strided_stage<N, R2, L2, COLS, false, W_SMEM, W_SMEM, U, COLS, TH, HV>(sm, g, rs, A.tw2, 1.f);
       if (live) MID::load(kk, gk, rs, KH ? __ldg(A.khat_unscale) : 1.f);
-      __syncthreads();
+      tile_sync<HV, TH>(bar);
       if (live) MID::run(sm, kk);
-      __syncthreads();
-      if (live) strided_stage<N, R2, L2, COLS, true, W_SMEM, W_SMEM, U, COLS, TH>(sm, g, rs, A.tw2, 1.f);
+      tile_sync<HV, TH>(bar);
+      if (live) strided_stage<N, R2, L2, COLS, true, W_SMEM, W_SMEM, U, COLS, TH, HV>(sm, g, rs, A.tw2, 1.f);
     } else {
-      typedef Middle<N, R2, COLS, COLS, KH, TH> MID;
+      typedef Middle<N, R2, COLS, COLS, KH, TH, HV> MID;
       typename MID::K kk;
       if (live) MID::load(kk, gk, rs, KH ? __ldg(A.khat_unscale) : 1.f);
-      __syncthreads();
+      tile_sync<HV, TH>(bar);
       if (live) MID::run(sm, kk);
     }
-    __syncthreads();
-    if (live) strided_stage<N, R1, N, COLS, true, W_SMEM, DSTG, U, COLS, TH>(sm, g, rs, A.tw1, 1.f, sc, sc_tile);
+    tile_sync<HV, TH>(bar);
+    if (live) strided_stage<N, R1, N, COLS, true, W_SMEM, DSTG, U, COLS, TH, HV>(sm, g, rs, A.tw1, 1.f, sc, sc_tile);
   }
 }
 

@@ -19,6 +19,7 @@
 
 #include "engine.cuh"
 #include "fft_fast.cuh"
+#include "fft_tma.cuh"
 #include "fft_x3.cuh"
 
 namespace lmvn {
@@ -72,6 +73,12 @@ struct FastEngine : ConvEngine, FastOps {
   int y_inv_prefetch = 0, z_prefetch = 0;  // measured: no gain for these two
   int khat_prefetch = 0;  // measured: hurts the z pass (plane-strided lines), kept as a knob
   int rows_prefetch = 1;
+  // OPT-IN (LMVN_TMA = mask of passes: 1 y forward, 2 y inverse, 4 merged z; 7 = all): strided passes of 512- and 256-point
+  // axes as persistent kernels fed by the TMA engine (fft_tma.cuh).  Bit-identical to k_strided and measured SLOWER on B200
+  // (config 3: y passes 0.112 against 0.093 ms, z pass 0.160 against 0.156 ms; 256^3: y 0.033 against 0.025 ms --
+  // profiles/r02_tma_strided_probe.log): 128 KB of the SM's shared memory are tiles in work, what is left holds ONE 64 KB tile
+  // in flight, less than the two co-resident CTAs of k_strided keep in flight in their registers.
+  int use_tma = 0;
   cplx* d_tw_m = nullptr;
   cplx* d_tw_nx = nullptr;
   cplx* d_tw_h = nullptr;
@@ -125,6 +132,7 @@ struct FastEngine : ConvEngine, FastOps {
     if (const char* e = getenv("LMVN_PREFETCH_Z")) z_prefetch = std::max(0, atoi(e));
     if (const char* e = getenv("LMVN_PREFETCH_KHAT")) khat_prefetch = atoi(e);
     if (const char* e = getenv("LMVN_PREFETCH_ROWS")) rows_prefetch = atoi(e);
+    if (const char* e = getenv("LMVN_TMA")) use_tma = atoi(e);
     if (const char* e = getenv("LMVN_CHAIN")) chain_ok = (*e != '0');
     if (const char* e = getenv("LMVN_CHAIN_WIDE")) chain_wide = (*e != '0');
     if (const char* e = getenv("LMVN_CHAIN_WIDE_UPDATE")) chain_wide_update = (*e == '1');
@@ -413,6 +421,80 @@ struct FastEngine : ConvEngine, FastOps {
     }
   }
 
+#ifndef LMVN_EMU
+  // ---- persistent TMA-fed strided passes (fft_tma.cuh) ----
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+      void* p = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+          q != cudaDriverEntryPointSuccess)
+        return nullptr;
+      return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+  }
+  // tensor map [slow][row][2 M floats] of a spectrum in the split layout; box = 16 complex columns x up to 256 rows
+  int spectrum_tensor_map(CUtensorMap* map, cplx* data, int n, long long row_stride, long long tile_stride, unsigned slow) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) { set_last_error("cuTensorMapEncodeTiled is not available"); return -1; }
+    const cuuint64_t gdim[3] = {cuuint64_t(2 * M), cuuint64_t(n), cuuint64_t(slow)};
+    const cuuint64_t gstr[2] = {cuuint64_t(row_stride) * sizeof(cplx), cuuint64_t(tile_stride) * sizeof(cplx)};
+    const cuuint32_t box[3] = {32, cuuint32_t(n < 256 ? n : 256), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, data, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed (%d)", int(r)); return -1; }
+    return 0;
+  }
+  bool tma_shape_ok(const fast::StridedArgs& a, const StridedGeom& g) const {
+    const int bit = (g.mode == fast::SM_FWD) ? 1 : (g.mode == fast::SM_INV ? 2 : 4);  // LMVN_TMA is a mask of passes
+    if (!(use_tma & bit) || !g.nyq || g.ncols > 0 || g.khat_half || (y_alt && g.tw_axis == 1)) return false;
+    if (g.mode != fast::SM_FWD && g.mode != fast::SM_INV && g.mode != fast::SM_FWD_MUL_INV) return false;
+    if (M % 16 != 0 || a.ncols != M || !encode_tiled()) return false;
+    return g.n == 512 || g.n == 256;
+  }
+  template <int N, int MODE>
+  int launch_strided_tma(const fast::StridedArgs& a, const CUtensorMap& map, long long n_tiles, cudaStream_t s) {
+    auto kfn = tma::k_strided_tma<N, MODE>;
+    const size_t smem = tma::Cfg<N>::SMEM;
+    LMVN_CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const long long items = n_tiles + a.nyq_groups;
+    const dim3 grid(unsigned(std::min<long long>(num_sms, (items + 1) / 2)));
+    static const bool dbg = getenv("LMVN_TMA_SYNC") != nullptr;  // debugging aid: localise a failing launch
+    if (dbg) {
+      const cudaError_t e0 = cudaStreamSynchronize(s);
+      if (e0 != cudaSuccess) { set_last_error("before TMA pass N=%d mode=%d: %s", N, MODE, cudaGetErrorString(e0)); return -1; }
+    }
+    LMVN_LAUNCH(kfn, grid, dim3(tma::kThreads), smem, s, map, a, int(n_tiles));
+    if (dbg) {
+      const cudaError_t e1 = cudaStreamSynchronize(s);
+      fprintf(stderr, "[tma] N=%d mode=%d data=%p khat=%p rs=%d ts=%lld slow=%u tiles=%d grid=%u: %s\n", N, MODE, (void*)a.data,
+              (const void*)a.khat, a.row_stride, a.tile_stride, a.slow, int(n_tiles), grid.x, cudaGetErrorString(e1));
+      if (e1 != cudaSuccess) { set_last_error("TMA pass N=%d mode=%d: %s", N, MODE, cudaGetErrorString(e1)); return -1; }
+    }
+    return 0;
+  }
+  template <int N>
+  int strided_tma(fast::StridedArgs a, const StridedGeom& g, cudaStream_t s) {
+    a.tiles_x = M / 16;
+    a.nyq_groups = int(ceil_div(size_t(g.slow), size_t(16)));
+    a.prefetch = 0;
+    a.prefetch_khat = 0;
+    CUtensorMap map;
+    LMVN_TRY(spectrum_tensor_map(&map, a.data, N, a.row_stride, a.tile_stride, g.slow));
+    const long long n_tiles = (long long)a.tiles_x * g.slow;
+    switch (g.mode) {
+      case fast::SM_FWD: return launch_strided_tma<N, fast::SM_FWD>(a, map, n_tiles, s);
+      case fast::SM_INV: return launch_strided_tma<N, fast::SM_INV>(a, map, n_tiles, s);
+      default: return launch_strided_tma<N, fast::SM_FWD_MUL_INV>(a, map, n_tiles, s);
+    }
+  }
+#endif
+
   // axis 1 = y, axis 0 = z
   int strided(cplx* data, const cplx* khat, int axis, int mode, float scale, cudaStream_t s, int z0 = 0,
               int nzs = -1) {
@@ -498,6 +580,16 @@ struct FastEngine : ConvEngine, FastOps {
     }
     const unsigned slow = g.slow;
     int rc;
+#ifndef LMVN_EMU
+    if (tma_shape_ok(a, g)) {
+      if (g.n == 512) LMVN_TRY(strided_tma<512>(a, g, s));
+      else LMVN_TRY(strided_tma<256>(a, g, s));
+      LMVN_CUDA_TRY(cudaGetLastError());
+      if (mode == fast::SM_FWD_MUL_INV) mark("fast_z_mul", 3 * C(), s);
+      else mark(g.tw_axis == 1 ? (mode == fast::SM_INV ? "fast_y_inv" : "fast_y_fwd") : "fast_z", 2 * C(), s);
+      return 0;
+    }
+#endif
 #define LMVN_STRIDED_CASE(NN)                                                                   \
   case NN: {                                                                                    \
     const bool wide = (mode == fast::SM_FWD_MUL_INV || mode == fast::SM_FWD_MUL_INV_SCATTER ||  \

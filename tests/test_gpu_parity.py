@@ -325,6 +325,27 @@ def test_half_precision_psf_spectra_opt_in(L, monkeypatch):
     pc.case_deconvolve_vs_oracle(L, dims, 3, 31, 0.006, iters_list=(1,), n_sources=200)
 
 
+# ---- opt-in TMA-fed strided passes (LMVN_TMA=7, csrc/fft_tma.cuh) -------------------------------------------------
+@pytest.mark.parametrize("dims", [(512, 256, 64), (256, 512, 128)])
+def test_tma_fed_strided_passes_opt_in(L, monkeypatch, dims):
+    """persistent strided passes fed by cp.async.bulk.tensor (tile ring, mbarriers, two 256-thread halves per CTA) on the
+    512- and 256-point axes: the same stage code on the same data as k_strided, so the loop must be BIT-identical to the
+    default build (10 iterations: enough launches for the halves of a CTA to drift apart -- the race the first version
+    had) and within the parity tolerance of the oracle."""
+    from libmultiviewnative_b200.synthetic import make_views
+
+    d = make_views(dims, num_views=2, kernel_size=15, n_sources=100, workers=4)
+    res = {}
+    for mask in ("0", "7"):
+        monkeypatch.setenv("LMVN_TMA", mask)
+        psi = d["psi0"].copy()
+        L.inplace_gpu_deconvolve(psi, d["views"], d["kernels1"], d["kernels2"], d["weights"], 10, 0.006, 1e-4)
+        res[mask] = psi
+    assert np.array_equal(res["0"], res["7"])
+    monkeypatch.setenv("LMVN_TMA", "7")
+    pc.case_deconvolve_vs_oracle(L, dims, 2, 15, 0.006, iters_list=(1,), n_sources=100)
+
+
 # ---- the callers either side of the path (SURVEY §8f-2, f-3) through the CUDA entry point -------------------
 def test_tiler_through_the_gpu_entry_point(L):
     """block tiler with halo (ref: tests/tiff_fixtures.hpp:225-258): every block is one inplace_gpu_deconvolve

@@ -18,7 +18,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from libmultiviewnative_b200 import load  # noqa: E402
 from libmultiviewnative_b200.synthetic import make_views_fast  # noqa: E402
 
-KNOBS = ("LMVN_LINK_REVERSE", "LMVN_L2_CARRY", "LMVN_L2_KEEP_MB", "LMVN_PREFETCH", "LMVN_X3")
+KNOBS = ("LMVN_LINK_REVERSE", "LMVN_TMA", "LMVN_PREFETCH", "LMVN_X3", "LMVN_GRAPH")
 
 
 def run(lib, d, dims, nv, iters, env, long_iters):
