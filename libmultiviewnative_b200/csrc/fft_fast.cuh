@@ -1106,21 +1106,27 @@ static __global__ void __launch_bounds__(kLinkThreads, LMVN_LINK_BLOCKS) k_rows_
 
 // ------------------------------------------------------------------------------
 // x passes for nx = 1024 (M = 512 complex samples per row).  One more radix-2 level
-// around the M = 256 scheme, decimation in time: a lane loads float4 = one even and one
-// odd complex sample (16 lanes x 16 B = two full lines), runs the two 256-point
-// sub-transforms E, O exactly like the M = 256 kernel (radix 16, exchange, radix 16,
-// exchange to natural order) and fuses the last butterfly Z[k] = E[k] + w_512^k O[k],
-// Z[k+256] = E[k] - w_512^k O[k] into the real-transform split: the pair (k, 512-k)
-// needs Z[k] and Z[256 + (256-k)] = E[256-k] + conj(w_512^k) O[256-k].  The inverse is
-// the mirror; E'[k], O'[k] for k = lane + 16 i are exactly the inputs of the lane's
+// around the M = 256 scheme, decimation in time, and ONE WARP PER ROW: the half-warp
+// h = 0 owns the even complex samples (sub-transform E), h = 1 the odd ones (O).  Lane
+// (h, j) loads float2 = complex sample 2 (j + 16 r) + h, so a warp-wide access is 256
+// contiguous bytes; each half-warp runs its 256-point sub-transform exactly like the
+// M = 256 kernel (radix 16, exchange, radix 16, exchange to natural order, slabs se / so)
+// and the last butterfly Z[k] = E[k] + w_512^k O[k], Z[k+256] = E[k] - w_512^k O[k] is
+// fused into the real-transform split, 8 (k, 512-k) pairs per lane: the pair needs Z[k]
+// and Z[256 + (256-k)] = E[256-k] + conj(w_512^k) O[256-k].  The inverse is the mirror;
+// E'[k] (h = 0) / O'[k] (h = 1) for k = j + 16 i are exactly the inputs of the lane's
 // first inverse radix-16, so the un-combine costs no extra exchange.
+// (Until round 2 a 16-lane group held BOTH sub-transforms of a row, 32 complex values per
+// lane: the chained kernel needed 170 registers, 12 warps per SM, and ran at 3.4-4.3 TB/s.
+// With 16 values per lane the chained kernels fit 128 registers like the M <= 256 ones;
+// the arithmetic per element is unchanged -- results are bit-identical.)
 // ------------------------------------------------------------------------------
 struct RowWide {
   static const int H = 256, M = 512, NX = 1024;
   static const int RS = 272;                 // 17 * 16: pitch of one half-length slab
   static const int SLAB = 2 * RS;            // E and O (>= 512: also holds Z in natural order)
-  static const int GROUPS = kRowThreads / 16;
-  static const int ROWS = GROUPS;            // one row per 16-lane group and iteration
+  static const int GROUPS = kRowThreads / 32;
+  static const int ROWS = GROUPS;            // one row per warp and iteration
   static const int SMEM = GROUPS * SLAB * int(sizeof(cplx));
 };
 
@@ -1139,83 +1145,64 @@ __device__ __forceinline__ void st_stream4(float4* p, float4 v) {
 #endif
 }
 
-template <bool WRAPPED>
-__device__ __forceinline__ void rows_fwd_wide_from_regs(const RowArgs& A, cplx* slab, long long row, int lane, cplx* ve,
-                                                        cplx* vo);
+// v[r] = complex sample 2 m + h of the row, m = j + 16 r (lane = 16 h + j)
+__device__ __forceinline__ void rows_fwd_wide_from_regs(const RowArgs& A, cplx* slab, long long row, int lane, cplx* v);
 
 template <bool WRAPPED>
 __device__ __forceinline__ void rows_fwd_wide_group(const RowArgs& A, cplx* slab, long long row, int lane) {
   constexpr int nx = RowWide::NX;
-  cplx ve[16], vo[16];
+  const int h = lane >> 4, j = lane & 15;
+  cplx v[16];
   if (!WRAPPED) {
-    const float4* in = reinterpret_cast<const float4*>(A.src.data + row * nx);
+    const float2* in = reinterpret_cast<const float2*>(A.src.data + row * nx);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      const float4 f = ld_stream4(in + lane + 16 * r);
-      ve[r] = cmake(f.x, f.y);
-      vo[r] = cmake(f.z, f.w);
-    }
+    for (int r = 0; r < 16; ++r) v[r] = ld_stream(in + 2 * (j + 16 * r) + h);
   } else {
     const int z = int(row / A.ny) + A.z0, y = int(row % A.ny);
     const int sz = gen::wrap_src_index(z, A.nz_wrap, A.src.kz);
     const int sy = gen::wrap_src_index(y, A.ny, A.src.ky);
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
-      float f[4] = {0.f, 0.f, 0.f, 0.f};
+      float f[2] = {0.f, 0.f};
       if (sz >= 0 && sy >= 0) {
         const float* kr = A.src.data + (size_t(sz) * A.src.ky + sy) * A.src.kx;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int sx = gen::wrap_src_index(4 * (lane + 16 * r) + c, nx, A.src.kx);
+        for (int c = 0; c < 2; ++c) {
+          const int sx = gen::wrap_src_index(4 * (j + 16 * r) + 2 * h + c, nx, A.src.kx);
           if (sx >= 0) f[c] = kr[sx];
         }
       }
-      ve[r] = cmake(f[0], f[1]);
-      vo[r] = cmake(f[2], f[3]);
+      v[r] = cmake(f[0], f[1]);
     }
   }
-  rows_fwd_wide_from_regs<WRAPPED>(A, slab, row, lane, ve, vo);
+  rows_fwd_wide_from_regs(A, slab, row, lane, v);
 }
 
-// ve[r], vo[r] = complex samples 2m, 2m+1 with m = lane + 16 r
-template <bool WRAPPED>
-__device__ __forceinline__ void rows_fwd_wide_from_regs(const RowArgs& A, cplx* slab, long long row, int lane, cplx* ve,
-                                                        cplx* vo) {
+__device__ __forceinline__ void rows_fwd_wide_from_regs(const RowArgs& A, cplx* slab, long long row, int lane, cplx* v) {
   constexpr int H = RowWide::H, M = RowWide::M, RS = RowWide::RS;
-  cplx* se = slab;
-  cplx* so = slab + RS;
-  Bfly<16, false>::run(ve);
-  Bfly<16, false>::run(vo);
+  const int h = lane >> 4, j = lane & 15;
+  cplx* sh = slab + h * RS;  // this half-warp's sub-transform
+  const cplx* se = slab;
+  const cplx* so = slab + RS;
+  Bfly<16, false>::run(v);
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
-    cplx a = ve[q], b = vo[q];
-    if (q > 0) {
-      const cplx w = __ldg(A.tw_h + lane * q);
-      a = cmul(a, w);
-      b = cmul(b, w);
-    }
-    se[q * 17 + lane] = a;
-    so[q * 17 + lane] = b;
+    cplx a = v[q];
+    if (q > 0) a = cmul(a, __ldg(A.tw_h + j * q));
+    sh[q * 17 + j] = a;
   }
   __syncwarp();
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    ve[j] = se[lane * 17 + j];
-    vo[j] = so[lane * 17 + j];
-  }
-  Bfly<16, false>::run(ve);
-  Bfly<16, false>::run(vo);
+  for (int t = 0; t < 16; ++t) v[t] = sh[j * 17 + t];
+  Bfly<16, false>::run(v);
   __syncwarp();
 #pragma unroll
-  for (int q2 = 0; q2 < 16; ++q2) {  // E[k], O[k], k = lane + 16 q2, natural order
-    se[lane + 16 * q2] = ve[q2];
-    so[lane + 16 * q2] = vo[q2];
-  }
+  for (int q2 = 0; q2 < 16; ++q2) sh[j + 16 * q2] = v[q2];  // E[k] / O[k], k = j + 16 q2, natural order
   __syncwarp();
   cplx* orow = A.spec + row * A.nxp;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int k = lane + 16 * i;
+  for (int i = 0; i < 8; ++i) {
+    const int k = lane + 32 * i;
     if (k == 0) {
       const cplx e0 = se[0], o0 = so[0];
       const cplx z0 = cadd(e0, o0), zh = csub(e0, o0);  // Z[0], Z[256]
@@ -1238,11 +1225,12 @@ __device__ __forceinline__ void rows_fwd_wide_from_regs(const RowArgs& A, cplx* 
 template <int EPI, bool CHAIN = false>
 __device__ __forceinline__ void rows_inv_wide_group(const RowArgs& A, cplx* slab, long long row, int lane) {
   constexpr int H = RowWide::H, M = RowWide::M, nx = RowWide::NX, RS = RowWide::RS;
+  const int h = lane >> 4, j = lane & 15;
   const cplx* irow = A.spec + row * A.nxp;
   // ---- loads + inverse split: Z in natural order ----
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int k = lane + 16 * i;
+  for (int i = 0; i < 8; ++i) {
+    const int k = lane + 32 * i;
     const cplx xk = ld_stream(irow + k);
     const cplx xm = ld_stream((k == 0 && A.nyq) ? A.nyq + row : irow + (M - k));  // k = 0 reads X[512]
     if (k == 0) {
@@ -1256,167 +1244,122 @@ __device__ __forceinline__ void rows_inv_wide_group(const RowArgs& A, cplx* slab
       slab[M - k] = zm;
     }
   }
+  // epilogue operands: element n = 2 (j + 16 r) + h of the row = real samples 2n, 2n+1 (this lane's results); fetched
+  // now so that their latency overlaps the transform
+  float* obase = (EPI == gen::EPI_UPDATE) ? A.ep.psi : A.out;
+  float2* orow = reinterpret_cast<float2*>(obase + row * nx);
+  float2 oa[16], ob[16];
+  if (EPI != gen::EPI_STORE) {
+    const float2* pa = reinterpret_cast<const float2*>((EPI == gen::EPI_QUOTIENT ? A.ep.view : A.ep.psi) + row * nx);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) oa[r] = ld_stream(pa + 2 * (j + 16 * r) + h);
+  }
   __syncwarp();
-  // ---- un-combine: E'[k] = Z[k] + Z[k+256], O'[k] = (Z[k] - Z[k+256]) conj(w_512^k), k = lane + 16 i ----
-  cplx ve[16], vo[16];
+  // ---- un-combine: E'[k] = Z[k] + Z[k+256] (h = 0), O'[k] = (Z[k] - Z[k+256]) conj(w_512^k) (h = 1), k = j + 16 i ----
+  cplx v[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const int k = lane + 16 * i;
+    const int k = j + 16 * i;
     const cplx a = slab[k], b = slab[k + H];
-    ve[i] = cadd(a, b);
-    const cplx d = csub(a, b);
-    vo[i] = (k == 0) ? d : cmulc(d, __ldg(A.tw_m + k));
+    if (h == 0) {
+      v[i] = cadd(a, b);
+    } else {
+      const cplx d = csub(a, b);
+      v[i] = (k == 0) ? d : cmulc(d, __ldg(A.tw_m + k));
+    }
   }
-  // these are the inputs Z[q_blk + 16 q2] of the lane's first inverse radix-16 (q_blk = lane)
-  Bfly<16, true>::run(ve);
-  Bfly<16, true>::run(vo);
+  // these are the inputs Z[q_blk + 16 q2] of the lane's first inverse radix-16 (q_blk = j)
+  Bfly<16, true>::run(v);
   __syncwarp();
-  cplx* se = slab;
-  cplx* so = slab + RS;
+  cplx* sh = slab + h * RS;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    se[lane * 17 + j] = ve[j];
-    so[lane * 17 + j] = vo[j];
-  }
+  for (int t = 0; t < 16; ++t) sh[j * 17 + t] = v[t];
   __syncwarp();
+  if (EPI == gen::EPI_UPDATE) {
+    const float2* pb = reinterpret_cast<const float2*>(A.ep.weights + row * nx);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) ob[r] = ld_stream(pb + 2 * (j + 16 * r) + h);
+  }
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
-    cplx a = se[q * 17 + lane], b = so[q * 17 + lane];
-    if (q > 0) {
-      const cplx w = __ldg(A.tw_h + lane * q);
-      a = cmulc(a, w);
-      b = cmulc(b, w);
-    }
-    ve[q] = a;
-    vo[q] = b;
+    cplx a = sh[q * 17 + j];
+    if (q > 0) a = cmulc(a, __ldg(A.tw_h + j * q));
+    v[q] = a;
   }
-  Bfly<16, true>::run(ve);
-  Bfly<16, true>::run(vo);
-  // ve[r], vo[r] = complex samples 2m, 2m+1 with m = lane + 16 r = real samples 4m .. 4m+3
-  float* obase = (EPI == gen::EPI_UPDATE) ? A.ep.psi : A.out;
-  float4* orow = reinterpret_cast<float4*>(obase + row * nx);
-  const float4* pa = reinterpret_cast<const float4*>((EPI == gen::EPI_QUOTIENT ? A.ep.view : A.ep.psi) + row * nx);
-  const float4* pb = reinterpret_cast<const float4*>(A.ep.weights + row * nx);
-  // operands CH float4 at a time (register budget; the chained form keeps all 32 results live)
-  constexpr int CH = CHAIN ? (EPI == gen::EPI_UPDATE ? 2 : 4) : (EPI == gen::EPI_UPDATE ? 4 : 8);
+  Bfly<16, true>::run(v);
+  // v[r] = complex sample 2 m + h, m = j + 16 r = real samples 4 m + 2 h, 4 m + 2 h + 1 (1/N lives in K^: no scale here)
 #pragma unroll
-  for (int h = 0; h < 16 / CH; ++h) {
-    float4 oa[CH], ob[CH];
-    if (EPI != gen::EPI_STORE) {
-#pragma unroll
-      for (int r = 0; r < CH; ++r) oa[r] = ld_stream4(pa + lane + 16 * (CH * h + r));
+  for (int r = 0; r < 16; ++r) {
+    float2 val = v[r];
+    if (EPI == gen::EPI_QUOTIENT) {
+      val.x = quotient(oa[r].x, val.x, A.ep.zero_view_guard);
+      val.y = quotient(oa[r].y, val.y, A.ep.zero_view_guard);
+    } else if (EPI == gen::EPI_UPDATE) {
+      val.x = rl_update(oa[r].x, val.x, ob[r].x, A.ep.up);
+      val.y = rl_update(oa[r].y, val.y, ob[r].y, A.ep.up);
     }
-    if (EPI == gen::EPI_UPDATE) {
-#pragma unroll
-      for (int r = 0; r < CH; ++r) ob[r] = ld_stream4(pb + lane + 16 * (CH * h + r));
-    }
-#pragma unroll
-    for (int r = 0; r < CH; ++r) {
-      const int rr = CH * h + r;
-      float4 val = make_float4(ve[rr].x, ve[rr].y, vo[rr].x, vo[rr].y);  // 1/N lives in K^: no scale here
-      if (EPI == gen::EPI_QUOTIENT) {
-        const int zg = A.ep.zero_view_guard;
-        val.x = quotient(oa[r].x, val.x, zg); val.y = quotient(oa[r].y, val.y, zg);
-        val.z = quotient(oa[r].z, val.z, zg); val.w = quotient(oa[r].w, val.w, zg);
-      } else if (EPI == gen::EPI_UPDATE) {
-        val.x = rl_update(oa[r].x, val.x, ob[r].x, A.ep.up); val.y = rl_update(oa[r].y, val.y, ob[r].y, A.ep.up);
-        val.z = rl_update(oa[r].z, val.z, ob[r].z, A.ep.up); val.w = rl_update(oa[r].w, val.w, ob[r].w, A.ep.up);
-      }
-      if (!CHAIN || EPI == gen::EPI_UPDATE) st_stream4(orow + lane + 16 * rr, val);
-      if (CHAIN) {
-        ve[rr] = cmake(val.x, val.y);
-        vo[rr] = cmake(val.z, val.w);
-      }
-    }
-#if !defined(LMVN_EMU) && defined(__CUDA_ARCH__)
-    if (CHAIN) asm volatile("" ::: "memory");  // keep the operand loads of the next chunk from being hoisted (spills)
-#endif
-  }
-  if (CHAIN) {
-    __syncwarp();
-    rows_fwd_wide_from_regs<false>(A, slab, row, lane, ve, vo);
-    return;
+    if (!CHAIN || EPI == gen::EPI_UPDATE) st_stream(orow + 2 * (j + 16 * r) + h, val);
+    if (CHAIN) v[r] = val;
   }
   __syncwarp();
+  if (CHAIN) rows_fwd_wide_from_regs(A, slab, row, lane, v);
 }
 
 template <bool WRAPPED>
 static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_fwd_wide(RowArgs A) {
   LMVN_DYN_SMEM(cplx, sm);
-  const int lane = threadIdx.x % 16;
-  const int group = threadIdx.x / 16;
+  const int lane = threadIdx.x % 32;
+  const int group = threadIdx.x / 32;
   cplx* slab = sm + group * RowWide::SLAB;
   const long long rows = (long long)A.nz * A.ny;
   const long long stride = (long long)gridDim.x * RowWide::ROWS;
   for (long long row = (long long)blockIdx.x * RowWide::ROWS + group; row < rows; row += stride) {
-    if (!WRAPPED && A.prefetch && row + stride < rows) {  // next iteration's row: 4 KB = 32 lines
-      const char* nxt = reinterpret_cast<const char*>(A.src.data + (row + stride) * RowWide::NX);
-      prefetch_l2(nxt + lane * 128);
-      prefetch_l2(nxt + 2048 + lane * 128);
-    }
+    if (!WRAPPED && A.prefetch && row + stride < rows)  // next iteration's row: 4 KB = 32 lines
+      prefetch_l2(reinterpret_cast<const char*>(A.src.data + (row + stride) * RowWide::NX) + lane * 128);
     rows_fwd_wide_group<WRAPPED>(A, slab, row, lane);
   }
+}
+
+// next iteration's spectrum row and operand rows into L2
+template <int EPI>
+__device__ __forceinline__ void rows_wide_prefetch(const RowArgs& A, long long nr, int lane) {
+  const char* sp = reinterpret_cast<const char*>(A.spec + nr * A.nxp);
+  for (int b = lane * 128; b < A.nxp * int(sizeof(cplx)); b += 32 * 128) prefetch_l2(sp + b);
+  if (EPI != gen::EPI_STORE)
+    prefetch_l2(reinterpret_cast<const char*>((EPI == gen::EPI_QUOTIENT ? A.ep.view : A.ep.psi) + nr * RowWide::NX) + lane * 128);
+  if (EPI == gen::EPI_UPDATE)
+    prefetch_l2(reinterpret_cast<const char*>(A.ep.weights + nr * RowWide::NX) + lane * 128);
 }
 
 template <int EPI>
 static __global__ void __launch_bounds__(kRowThreads, 2) k_rows_inv_wide(RowArgs A) {
   LMVN_DYN_SMEM(cplx, sm);
-  const int lane = threadIdx.x % 16;
-  const int group = threadIdx.x / 16;
+  const int lane = threadIdx.x % 32;
+  const int group = threadIdx.x / 32;
   cplx* slab = sm + group * RowWide::SLAB;
   const long long rows = (long long)A.nz * A.ny;
   const long long stride = (long long)gridDim.x * RowWide::ROWS;
   for (long long row = (long long)blockIdx.x * RowWide::ROWS + group; row < rows; row += stride) {
-    if (A.prefetch && row + stride < rows) {
-      const long long nr = row + stride;
-      const char* sp = reinterpret_cast<const char*>(A.spec + nr * A.nxp);
-      for (int b = lane * 128; b < A.nxp * int(sizeof(cplx)); b += 16 * 128) prefetch_l2(sp + b);
-      if (EPI != gen::EPI_STORE) {
-        const char* oa = reinterpret_cast<const char*>((EPI == gen::EPI_QUOTIENT ? A.ep.view : A.ep.psi) + nr * RowWide::NX);
-        prefetch_l2(oa + lane * 128);
-        prefetch_l2(oa + 2048 + lane * 128);
-      }
-      if (EPI == gen::EPI_UPDATE) {
-        const char* ob = reinterpret_cast<const char*>(A.ep.weights + nr * RowWide::NX);
-        prefetch_l2(ob + lane * 128);
-        prefetch_l2(ob + 2048 + lane * 128);
-      }
-    }
+    if (A.prefetch && row + stride < rows) rows_wide_prefetch<EPI>(A, row + stride, lane);
     rows_inv_wide_group<EPI>(A, slab, row, lane);
   }
 }
 
-// 128 threads per CTA, three CTAs per SM: 170 registers per thread -- the chained form keeps 32 results of the
-// inverse live through the epilogue and spills at 128
-static const int kChainWideThreads = 128;
-#ifndef LMVN_CHAIN_WIDE_BLOCKS
-#define LMVN_CHAIN_WIDE_BLOCKS 3
-#endif
+// the chained link for nx = 1024: four CTAs of 128 threads per SM like the M <= 256 links
+static const int kChainWideThreads = LMVN_LINK_THREADS;
 template <int EPI>
-static __global__ void __launch_bounds__(kChainWideThreads, LMVN_CHAIN_WIDE_BLOCKS) k_rows_inv_fwd_wide(RowArgs A) {
+static __global__ void __launch_bounds__(kChainWideThreads, LMVN_LINK_BLOCKS) k_rows_inv_fwd_wide(RowArgs A) {
   LMVN_DYN_SMEM(cplx, sm);
-  constexpr int GROUPS = kChainWideThreads / 16;
-  const int lane = threadIdx.x % 16;
-  const int group = threadIdx.x / 16;
+  constexpr int GROUPS = kChainWideThreads / 32;
+  const int lane = threadIdx.x % 32;
+  const int group = threadIdx.x / 32;
   cplx* slab = sm + group * RowWide::SLAB;
   const long long rows = (long long)A.nz * A.ny;
-  const long long stride = (long long)gridDim.x * GROUPS;
-  for (long long row = (long long)blockIdx.x * GROUPS + group; row < rows; row += stride) {
-    if (A.prefetch && row + stride < rows) {
-      const long long nr = row + stride;
-      const char* sp = reinterpret_cast<const char*>(A.spec + nr * A.nxp);
-      for (int b = lane * 128; b < A.nxp * int(sizeof(cplx)); b += 16 * 128) prefetch_l2(sp + b);
-      const char* oa = reinterpret_cast<const char*>((EPI == gen::EPI_QUOTIENT ? A.ep.view : A.ep.psi) + nr * RowWide::NX);
-      prefetch_l2(oa + lane * 128);
-      prefetch_l2(oa + 2048 + lane * 128);
-      if (EPI == gen::EPI_UPDATE) {
-        const char* ob = reinterpret_cast<const char*>(A.ep.weights + nr * RowWide::NX);
-        prefetch_l2(ob + lane * 128);
-        prefetch_l2(ob + 2048 + lane * 128);
-      }
-    }
-    rows_inv_wide_group<EPI, true>(A, slab, row, lane);
-  }
+  // one row per warp and CTA (grid = rows / GROUPS), left to the hardware CTA scheduler like the update link of the
+  // narrower rows: inside a persistent loop the compiler keeps the lane's 31 twiddles in registers across iterations
+  // and the kernel spills
+  const long long row = (long long)blockIdx.x * GROUPS + group;
+  if (row < rows) rows_inv_wide_group<EPI, true>(A, slab, row, lane);
 }
 
 }  // namespace fast

@@ -98,7 +98,7 @@ struct FastEngine : ConvEngine, FastOps {
   const cplx* nyq_of(const cplx* spec) const { return split ? spec + main_elems() : nullptr; }
   size_t work_elems() const override { return khat_elems(); }
   int launches_per_conv() const override { return can_chain() ? 4 : 5; }
-  // nx = 1024: the update link is two launches (rows_inv_fwd below)
+  // nx = 1024 with LMVN_CHAIN_WIDE_UPDATE=0: the update link is two launches (rows_inv_fwd below)
   int launches_per_view_iteration() const override {
     return 2 * launches_per_conv() + ((can_chain() && M == 512 && !chain_wide_update) ? 1 : 0);
   }
@@ -135,7 +135,7 @@ struct FastEngine : ConvEngine, FastOps {
     if (const char* e = getenv("LMVN_TMA")) use_tma = atoi(e);
     if (const char* e = getenv("LMVN_CHAIN")) chain_ok = (*e != '0');
     if (const char* e = getenv("LMVN_CHAIN_WIDE")) chain_wide = (*e != '0');
-    if (const char* e = getenv("LMVN_CHAIN_WIDE_UPDATE")) chain_wide_update = (*e == '1');
+    if (const char* e = getenv("LMVN_CHAIN_WIDE_UPDATE")) chain_wide_update = (*e != '0');
     if (const char* e = getenv("LMVN_ROWS_CTAS")) rows_ctas_per_sm = update_ctas_per_sm = std::max(1, atoi(e));
     {
       std::lock_guard<std::mutex> lk(plan->fast_mu);
@@ -645,9 +645,9 @@ struct FastEngine : ConvEngine, FastOps {
       return -1;
     }
     if (M == 512 && ep.mode == gen::EPI_UPDATE && !spec_out && !chain_wide_update) {
-      // nx = 1024: the chained update link keeps 32 results of the inverse live through a three-operand epilogue (170
-      // registers, 12 warps per SM) and is SLOWER than the two passes it replaces: 6.38 ms against 4.08 + 1.44 ms at 1024^3
-      // (profiles/r02_1024_wide_tiles.log).  The quotient link stays chained (3.08 against 2.81 + 1.48 ms).
+      // A/B (LMVN_CHAIN_WIDE_UPDATE=0): the update link of nx = 1024 as the two passes it fuses.  That was the default while a
+      // 16-lane group held a whole row (170 registers, 6.38 ms chained against 4.08 + 1.44 ms at 1024^3); with one warp per
+      // row the chained kernel fits 128 registers: 3.91 ms against 2.89 + 1.52 ms (profiles/r02_1024_wide_tiles.log).
       LMVN_TRY(rows_inv(spec, ep.psi, ep, s, 0, nzs));
       gen::RealSource src{ep.psi, 0, 0, 0, 0};
       return rows_fwd(src, spec, s, 0, nzs);
@@ -676,8 +676,8 @@ struct FastEngine : ConvEngine, FastOps {
       case 256: LMVN_TRY(launch_rows_inv_fwd<256>(a, s)); break;
       case 512: {
         const size_t rows = size_t(a.nz) * plan->ny;
-        const int groups = fast::kChainWideThreads / 16;
-        const dim3 grid(unsigned(std::min<size_t>(ceil_div(rows, size_t(groups)), size_t(num_sms) * 24)));
+        const int groups = fast::kChainWideThreads / 32;
+        const dim3 grid(unsigned(ceil_div(rows, size_t(groups))));  // one row per warp, no loop in the kernel
         const size_t smem = size_t(groups) * fast::RowWide::SLAB * sizeof(cplx);
         auto k1 = fast::k_rows_inv_fwd_wide<gen::EPI_QUOTIENT>;
         auto k2 = fast::k_rows_inv_fwd_wide<gen::EPI_UPDATE>;
@@ -699,10 +699,9 @@ struct FastEngine : ConvEngine, FastOps {
   }
 
   bool chain_ok = true;
-  // nx = 1024: the chained kernel runs 128-thread CTAs (170 registers per thread: it keeps 32 results live through
-  // the epilogue); +3 % over the two separate passes (LMVN_CHAIN_WIDE=0 for A/B)
+  // nx = 1024: chained links too (one warp per row, 128 registers; LMVN_CHAIN_WIDE=0 / LMVN_CHAIN_WIDE_UPDATE=0 for A/B)
   bool chain_wide = true;
-  bool chain_wide_update = false;  // LMVN_CHAIN_WIDE_UPDATE=1: chain the update link at nx = 1024 too (A/B)
+  bool chain_wide_update = true;
   bool can_chain() const override { return chain_ok && (M <= 256 || chain_wide); }
   int chain_begin(const float* in, cplx* work, cudaStream_t s) override {
     gen::RealSource src{in, 0, 0, 0, 0};
