@@ -121,6 +121,37 @@ __global__ void __launch_bounds__(256, 2) k_zcopy_persistent(float2* data, const
   }
 }
 
+// copies in the access shape of the chained x kernels ("links") of config 3: a 16-lane group handles 2 rows per iteration --
+// spectrum rows (128 complex = 1 KB) in and out in place, real rows (256 floats = 1 KB) of the operands in, psi out.
+// STREAMS = 3: quotient link (spectrum in/out, view in); 5: update link (spectrum in/out, psi in/out, weights in).
+template <int STREAMS>
+__global__ void __launch_bounds__(128, 4) k_link_copy(float2* spec, const float2* __restrict__ opa, const float2* __restrict__ opb,
+                                                      float2* psi, long long rows) {
+  const int lane = threadIdx.x % 16, group = threadIdx.x / 16;
+  for (long long row = ((long long)blockIdx.x * 8 + group) * 2; row < rows; row += (long long)gridDim.x * 16) {
+    float2 v[16], a[16], b[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = __ldcg(spec + (row + r / 8) * 128 + lane + 16 * (r % 8));
+#pragma unroll
+    for (int r = 0; r < 16; ++r) a[r] = __ldcg((STREAMS == 5 ? psi : opa) + (row + r / 8) * 128 + lane + 16 * (r % 8));
+    if (STREAMS == 5) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) b[r] = __ldcg(opb + (row + r / 8) * 128 + lane + 16 * (r % 8));
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      v[r].x = v[r].x * a[r].x + (STREAMS == 5 ? b[r].y : 1.f);
+      v[r].y = v[r].y * 1.0001f + v[(r + 1) & 15].x;  // the whole group of rows before the first store, like a transform
+    }
+    if (STREAMS == 5) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) __stcg(psi + (row + r / 8) * 128 + lane + 16 * (r % 8), v[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) __stcg(spec + (row + r / 8) * 128 + lane + 16 * (r % 8), v[(r + 3) & 15]);
+  }
+}
+
 template <typename F>
 static void time_it(const char* name, double bytes, cudaEvent_t e0, cudaEvent_t e1, F launch) {
   float best = 1e9f;
@@ -180,7 +211,8 @@ int main() {
              bytes / best * 1e-6, cudaGetErrorString(cudaGetLastError()));
     }
   float2* c;
-  cudaMalloc(&c, elems * sizeof(float2));
+  cudaMalloc(&c, 2 * elems * sizeof(float2));
+  cudaMemset(c, 0, 2 * elems * sizeof(float2));
   run_variant<0, 0, 2, true>("K^ ld.cg, st.cg, 2 CTAs/SM, in place (= the z pass)", a, b, c, e0, e1);
   run_variant<1, 0, 2, true>("K^ ld.nc", a, b, c, e0, e1);
   run_variant<2, 0, 2, true>("K^ ld.cs", a, b, c, e0, e1);
@@ -199,6 +231,16 @@ int main() {
           [&] { k_zcopy_persistent<false><<<296, 256>>>(a, b, a, pitch0, 4096); });
   time_it("3C copy, in place, one tile per CTA, loads and stores interleaved", c3, e0, e1,
           [&] { k_zcopy_persistent<false><<<4096, 256>>>(a, b, a, pitch0, 4096); });
+  {
+    const long long rows = 512LL * 512;
+    const double cs = double(rows) * 128 * 8;  // one stream
+    time_it("link-shaped copy, 3 streams (quotient link), persistent 148 x 16 CTAs", 3 * cs, e0, e1,
+            [&] { k_link_copy<3><<<148 * 16, 128>>>(a, b, c, c, rows); });
+    time_it("link-shaped copy, 5 streams (update link), one iteration per CTA", 5 * cs, e0, e1,
+            [&] { k_link_copy<5><<<unsigned(rows / 16), 128>>>(a, b, c, c + rows * 128, rows); });
+    time_it("link-shaped copy, 5 streams (update link), persistent 148 x 16 CTAs", 5 * cs, e0, e1,
+            [&] { k_link_copy<5><<<148 * 16, 128>>>(a, b, c, c + rows * 128, rows); });
+  }
   time_it("2C copy, z-shaped, in place", c2, e0, e1, [&] { k_copy2<false, true><<<512 * 8, 256>>>(a, c, pitch0); });
   time_it("2C copy, z-shaped, out of place", c2, e0, e1, [&] { k_copy2<false, false><<<512 * 8, 256>>>(a, c, pitch0); });
   time_it("2C copy, y-shaped, in place", c2, e0, e1, [&] { k_copy2<true, true><<<512 * 8, 256>>>(a, c, pitch0); });
