@@ -18,7 +18,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from libmultiviewnative_b200 import load  # noqa: E402
 from libmultiviewnative_b200.synthetic import make_views_fast  # noqa: E402
 
-KNOBS = ("LMVN_LINK_REVERSE", "LMVN_PERSIST", "LMVN_OOP_Z", "LMVN_TMA", "LMVN_PREFETCH", "LMVN_X3", "LMVN_GRAPH", "LMVN_PREFETCH_KHAT_AHEAD", "LMVN_PREFETCH_Z", "LMVN_PREFETCH_YINV", "LMVN_PREFETCH_KHAT")
+KNOBS = ("LMVN_LINK_REVERSE", "LMVN_PREFETCH_LINK", "LMVN_PERSIST", "LMVN_OOP_Z", "LMVN_TMA", "LMVN_PREFETCH", "LMVN_X3", "LMVN_GRAPH", "LMVN_PREFETCH_KHAT_AHEAD", "LMVN_PREFETCH_Z", "LMVN_PREFETCH_YINV", "LMVN_PREFETCH_KHAT")
 
 
 def run(lib, d, dims, nv, iters, env, long_iters):
