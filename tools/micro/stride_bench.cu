@@ -152,6 +152,32 @@ __global__ void __launch_bounds__(128, 4) k_link_copy(float2* spec, const float2
   }
 }
 
+// the merged z pass of a 1024-point axis (1024^3: 513 -> 512 columns, plane pitch 1024 x 512): COLS = 16 -> 128 KB tiles, 512
+// threads, one CTA per SM (shipped); COLS = 8 -> 64 KB tiles, 256 threads, two CTAs per SM (half lines).  3C, phased, in place.
+template <int COLS>
+__global__ void __launch_bounds__(COLS * 32, COLS == 16 ? 1 : 2) k_z1024_copy(float2* data, const float2* __restrict__ khat, long long pitch,
+                                                                             int tiles_x) {
+  extern __shared__ float2 dummy[];  // occupies the tile's shared memory so that the residency matches
+  const int c = threadIdx.x % COLS, rg = threadIdx.x / COLS;  // 32 row groups
+  const int tile = blockIdx.x;
+  const long long base = (long long)(tile / tiles_x) * 512 + (tile % tiles_x) * COLS + c;
+  float2 v[32];
+  float2* p = data + base + rg * pitch;
+#pragma unroll
+  for (int r = 0; r < 32; ++r) v[r] = __ldcg(p + (long long)r * 32 * pitch);
+  const float2* k = khat + base + rg * pitch;
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    const float2 w = __ldcg(k + (long long)r * 32 * pitch);
+    v[r].x = v[r].x * w.x - v[r].y * w.y;
+  }
+#pragma unroll
+  for (int r = 0; r < 32; ++r) v[r].y = v[r].y * 1.0001f + v[(r + 1) & 31].x;
+  if (v[0].x == 123.456f) dummy[threadIdx.x] = v[1];
+#pragma unroll
+  for (int r = 0; r < 32; ++r) __stcg(p + (long long)r * 32 * pitch, v[r]);
+}
+
 template <typename F>
 static void time_it(const char* name, double bytes, cudaEvent_t e0, cudaEvent_t e1, F launch) {
   float best = 1e9f;
@@ -240,6 +266,23 @@ int main() {
             [&] { k_link_copy<5><<<unsigned(rows / 16), 128>>>(a, b, c, c + rows * 128, rows); });
     time_it("link-shaped copy, 5 streams (update link), persistent 148 x 16 CTAs", 5 * cs, e0, e1,
             [&] { k_link_copy<5><<<148 * 16, 128>>>(a, b, c, c + rows * 128, rows); });
+  }
+  {
+    // 1024 planes x 256 rows x 512 columns (a quarter of the 1024^3 spectrum: 1 GiB per array)
+    float2 *d1, *k1;
+    const long long pitch1 = 256LL * 512;
+    cudaMalloc(&d1, 1024 * pitch1 * sizeof(float2));
+    cudaMalloc(&k1, 1024 * pitch1 * sizeof(float2));
+    cudaMemset(d1, 0, 1024 * pitch1 * sizeof(float2));
+    cudaMemset(k1, 0, 1024 * pitch1 * sizeof(float2));
+    const double b3 = 3.0 * 1024 * pitch1 * 8;
+    cudaFuncSetAttribute(k_z1024_copy<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    cudaFuncSetAttribute(k_z1024_copy<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    time_it("1024-point z-shaped 3C copy, 128 KB tiles, 512 threads, 1 CTA/SM", b3, e0, e1,
+            [&] { k_z1024_copy<16><<<256 * 32, 512, 128 * 1024>>>(d1, k1, pitch1, 32); });
+    time_it("1024-point z-shaped 3C copy, 64 KB tiles (8 columns), 256 threads, 2 CTAs/SM", b3, e0, e1,
+            [&] { k_z1024_copy<8><<<256 * 64, 256, 64 * 1024>>>(d1, k1, pitch1, 64); });
+    cudaFree(d1); cudaFree(k1);
   }
   time_it("2C copy, z-shaped, in place", c2, e0, e1, [&] { k_copy2<false, true><<<512 * 8, 256>>>(a, c, pitch0); });
   time_it("2C copy, z-shaped, out of place", c2, e0, e1, [&] { k_copy2<false, false><<<512 * 8, 256>>>(a, c, pitch0); });
