@@ -400,7 +400,8 @@ def test_tiff_fixture_directory_through_the_gpu_entry_point(L, tmp_path):
 
 
 # ---- one volume over several ranks (slab-decomposed plans), all ranks on this GPU ------------
-@pytest.mark.parametrize("dims,world", [((64, 64, 64), 2), ((128, 128, 128), 4), ((256, 256, 256), 8), ((1024, 64, 64), 2)])
+@pytest.mark.parametrize("dims,world", [((64, 64, 64), 2), ((128, 128, 128), 4), ((256, 256, 256), 8), ((1024, 64, 64), 2),
+                                        ((64, 64, 1024), 2)])
 def test_slab_group_equals_single_plan(L, dims, world, monkeypatch):
     """parity of the multi-GPU code path against the single-GPU path (256^3 case
     included).  Same butterflies on the same data; the single-GPU loop runs the chained x passes (another
