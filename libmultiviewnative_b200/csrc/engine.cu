@@ -363,6 +363,7 @@ Deconv::~Deconv() {
 static const size_t kMaxKernelVoxels = size_t(1) << 24;
 
 int Deconv::init(const int* d, int nviews, int dev, int strategy) {
+  NvtxRange nvtx_("lmvn::plan_create");
   if (!d || d[0] <= 0 || d[1] <= 0 || d[2] <= 0) {
     set_last_error("invalid image dims");
     return -1;
@@ -828,6 +829,7 @@ int Deconv::download_stack(float* dst_h, const float* src) {
 
 int Deconv::set_view(int v, const float* image_h, const float* weights_h, const float* k1, const int* k1d,
                      const float* k2, const int* k2d) {
+  NvtxRange nvtx_("lmvn::set_view (upload + PSF spectra)");
   if (v < 0 || v >= num_views) {
     set_last_error("view index %d out of range", v);
     return -1;
@@ -860,6 +862,7 @@ int Deconv::set_view(int v, const float* image_h, const float* weights_h, const 
 }
 
 int Deconv::set_psi(const float* psi_h) {
+  NvtxRange nvtx_("lmvn::set_psi (upload)");
   if (!psi_h) {
     set_last_error("psi is null");
     return -1;
@@ -871,6 +874,7 @@ int Deconv::set_psi(const float* psi_h) {
 }
 
 int Deconv::get_psi(float* psi_h) {
+  NvtxRange nvtx_("lmvn::get_psi (download)");
   if (!psi_h) {
     set_last_error("psi is null");
     return -1;
@@ -888,6 +892,7 @@ int Deconv::synchronize() {
 }
 
 int Deconv::iterate(int iterations, double lambda, float min_value, float* device_ms) {
+  NvtxRange nvtx_("lmvn::iterate (RL loop)");
   if (!psi_set) {
     set_last_error("psi has not been set");
     return -1;
@@ -1006,6 +1011,7 @@ int Deconv::iterate(int iterations, double lambda, float min_value, float* devic
 }
 
 int Deconv::convolve_psi(int view, int which, int repeats, float* device_ms) {
+  NvtxRange nvtx_("lmvn::convolve");
   if (view < 0 || view >= num_views || !view_set[view] || !psi_set) {
     set_last_error("convolve: view %d / psi not set", view);
     return -1;

@@ -24,6 +24,26 @@
 #include <cstring>
 #include <string>
 
+// NVTX ranges around the phases of a call (plan, uploads + PSF spectra, loop, download): visible in Nsight Systems and
+// `ncu --nvtx`; header-only NVTX 3, nothing to link, a few nanoseconds when no tool is attached.
+#if !defined(LMVN_EMU) && !defined(LMVN_NO_NVTX)
+#include <nvtx3/nvToolsExt.h>
+namespace lmvn {
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+}  // namespace lmvn
+#else
+namespace lmvn {
+struct NvtxRange {
+  explicit NvtxRange(const char*) {}
+};
+}  // namespace lmvn
+#endif
+
 // Test builds under AddressSanitizer (host emulation, -DLMVN_ARENA_REDZONE): poisoned red zones between the
 // sub-buffers carved out of a device arena, so that index math that strays into a neighbouring buffer is reported.
 #if defined(LMVN_EMU) && defined(LMVN_ARENA_REDZONE)
