@@ -98,6 +98,24 @@ def test_kernels_are_sm100a(lib):
     assert not re.search(r"sm_(?!100a)\d+", out), out
 
 
+@needs_nvcc
+def test_sass_carries_the_blackwell_paths(lib):
+    """what the shipped library is made of, checked on its SASS (no GPU needed): packed FP32x2 arithmetic in the transforms,
+    the tensor-map TMA copies + mbarrier waits of the TMA-fed strided passes (csrc/fft_tma.cuh), the bulk copies of the
+    two-pass schedule (csrc/fft_x3.cuh), and no library FFT / BLAS kernels at all."""
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    import subprocess
+
+    sass = subprocess.run([cuobjdump, "-sass", lib.path], capture_output=True, text=True).stdout
+    for mnemonic in ("FFMA2", "FADD2", "UTMALDG.3D", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "UBLKCP", "LDG.E.64.STRONG.GPU"):
+        assert mnemonic in sass, mnemonic
+    funcs = re.findall(r"Function : (\S+)", sass)
+    assert any("k_strided_tma" in f for f in funcs) and any("k_rows_inv_fwd" in f for f in funcs)
+    assert not any(("cufft" in f.lower()) or ("cublas" in f.lower()) for f in funcs)
+
+
 def _build_c_client(tmp_path):
     import shutil
     import subprocess
